@@ -1,0 +1,142 @@
+/* lrm_c.h — C ABI of the B200-native leg-movability library (liblrm_b200.so).
+ *
+ * This is the drop-in boundary for the reference's host<->CUDA plugin surface.  The reference has
+ * no extern "C" layer: plain-C++ callers (bench.cpp, several_leg.cpp) reach CUDA through the C++
+ * symbols declared in cross_compiled.cuh / one_leg.cu.h / several_leg.cu.h /
+ * several_leg_octree.cu.h.  Each entry point below names the reference interface it replaces;
+ * include/lrm_compat.hpp re-exports the reference's own C++ signatures on top of these.
+ *
+ * Conventions
+ *   - units: millimetres and radians (static_variables.cpp:45-49), all arithmetic FP32.
+ *   - points / vectors are N x 3 float AoS (the layout of the reference's Array<float3>).
+ *   - flags are one byte per element, 0 or 1 (the layout of Array<bool>).
+ *   - quat is the body orientation in the reference's storage (settings.h:51 quatTest,
+ *     unified_math_cuda.cu.h:13-27): {1,0,0,0} is the identity.  NULL means identity.
+ *   - on_device != 0: all data pointers are device pointers on the current device, the call is
+ *     asynchronous on `stream` unless kernel_ms is requested (then it synchronises the stream).
+ *     on_device == 0: pointers are host pointers; the library stages through device memory
+ *     (alloc, H2D, kernel, D2H, free — the contract of apply_kernel, cross_compiled.cu:34-79).
+ *   - kernel_ms (may be NULL) receives the cudaEvent time of the kernel(s) only — the number the
+ *     reference's apply_kernel returns (cross_compiled.cu:58-65).
+ *   - return value: 0 on success, negative lrm_status otherwise; lrm_last_error() gives the text.
+ *     No entry point ever computes on the CPU: without a usable CUDA device every compute call
+ *     fails with LRM_ERR_CUDA.
+ */
+#ifndef LRM_C_H
+#define LRM_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRM_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define LRM_API __attribute__((visibility("default")))
+#else
+#define LRM_API
+#endif
+
+typedef enum {
+    LRM_OK = 0,
+    LRM_ERR_INVALID = -1, /* bad argument (NULL pointer, misaligned buffer, bad count) */
+    LRM_ERR_CUDA = -2,    /* CUDA runtime error, text in lrm_last_error() */
+    LRM_ERR_UNSUPPORTED = -3
+} lrm_status;
+
+/* Field-for-field the reference's LegDimensions (HeaderCPP.h:19-52): 14 floats, 56 bytes. */
+typedef struct lrm_leg {
+    float body_angle;
+    float body;
+    float coxa_pitch;
+    float coxa_length;
+    float tibia_length;
+    float femur_length;
+    float tibia_absolute_pos;
+    float tibia_absolute_neg;
+    float max_angle_coxa;
+    float min_angle_coxa;
+    float max_angle_tibia;
+    float min_angle_tibia;
+    float max_angle_femur;
+    float min_angle_femur;
+} lrm_leg_t;
+
+/* ---- library / device ------------------------------------------------------------------- */
+LRM_API int lrm_abi_version(void);
+LRM_API const char* lrm_last_error(void);
+LRM_API int lrm_device_count(void);
+LRM_API int lrm_set_device(int device);
+
+/* Default legs of the reference: robot 0 = get_moonbot_leg, 1 = get_M2_leg
+ * (static_variables.cpp:44-93).  Pure host arithmetic. */
+LRM_API int lrm_default_leg(int robot, float azimuth, lrm_leg_t* out);
+
+/* ---- one-leg hot path -------------------------------------------------------------------- */
+/* Replaces apply_kernel(points, dim, reachability_global_kernel, out)
+ * (cross_compiled.cuh:4-7, one_leg_global.cu:149-156; one_leg.cu:343-357 when quat is identity). */
+LRM_API int lrm_reach(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, uint8_t* flags,
+              int on_device, void* stream, float* kernel_ms);
+
+/* Replaces apply_kernel(points, dim, distance_global_kernel, out)
+ * (one_leg_global.cu:157-166; one_leg.cu:359-375).  out_xyz[i] = d(p_i) with p_i - d(p_i) on the
+ * reachability edge.  flags (may be NULL) receives distance_global's bool. */
+LRM_API int lrm_dist(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, float* out_xyz,
+             uint8_t* flags, int on_device, void* stream, float* kernel_ms);
+
+/* Both results in one pass over the points (25 B/point of HBM traffic instead of 13 + 24):
+ * reach_flags[i] == reachability_global(p_i), out_xyz[i] == distance_global's vector. */
+LRM_API int lrm_reach_dist(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat,
+                   uint8_t* reach_flags, float* out_xyz, int on_device, void* stream,
+                   float* kernel_ms);
+
+/* SoA twins: x, y, z planes in / dx, dy, dz planes out (the layout of the reference's on-disk
+ * protocol dist_input_t{x,y,z}.bin -> out_dist_x{x,y,z}.bin, several_leg.cpp:126-221).
+ * Any output pointer may be NULL to skip that result.  Device pointers only. */
+LRM_API int lrm_reach_dist_soa(const float* x, const float* y, const float* z, size_t n,
+                       const lrm_leg_t* leg, const float* quat, uint8_t* reach_flags, float* dx,
+                       float* dy, float* dz, void* stream, float* kernel_ms);
+
+/* Forward kinematics (coxa, femur, tibia) -> xyz, replaces forward_kine_kernel
+ * (one_leg.cu:377-414; like the reference it ignores coxa_pitch). */
+LRM_API int lrm_forward_kine(const float* angles, size_t n, const lrm_leg_t* leg, float* out_xyz,
+                     int on_device, void* stream, float* kernel_ms);
+
+/* ---- benchmark support ------------------------------------------------------------------- */
+/* Regular lattice written straight into device memory, x-major / z-fastest like
+ * generate3DGrid (bench.cpp:30-50): point i -> (ix, iy, iz) = (i / (ny*nz), (i / nz) % ny, i % nz),
+ * coordinate = lo + (float)index * step, evaluated with separately rounded multiply and add so
+ * that a host loop doing the same two float operations is bit-identical.
+ * Writes points [first, first + count) to out_xyz (device, AoS). */
+LRM_API int lrm_make_lattice(float* out_xyz, const float lo[3], const float step[3], const uint32_t dims[3],
+                     size_t first, size_t count, void* stream);
+
+/* ---- multi-leg body positionability ------------------------------------------------------ */
+typedef struct lrm_posit_opts {
+    int pre_cull;        /* apply the constructor culls of multi_rot_estimator
+                            (several_leg.cu:371-374): 60 mm colliding sphere, 400 mm far body,
+                            400 mm far target.  robot_full_struct always does. */
+    int first_hit_only;  /* reserved, must be 0 */
+} lrm_posit_opts_t;
+
+/* Orientation set of robot_full_struct (several_leg.cu:811-857): writes 45 quaternions. */
+LRM_API int lrm_full_struct_orientations(float* out_quat4, int capacity);
+
+/* Replaces robot_full_struct's pipeline (several_leg.cu:326-877) with a per-pose result instead
+ * of a compacted list: standable[b] = 1 + index of the first orientation in `quats` for which the
+ * body position bodies[b] passes the cull cylinders and EVERY leg reaches at least one map point
+ * (reachable_rotate_leg, several_leg.cu:48-67); 0 if none.  The reference hard-codes 4 legs
+ * (several_leg.cu:681-697); nlegs is free here (hexapod = 6).
+ * bodies: nb x 3, map: nt x 3 (device pointers when on_device). */
+LRM_API int lrm_positionability(const float* bodies, size_t nb, const float* map, size_t nt,
+                        const lrm_leg_t* legs, int nlegs, const float* quats, int nq,
+                        const lrm_posit_opts_t* opts, uint8_t* standable, int on_device,
+                        void* stream, float* kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRM_C_H */

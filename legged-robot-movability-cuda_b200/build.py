@@ -1,0 +1,51 @@
+"""Build liblrm_b200.so (hand-written sm_100a CUDA + the C ABI of include/lrm_c.h) in-tree.
+
+    python legged-robot-movability-cuda_b200/build.py [--force] [--verbose]
+
+nvcc cross-compiles for sm_100a without a GPU.  The .so is git-ignored but travels with the tree
+to the GPU box.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "liblrm_b200.so")
+SOURCES = ["leg_plan.cpp", "one_leg_kernels.cu", "positionability.cu", "lrm_api.cu"]
+HEADERS = ["leg_plan.h", "leg_math.cuh", "bulk_copy.cuh", "kernels.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-std=c++17", "-O3", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "--expt-relaxed-constexpr",
+    "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
+]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps += [os.path.join(ROOT, "include", "lrm_c.h"), os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB]
+    cmd += ["-x", "cu"] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-lcudart"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

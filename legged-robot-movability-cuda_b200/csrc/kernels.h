@@ -1,0 +1,43 @@
+// kernels.h — launchers shared between the kernel translation units and the C ABI (lrm_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "leg_plan.h"
+
+namespace lrm {
+
+enum : int { kModeReach = 1, kModeDist = 2, kModeBoth = 3 };
+
+// One-leg sweep over N x 3 AoS points already on the device.  mode: kModeReach -> flag only,
+// kModeDist -> vector (+ distance_global's bool if flag != nullptr), kModeBoth -> vector +
+// reachability flag.
+cudaError_t launch_one_leg_aos(int mode, const LegPlan& plan, const float* xyz, float* out_vec,
+                               uint8_t* flag, size_t n, cudaStream_t stream);
+// SoA planes; dx == nullptr selects reach-only.
+cudaError_t launch_one_leg_soa(const LegPlan& plan, const float* x, const float* y, const float* z,
+                               float* dx, float* dy, float* dz, uint8_t* flag, size_t n,
+                               cudaStream_t stream);
+cudaError_t launch_forward_kine(const float* angles, const lrm_leg_t& leg, float* out, size_t n,
+                                cudaStream_t stream);
+cudaError_t launch_lattice(float* out, const float lo[3], const float step[3],
+                           const uint32_t dims[3], size_t first, size_t count,
+                           cudaStream_t stream);
+
+// Multi-leg positionability (positionability.cu).  All pointers are device pointers.
+struct PositParams {
+    const float* bodies;   // nb x 3
+    size_t nb;
+    const float* map;      // nt x 3
+    size_t nt;
+    const lrm_leg_t* legs; // host
+    int nlegs;
+    const float* quats;    // host, nq x 4
+    int nq;
+    int pre_cull;
+    uint8_t* standable;    // nb
+};
+cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float* kernel_ms);
+
+}  // namespace lrm

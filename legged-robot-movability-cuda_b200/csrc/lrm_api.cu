@@ -1,0 +1,308 @@
+// lrm_api.cu — the extern "C" layer declared in include/lrm_c.h.
+//
+// Host-pointer calls follow the contract of the reference's apply_kernel
+// (cross_compiled.cu:34-79): allocate device buffers, H2D, event-timed kernel, D2H, free — the
+// returned kernel_ms is the kernel alone.  Device-pointer calls are asynchronous on the caller's
+// stream.  There is no CPU fallback anywhere in this file: every compute entry point either runs
+// the CUDA kernels or fails with LRM_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "kernels.h"
+#include "leg_plan.h"
+#include "lrm_c.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(lrm_status code, const std::string& msg) {
+    g_error = msg;
+    return (int)code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_error = std::string(where) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();  // clear the sticky-free error state
+    return (int)LRM_ERR_CUDA;
+}
+#define LRM_CUDA(call, where)                            \
+    do {                                                 \
+        cudaError_t e_ = (call);                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, where); \
+    } while (0)
+
+// Frees device scratch on every exit path of a host-pointer call.
+struct DeviceScratch {
+    void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+    int n = 0;
+    cudaError_t alloc(void** out, size_t bytes) {
+        cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+        if (e == cudaSuccess) ptr[n++] = *out;
+        return e;
+    }
+    ~DeviceScratch() {
+        for (int i = 0; i < n; i++) cudaFree(ptr[i]);
+    }
+};
+
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool on = false;
+    cudaError_t start(cudaStream_t s, bool want) {
+        on = want;
+        if (!on) return cudaSuccess;
+        cudaError_t e = cudaEventCreate(&a);
+        if (e != cudaSuccess) return e;
+        e = cudaEventCreate(&b);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(a, s);
+    }
+    cudaError_t stop(cudaStream_t s, float* ms) {
+        if (!on) return cudaSuccess;
+        cudaError_t e = cudaEventRecord(b, s);
+        if (e != cudaSuccess) return e;
+        e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) return e;
+        return cudaEventElapsedTime(ms, a, b);
+    }
+    ~EventPair() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
+// Shared body of lrm_reach / lrm_dist / lrm_reach_dist.
+int one_leg_call(int mode, const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat,
+                 float* out_xyz, uint8_t* flags, int on_device, void* stream_v, float* kernel_ms) {
+    if (!leg) return fail(LRM_ERR_INVALID, "leg is NULL");
+    if (n && !xyz) return fail(LRM_ERR_INVALID, "xyz is NULL");
+    if (n && (mode & lrm::kModeDist) && !out_xyz) return fail(LRM_ERR_INVALID, "out_xyz is NULL");
+    if (n && mode == lrm::kModeReach && !flags) return fail(LRM_ERR_INVALID, "flags is NULL");
+    if (n && mode == lrm::kModeBoth && !flags) return fail(LRM_ERR_INVALID, "reach_flags is NULL");
+    if (kernel_ms) *kernel_ms = 0.f;
+
+    lrm::LegPlan plan;
+    lrm::build_leg_plan(*leg, quat, &plan);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+
+    if (on_device) {
+        EventPair ev;
+        LRM_CUDA(ev.start(stream, kernel_ms != nullptr), "cudaEventRecord");
+        LRM_CUDA(lrm::launch_one_leg_aos(mode, plan, xyz, out_xyz, flags, n, stream),
+                 "one-leg kernel launch");
+        LRM_CUDA(ev.stop(stream, kernel_ms), "one-leg kernel");
+        return LRM_OK;
+    }
+
+    // host pointers: apply_kernel's malloc / H2D / kernel / D2H / free
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0)
+        return cuda_fail(ce != cudaSuccess ? ce : cudaErrorNoDevice,
+                         "no CUDA device (this library has no CPU path)");
+    DeviceScratch scratch;
+    float *d_in = nullptr, *d_vec = nullptr;
+    uint8_t* d_flag = nullptr;
+    LRM_CUDA(scratch.alloc((void**)&d_in, n * 12), "cudaMalloc input");
+    if (mode & lrm::kModeDist) LRM_CUDA(scratch.alloc((void**)&d_vec, n * 12), "cudaMalloc vectors");
+    if (flags) LRM_CUDA(scratch.alloc((void**)&d_flag, n), "cudaMalloc flags");
+    LRM_CUDA(cudaMemcpyAsync(d_in, xyz, n * 12, cudaMemcpyHostToDevice, stream), "H2D points");
+    {
+        EventPair ev;
+        LRM_CUDA(ev.start(stream, kernel_ms != nullptr), "cudaEventRecord");
+        LRM_CUDA(lrm::launch_one_leg_aos(mode, plan, d_in, d_vec, d_flag, n, stream),
+                 "one-leg kernel launch");
+        LRM_CUDA(ev.stop(stream, kernel_ms), "one-leg kernel");
+    }
+    if (d_vec)
+        LRM_CUDA(cudaMemcpyAsync(out_xyz, d_vec, n * 12, cudaMemcpyDeviceToHost, stream),
+                 "D2H vectors");
+    if (d_flag)
+        LRM_CUDA(cudaMemcpyAsync(flags, d_flag, n, cudaMemcpyDeviceToHost, stream), "D2H flags");
+    LRM_CUDA(cudaStreamSynchronize(stream), "stream synchronize");
+    return LRM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lrm_abi_version(void) { return LRM_ABI_VERSION; }
+const char* lrm_last_error(void) { return g_error.c_str(); }
+
+int lrm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int lrm_set_device(int device) {
+    LRM_CUDA(cudaSetDevice(device), "cudaSetDevice");
+    return LRM_OK;
+}
+
+int lrm_default_leg(int robot, float azimuth, lrm_leg_t* out) {
+    if (!out) return fail(LRM_ERR_INVALID, "out is NULL");
+    if (robot != 0 && robot != 1) return fail(LRM_ERR_INVALID, "robot must be 0 (moonbot) or 1 (M2)");
+    lrm::default_leg(robot, azimuth, out);
+    return LRM_OK;
+}
+
+int lrm_reach(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, uint8_t* flags,
+              int on_device, void* stream, float* kernel_ms) {
+    return one_leg_call(lrm::kModeReach, xyz, n, leg, quat, nullptr, flags, on_device, stream,
+                        kernel_ms);
+}
+int lrm_dist(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, float* out_xyz,
+             uint8_t* flags, int on_device, void* stream, float* kernel_ms) {
+    return one_leg_call(lrm::kModeDist, xyz, n, leg, quat, out_xyz, flags, on_device, stream,
+                        kernel_ms);
+}
+int lrm_reach_dist(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat,
+                   uint8_t* reach_flags, float* out_xyz, int on_device, void* stream,
+                   float* kernel_ms) {
+    return one_leg_call(lrm::kModeBoth, xyz, n, leg, quat, out_xyz, reach_flags, on_device, stream,
+                        kernel_ms);
+}
+
+int lrm_reach_dist_soa(const float* x, const float* y, const float* z, size_t n,
+                       const lrm_leg_t* leg, const float* quat, uint8_t* reach_flags, float* dx,
+                       float* dy, float* dz, void* stream_v, float* kernel_ms) {
+    if (!leg) return fail(LRM_ERR_INVALID, "leg is NULL");
+    if (n && (!x || !y || !z)) return fail(LRM_ERR_INVALID, "input plane is NULL");
+    const bool want_vec = dx || dy || dz;
+    if (want_vec && !(dx && dy && dz))
+        return fail(LRM_ERR_INVALID, "dx, dy, dz must be all set or all NULL");
+    if (n && !want_vec && !reach_flags) return fail(LRM_ERR_INVALID, "no output requested");
+    if (kernel_ms) *kernel_ms = 0.f;
+    lrm::LegPlan plan;
+    lrm::build_leg_plan(*leg, quat, &plan);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    EventPair ev;
+    LRM_CUDA(ev.start(stream, kernel_ms != nullptr), "cudaEventRecord");
+    LRM_CUDA(lrm::launch_one_leg_soa(plan, x, y, z, dx, dy, dz, reach_flags, n, stream),
+             "one-leg SoA kernel launch (planes must be 16-byte aligned)");
+    LRM_CUDA(ev.stop(stream, kernel_ms), "one-leg SoA kernel");
+    return LRM_OK;
+}
+
+int lrm_forward_kine(const float* angles, size_t n, const lrm_leg_t* leg, float* out_xyz,
+                     int on_device, void* stream_v, float* kernel_ms) {
+    if (!leg) return fail(LRM_ERR_INVALID, "leg is NULL");
+    if (n && (!angles || !out_xyz)) return fail(LRM_ERR_INVALID, "NULL buffer");
+    if (kernel_ms) *kernel_ms = 0.f;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    DeviceScratch scratch;
+    const float* d_in = angles;
+    float* d_out = out_xyz;
+    if (!on_device) {
+        float* tmp = nullptr;
+        LRM_CUDA(scratch.alloc((void**)&tmp, n * 12), "cudaMalloc angles");
+        LRM_CUDA(scratch.alloc((void**)&d_out, n * 12), "cudaMalloc xyz");
+        LRM_CUDA(cudaMemcpyAsync(tmp, angles, n * 12, cudaMemcpyHostToDevice, stream), "H2D angles");
+        d_in = tmp;
+    }
+    {
+        EventPair ev;
+        LRM_CUDA(ev.start(stream, kernel_ms != nullptr), "cudaEventRecord");
+        LRM_CUDA(lrm::launch_forward_kine(d_in, *leg, d_out, n, stream), "forward-kine launch");
+        LRM_CUDA(ev.stop(stream, kernel_ms), "forward-kine kernel");
+    }
+    if (!on_device) {
+        LRM_CUDA(cudaMemcpyAsync(out_xyz, d_out, n * 12, cudaMemcpyDeviceToHost, stream), "D2H xyz");
+        LRM_CUDA(cudaStreamSynchronize(stream), "stream synchronize");
+    }
+    return LRM_OK;
+}
+
+int lrm_make_lattice(float* out_xyz, const float lo[3], const float step[3], const uint32_t dims[3],
+                     size_t first, size_t count, void* stream) {
+    if (!lo || !step || !dims) return fail(LRM_ERR_INVALID, "NULL lattice description");
+    if (count && !out_xyz) return fail(LRM_ERR_INVALID, "out_xyz is NULL");
+    const size_t total = (size_t)dims[0] * dims[1] * dims[2];
+    if (dims[0] == 0 || dims[1] == 0 || dims[2] == 0 || first + count > total)
+        return fail(LRM_ERR_INVALID, "lattice range out of bounds");
+    LRM_CUDA(lrm::launch_lattice(out_xyz, lo, step, dims, first, count,
+                                 static_cast<cudaStream_t>(stream)),
+             "lattice kernel launch");
+    return LRM_OK;
+}
+
+int lrm_full_struct_orientations(float* out, int capacity) {
+    // several_leg.cu:811-857
+    if (!out || capacity < 45) return fail(LRM_ERR_INVALID, "need room for 45 quaternions");
+    const float pi = 3.14159265358979323846264338327950288419716939937510582097f;
+    const float ax[3] = {1, 0, 0}, ay[3] = {0, 1, 0}, az[3] = {0, 0, 1};
+    float q_init[4], tmp[4], q_roll[4], q_pitch[4], q_yaw[4];
+    lrm::quat_from_vect_angle(az, 0.f, q_init);
+    const float r_min = -pi / 8, r_max = pi / 8, p_min = -pi / 8, p_max = +pi / 8;
+    const float y_min = 0, y_max = pi / 2;
+    int k = 0;
+    for (int i = 0; i <= 2; i++) {
+        const float roll = r_min + (r_max - r_min) * ((float)i / 2.f);
+        lrm::quat_from_vect_angle(ax, roll, tmp);
+        lrm::quat_multiply(tmp, q_init, q_roll);
+        for (int j = 0; j <= 2; j++) {
+            const float pitch = p_min + (p_max - p_min) * ((float)j / 2.f);
+            lrm::quat_from_vect_angle(ay, pitch, tmp);
+            lrm::quat_multiply(tmp, q_roll, q_pitch);
+            for (int m = 0; m <= 4; m++) {
+                const float yaw = y_min + (y_max - y_min) * ((float)m / 4.f);
+                lrm::quat_from_vect_angle(az, yaw, tmp);
+                lrm::quat_multiply(tmp, q_pitch, q_yaw);
+                std::memcpy(out + 4 * k, q_yaw, sizeof q_yaw);
+                k++;
+            }
+        }
+    }
+    return LRM_OK;
+}
+
+int lrm_positionability(const float* bodies, size_t nb, const float* map, size_t nt,
+                        const lrm_leg_t* legs, int nlegs, const float* quats, int nq,
+                        const lrm_posit_opts_t* opts, uint8_t* standable, int on_device,
+                        void* stream_v, float* kernel_ms) {
+    if (!legs || nlegs <= 0 || nlegs > 8) return fail(LRM_ERR_INVALID, "1..8 legs required");
+    if (!quats || nq <= 0 || nq > 254) return fail(LRM_ERR_INVALID, "1..254 orientations required");
+    if (nb && (!bodies || !standable)) return fail(LRM_ERR_INVALID, "NULL body buffer");
+    if (nt && !map) return fail(LRM_ERR_INVALID, "map is NULL");
+    if (opts && opts->first_hit_only) return fail(LRM_ERR_INVALID, "first_hit_only must be 0");
+    if (kernel_ms) *kernel_ms = 0.f;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+
+    lrm::PositParams p;
+    p.nb = nb, p.nt = nt, p.legs = legs, p.nlegs = nlegs, p.quats = quats, p.nq = nq;
+    p.pre_cull = opts ? opts->pre_cull : 0;
+    DeviceScratch scratch;
+    if (on_device) {
+        p.bodies = bodies, p.map = map, p.standable = standable;
+    } else {
+        int count = 0;
+        cudaError_t ce = cudaGetDeviceCount(&count);
+        if (ce != cudaSuccess || count == 0)
+            return cuda_fail(ce != cudaSuccess ? ce : cudaErrorNoDevice,
+                             "no CUDA device (this library has no CPU path)");
+        float *d_b = nullptr, *d_m = nullptr;
+        uint8_t* d_s = nullptr;
+        LRM_CUDA(scratch.alloc((void**)&d_b, nb * 12), "cudaMalloc bodies");
+        LRM_CUDA(scratch.alloc((void**)&d_m, nt * 12), "cudaMalloc map");
+        LRM_CUDA(scratch.alloc((void**)&d_s, nb), "cudaMalloc result");
+        LRM_CUDA(cudaMemcpyAsync(d_b, bodies, nb * 12, cudaMemcpyHostToDevice, stream), "H2D bodies");
+        LRM_CUDA(cudaMemcpyAsync(d_m, map, nt * 12, cudaMemcpyHostToDevice, stream), "H2D map");
+        p.bodies = d_b, p.map = d_m, p.standable = d_s;
+    }
+    LRM_CUDA(lrm::run_positionability(p, stream, kernel_ms), "positionability");
+    if (!on_device) {
+        LRM_CUDA(cudaMemcpyAsync(standable, p.standable, nb, cudaMemcpyDeviceToHost, stream),
+                 "D2H result");
+        LRM_CUDA(cudaStreamSynchronize(stream), "stream synchronize");
+    }
+    return LRM_OK;
+}
+
+}  // extern "C"

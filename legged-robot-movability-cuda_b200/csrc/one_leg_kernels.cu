@@ -1,0 +1,335 @@
+// one_leg_kernels.cu — streaming kernels of the one-leg sweep (reach / distance / both).
+//
+// Replaces reachability_global_kernel, distance_global_kernel, reachability_circles_kernel,
+// distance_circles_kernel (one_leg_global.cu:149-166, one_leg.cu:343-375): one thread per point,
+// <<<ceil(N/256),256>>>, AoS float3 LDG/STG with 12-byte stride and a Circle[14] stack frame.
+//
+// Here: a persistent grid (a few CTAs per SM) walks the point array in tiles.  Tiles are staged
+// global -> shared by the bulk-copy engine (cp.async.bulk, mbarrier completion, kStages deep),
+// threads read their points from shared memory with conflict-free strides, keep every
+// intermediate in registers, write results back to shared memory and one thread per CTA sends
+// the tile to global memory with a bulk store.  Algorithmic HBM traffic: 12 B in + 1 B (flag)
+// and/or 12 B (vector) out per point — each byte crosses HBM exactly once.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bulk_copy.cuh"
+#include "kernels.h"
+#include "leg_math.cuh"
+
+namespace lrm {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTile = 1024;  // points per tile (multiple of 16 keeps every bulk copy 16-B sized)
+constexpr int kStages = 2;
+static_assert(kTile % kThreads == 0 && kTile % 16 == 0, "tile shape");
+
+template <int MODE>
+struct alignas(128) StreamSmem {
+    float in[kStages][3 * kTile];
+    float vec[(MODE & kModeDist) ? 2 : 1][(MODE & kModeDist) ? 3 * kTile : 4];
+    uint8_t flag[2][kTile];
+    alignas(16) SectorTable table;
+    alignas(8) uint64_t full[kStages];
+};
+
+template <int MODE, bool SOA>
+__device__ __forceinline__ void compute_point(const LegPlan& L, const SectorTable& tab,
+                                              const float* in, float* vec, uint8_t* flag, int i,
+                                              int stride_pts) {
+    float x, y, z;
+    if (SOA) {
+        x = in[i], y = in[stride_pts + i], z = in[2 * stride_pts + i];
+    } else {
+        x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];  // word stride 3: conflict-free
+    }
+    const CoxaPoint p = to_coxa_frame(L, x, y, z);
+    if (MODE == kModeReach) {
+        flag[i] = reach_coxa_frame(L, tab, p) ? 1 : 0;
+    } else {
+        const DistResult r = dist_coxa_frame(L, tab, p);
+        if (SOA) {
+            vec[i] = r.dx, vec[stride_pts + i] = r.dy, vec[2 * stride_pts + i] = r.dz;
+        } else {
+            vec[3 * i] = r.dx, vec[3 * i + 1] = r.dy, vec[3 * i + 2] = r.dz;
+        }
+        // MODE dist: distance_global's bool; MODE both: reachability_global's bool
+        flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
+    }
+}
+
+// AoS: in_x = xyz (N x 3), out_x = vectors (N x 3).  SoA: separate planes.
+template <int MODE, bool SOA>
+__global__ void __launch_bounds__(kThreads)
+    one_leg_stream_kernel(const __grid_constant__ LegPlan L, const float* __restrict__ in_x,
+                          const float* __restrict__ in_y, const float* __restrict__ in_z,
+                          float* __restrict__ out_x, float* __restrict__ out_y,
+                          float* __restrict__ out_z, uint8_t* __restrict__ out_flag, size_t n) {
+    extern __shared__ unsigned char smem_raw[];
+    auto& S = *reinterpret_cast<StreamSmem<MODE>*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const int tid = threadIdx.x;
+
+    const size_t n_bulk = n & ~size_t(15);  // points that move through the bulk engine
+    const size_t n_tiles = (n_bulk + kTile - 1) / kTile;
+    constexpr bool kVec = (MODE & kModeDist) != 0;
+
+    fill_sector_table(L, &S.table, tid, kThreads);
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) bulk::mbar_init(&S.full[s], 1);
+        bulk::fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto tile_count = [&](size_t tile) -> uint32_t {
+        const size_t first = tile * kTile;
+        return (uint32_t)((n_bulk - first < (size_t)kTile) ? (n_bulk - first) : kTile);
+    };
+    auto issue_load = [&](size_t tile, int stage) {
+        const uint32_t cnt = tile_count(tile);
+        const size_t first = tile * kTile;
+        if (SOA) {
+            bulk::mbar_expect_tx(&S.full[stage], 3 * cnt * 4);
+            bulk::load(&S.in[stage][0], in_x + first, cnt * 4, &S.full[stage]);
+            bulk::load(&S.in[stage][kTile], in_y + first, cnt * 4, &S.full[stage]);
+            bulk::load(&S.in[stage][2 * kTile], in_z + first, cnt * 4, &S.full[stage]);
+        } else {
+            bulk::mbar_expect_tx(&S.full[stage], cnt * 12);
+            bulk::load(&S.in[stage][0], in_x + 3 * first, cnt * 12, &S.full[stage]);
+        }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) {
+            const size_t tile = (size_t)blockIdx.x + (size_t)s * gridDim.x;
+            if (tile < n_tiles) issue_load(tile, s);
+        }
+    }
+
+    uint32_t it = 0;
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int stage = it % kStages;
+        const int ob = it & 1;
+        const uint32_t cnt = tile_count(tile);
+        bulk::mbar_wait(&S.full[stage], (it / kStages) & 1);
+
+        const float* in = S.in[stage];
+        float* vec = S.vec[kVec ? ob : 0];
+        uint8_t* flag = S.flag[ob];
+#pragma unroll 1
+        for (int i = tid; i < (int)cnt; i += kThreads)
+            compute_point<MODE, SOA>(L, S.table, in, vec, flag, i, kTile);
+
+        bulk::fence_proxy_async();  // results written through the generic proxy -> bulk engine
+        if (tid == 0) bulk::wait_group_read<0>();  // previous tile's store has drained its buffer
+        __syncthreads();
+        if (tid == 0) {
+            const size_t first = tile * kTile;
+            if (kVec) {
+                if (SOA) {
+                    bulk::store(out_x + first, vec, cnt * 4);
+                    bulk::store(out_y + first, vec + kTile, cnt * 4);
+                    bulk::store(out_z + first, vec + 2 * kTile, cnt * 4);
+                } else {
+                    bulk::store(out_x + 3 * first, vec, cnt * 12);
+                }
+            }
+            if (out_flag) bulk::store(out_flag + first, flag, cnt);
+            bulk::commit_group();
+            const size_t next = tile + (size_t)kStages * gridDim.x;
+            if (next < n_tiles) issue_load(next, stage);
+        }
+    }
+    if (tid == 0) bulk::wait_group<0>();
+
+    // the last n % 16 points bypass the bulk engine (sizes must be multiples of 16 B)
+    if (blockIdx.x == 0) {
+        const size_t i = n_bulk + tid;
+        if (i < n) {
+            float xyz[3], v[3];
+            uint8_t f;
+            if (SOA) {
+                xyz[0] = in_x[i], xyz[1] = in_y[i], xyz[2] = in_z[i];
+            } else {
+                xyz[0] = in_x[3 * i], xyz[1] = in_x[3 * i + 1], xyz[2] = in_x[3 * i + 2];
+            }
+            compute_point<MODE, false>(L, S.table, xyz, v, &f, 0, 0);
+            if (kVec) {
+                if (SOA) {
+                    out_x[i] = v[0], out_y[i] = v[1], out_z[i] = v[2];
+                } else {
+                    out_x[3 * i] = v[0], out_x[3 * i + 1] = v[1], out_x[3 * i + 2] = v[2];
+                }
+            }
+            if (out_flag) out_flag[i] = f;
+        }
+    }
+}
+
+// Same math with plain per-thread global accesses: used when a caller's buffers are not 16-byte
+// aligned (the bulk engine's requirement) — still the GPU path, just without staging.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+    one_leg_plain_kernel(const __grid_constant__ LegPlan L, const float* __restrict__ xyz,
+                         float* __restrict__ out_vec, uint8_t* __restrict__ out_flag, size_t n) {
+    __shared__ SectorTable table;
+    fill_sector_table(L, &table, threadIdx.x, kThreads);
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        float p[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        float v[3];
+        uint8_t f;
+        compute_point<MODE, false>(L, table, p, v, &f, 0, 0);
+        if (MODE & kModeDist) {
+            out_vec[3 * i] = v[0], out_vec[3 * i + 1] = v[1], out_vec[3 * i + 2] = v[2];
+        }
+        if (out_flag) out_flag[i] = f;
+    }
+}
+
+// forward_kine_kernel, one_leg.cu:377-414 (coxa_pitch is ignored there too)
+__global__ void forward_kine_kernel_b200(const float* __restrict__ angles, lrm_leg_t leg,
+                                         float* __restrict__ out, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float coxa = angles[3 * i], femur = angles[3 * i + 1], tibia = angles[3 * i + 2];
+        float sh, ch, s, c;
+        sincosf(coxa, &sh, &ch);
+        float x = leg.body + ch * leg.coxa_length, y = sh * leg.coxa_length, z = 0.f;
+        sincosf(femur, &s, &c);
+        float horiz = c * leg.femur_length, vert = s * leg.femur_length;
+        x += ch * horiz, y += sh * horiz, z += vert;
+        sincosf(tibia + femur, &s, &c);
+        horiz = c * leg.tibia_length, vert = s * leg.tibia_length;
+        x += ch * horiz, y += sh * horiz, z += vert;
+        out[3 * i] = x, out[3 * i + 1] = y, out[3 * i + 2] = z;
+    }
+}
+
+// generate3DGrid (bench.cpp:30-50) on the device: x-major, z fastest
+__global__ void lattice_kernel(float* __restrict__ out, float3 lo, float3 step, uint32_t ny,
+                               uint32_t nz, size_t first, size_t count) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+        const size_t i = first + k;
+        const uint32_t iz = (uint32_t)(i % nz);
+        const size_t t = i / nz;
+        const uint32_t iy = (uint32_t)(t % ny);
+        const uint32_t ix = (uint32_t)(t / ny);
+        // separately rounded multiply and add: a host loop with the same two operations matches
+        out[3 * k] = __fadd_rn(lo.x, __fmul_rn((float)ix, step.x));
+        out[3 * k + 1] = __fadd_rn(lo.y, __fmul_rn((float)iy, step.y));
+        out[3 * k + 2] = __fadd_rn(lo.z, __fmul_rn((float)iz, step.z));
+    }
+}
+
+int g_sm_count = 0;
+int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+template <int MODE, bool SOA>
+cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy, const float* iz,
+                          float* ox, float* oy, float* oz, uint8_t* flag, size_t n,
+                          cudaStream_t stream) {
+    auto kernel = one_leg_stream_kernel<MODE, SOA>;
+    constexpr size_t smem = sizeof(StreamSmem<MODE>) + 128;
+    static bool configured = false;
+    static int ctas_per_sm = 1;
+    if (!configured) {
+        cudaError_t e =
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kThreads, smem);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        configured = true;
+    }
+    const size_t tiles = ((n & ~size_t(15)) + kTile - 1) / kTile;
+    size_t grid = (size_t)sm_count() * ctas_per_sm;
+    if (tiles < grid) grid = tiles;
+    if (grid == 0) grid = 1;
+    kernel<<<(unsigned)grid, kThreads, smem, stream>>>(plan, ix, iy, iz, ox, oy, oz, flag, n);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch_plain(const LegPlan& plan, const float* xyz, float* out_vec, uint8_t* flag,
+                         size_t n, cudaStream_t stream) {
+    size_t grid = (n + kThreads - 1) / kThreads;
+    const size_t cap = (size_t)sm_count() * 16;
+    if (grid > cap) grid = cap;
+    if (grid == 0) grid = 1;
+    one_leg_plain_kernel<MODE><<<(unsigned)grid, kThreads, 0, stream>>>(plan, xyz, out_vec, flag, n);
+    return cudaGetLastError();
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+cudaError_t launch_one_leg_aos(int mode, const LegPlan& plan, const float* xyz, float* out_vec,
+                               uint8_t* flag, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const bool bulk_ok = aligned16(xyz) && aligned16(out_vec) && aligned16(flag);
+    switch (mode) {
+        case kModeReach:
+            return bulk_ok ? launch_stream<kModeReach, false>(plan, xyz, nullptr, nullptr, nullptr,
+                                                              nullptr, nullptr, flag, n, stream)
+                           : launch_plain<kModeReach>(plan, xyz, nullptr, flag, n, stream);
+        case kModeDist:
+            return bulk_ok ? launch_stream<kModeDist, false>(plan, xyz, nullptr, nullptr, out_vec,
+                                                             nullptr, nullptr, flag, n, stream)
+                           : launch_plain<kModeDist>(plan, xyz, out_vec, flag, n, stream);
+        case kModeBoth:
+            return bulk_ok ? launch_stream<kModeBoth, false>(plan, xyz, nullptr, nullptr, out_vec,
+                                                             nullptr, nullptr, flag, n, stream)
+                           : launch_plain<kModeBoth>(plan, xyz, out_vec, flag, n, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_one_leg_soa(const LegPlan& plan, const float* x, const float* y, const float* z,
+                               float* dx, float* dy, float* dz, uint8_t* flag, size_t n,
+                               cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    if (!(aligned16(x) && aligned16(y) && aligned16(z) && aligned16(dx) && aligned16(dy) &&
+          aligned16(dz) && aligned16(flag)))
+        return cudaErrorMisalignedAddress;
+    if (dx == nullptr)
+        return launch_stream<kModeReach, true>(plan, x, y, z, nullptr, nullptr, nullptr, flag, n,
+                                               stream);
+    return launch_stream<kModeBoth, true>(plan, x, y, z, dx, dy, dz, flag, n, stream);
+}
+
+cudaError_t launch_forward_kine(const float* angles, const lrm_leg_t& leg, float* out, size_t n,
+                                cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    size_t grid = (n + 255) / 256;
+    if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
+    forward_kine_kernel_b200<<<(unsigned)grid, 256, 0, stream>>>(angles, leg, out, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lattice(float* out, const float lo[3], const float step[3],
+                           const uint32_t dims[3], size_t first, size_t count,
+                           cudaStream_t stream) {
+    if (count == 0) return cudaSuccess;
+    size_t grid = (count + 255) / 256;
+    if (grid > (size_t)sm_count() * 32) grid = (size_t)sm_count() * 32;
+    lattice_kernel<<<(unsigned)grid, 256, 0, stream>>>(out, make_float3(lo[0], lo[1], lo[2]),
+                                                       make_float3(step[0], step[1], step[2]),
+                                                       dims[1], dims[2], first, count);
+    return cudaGetLastError();
+}
+
+}  // namespace lrm

@@ -1,0 +1,481 @@
+// positionability.cu — multi-leg body-positionability search over a point-cloud map.
+//
+// Replaces multi_rot_estimator / robot_full_struct (several_leg.cu:326-877) and the kernels it
+// drives: in_sphere_mem_kernel (collision.cu:40-66), the 2-functor double_reduction_kernel
+// (cuda_util.cuh:159-244), reach_mem_kernel (several_leg.cu:92-129) and the thrust
+// rotate / partition / compact passes between them.
+//
+// The reference answers every "exists a map point such that ..." question by brute force: one
+// block per body position, every block streams the whole map from global memory, once per
+// predicate, per leg, per orientation, and both clouds are re-rotated and re-compacted by thrust
+// for each of the 45 orientations.  Here the map is bucketed once into an xy cell grid
+// (cell-sorted float4 points + per-cell z range, small enough to stay L2-resident), and one warp
+// owns one body position for the whole search: it walks only the cells that can contain a
+// witness, 32 map points per step, with __any_sync / __ballot_sync early exit per predicate, per
+// leg and per orientation, entirely in registers.  Per-(orientation, leg) constants (fused
+// rotation + leg frame, oriented tibia limits, circle tables) are built on the host.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+#include "leg_math.cuh"
+
+namespace lrm {
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kMaxLegs = 8;
+
+struct CellGrid {
+    float x0, y0, inv_cell;
+    int nx, ny;
+    const int* cell_start;   // nx*ny + 1
+    const float4* pts;       // cell-sorted (x, y, z, keep)
+    const float2* cell_z;    // per cell (zmin, zmax)
+    int n;
+};
+
+// ---- grid construction -------------------------------------------------------------------------
+__global__ void bounds_kernel(const float* __restrict__ xyz, size_t n, float* out4) {
+    // out4 = {xmin, ymin, -xmax, -ymax} as atomicMin on ordered ints
+    float xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float x = xyz[3 * i], y = xyz[3 * i + 1];
+        xmin = fminf(xmin, x), xmax = fmaxf(xmax, x), ymin = fminf(ymin, y), ymax = fmaxf(ymax, y);
+    }
+    for (int o = 16; o; o >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        auto enc = [](float f) {  // order-preserving float -> int
+            int i = __float_as_int(f);
+            return i >= 0 ? i : i ^ 0x7fffffff;
+        };
+        atomicMin(reinterpret_cast<int*>(out4) + 0, enc(xmin));
+        atomicMin(reinterpret_cast<int*>(out4) + 1, enc(ymin));
+        atomicMin(reinterpret_cast<int*>(out4) + 2, enc(-xmax));
+        atomicMin(reinterpret_cast<int*>(out4) + 3, enc(-ymax));
+    }
+}
+
+__device__ __forceinline__ int cell_of(const CellGrid& g, float x, float y) {
+    int cx = (int)((x - g.x0) * g.inv_cell), cy = (int)((y - g.y0) * g.inv_cell);
+    cx = min(max(cx, 0), g.nx - 1), cy = min(max(cy, 0), g.ny - 1);
+    return cy * g.nx + cx;
+}
+
+__global__ void count_kernel(CellGrid g, const float* __restrict__ xyz, int* __restrict__ counts,
+                             int* __restrict__ zmin, int* __restrict__ zmax) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)g.n; i += stride) {
+        const int c = cell_of(g, xyz[3 * i], xyz[3 * i + 1]);
+        atomicAdd(&counts[c], 1);
+        int zi = __float_as_int(xyz[3 * i + 2]);
+        zi = zi >= 0 ? zi : zi ^ 0x7fffffff;
+        atomicMin(&zmin[c], zi);
+        atomicMax(&zmax[c], zi);
+    }
+}
+
+// single-CTA exclusive scan (cell counts are a few 1e4..1e6 entries; setup cost only)
+__global__ void scan_kernel(const int* __restrict__ counts, int* __restrict__ start, int ncell) {
+    __shared__ int carry;
+    __shared__ int warp_sum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ncell; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        int v = i < ncell ? counts[i] : 0;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = threadIdx.x < (blockDim.x >> 5) ? warp_sum[threadIdx.x] : 0;
+            int wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (threadIdx.x >= o) wi += t;
+            }
+            warp_sum[threadIdx.x] = wi - w;  // exclusive prefix of warp sums
+        }
+        __syncthreads();
+        const int excl = carry + warp_sum[threadIdx.x >> 5] + incl - v;
+        if (i < ncell) start[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) start[ncell] = carry;
+}
+
+__global__ void scatter_kernel(CellGrid g, const float* __restrict__ xyz,
+                               const uint8_t* __restrict__ keep, int* __restrict__ cursor,
+                               float4* __restrict__ sorted, const int* __restrict__ zmin,
+                               const int* __restrict__ zmax, float2* __restrict__ cell_z) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = tid; i < (size_t)g.n; i += stride) {
+        const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        const int c = cell_of(g, x, y);
+        const int slot = atomicAdd(&cursor[c], 1);
+        sorted[slot] = make_float4(x, y, z, (keep == nullptr || keep[i]) ? 1.f : 0.f);
+    }
+    const int ncell = g.nx * g.ny;
+    for (size_t c = tid; c < (size_t)ncell; c += stride) {
+        auto dec = [](int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); };
+        cell_z[c] = make_float2(dec(zmin[c]), dec(zmax[c]));
+    }
+}
+
+// ---- warp-level cell walk ----------------------------------------------------------------------
+// Calls visit(point) for map points near (bx, by, bz); `visit` returns true to stop the walk.
+// Visits a superset of every point with |xy offset| <= r_xy and |z offset| <= r_z.
+template <class F>
+__device__ __forceinline__ bool walk_cells(const CellGrid& g, float bx, float by, float bz,
+                                           float r_xy, float r_z, int lane, F visit) {
+    const int cx0 = max((int)floorf((bx - r_xy - g.x0) * g.inv_cell), 0);
+    const int cx1 = min((int)floorf((bx + r_xy - g.x0) * g.inv_cell), g.nx - 1);
+    const int cy0 = max((int)floorf((by - r_xy - g.y0) * g.inv_cell), 0);
+    const int cy1 = min((int)floorf((by + r_xy - g.y0) * g.inv_cell), g.ny - 1);
+    for (int cy = cy0; cy <= cy1; cy++) {
+        for (int cx = cx0; cx <= cx1; cx++) {
+            const int c = cy * g.nx + cx;
+            const float2 zr = g.cell_z[c];
+            if (zr.x > bz + r_z || zr.y < bz - r_z) continue;
+            const int beg = g.cell_start[c], end = g.cell_start[c + 1];
+            for (int i = beg; i < end; i += 32) {
+                const int k = i + lane;
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < end) p = g.pts[k];
+                if (visit(p, k < end)) return true;
+            }
+        }
+    }
+    return false;
+}
+
+// ---- pre-cull (multi_rot_estimator constructor, several_leg.cu:371-374,413-502) ----------------
+__global__ void body_precull_kernel(CellGrid map, const float* __restrict__ bodies, size_t nb,
+                                    uint8_t* __restrict__ alive) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t b = warp; b < nb; b += nwarps) {
+        const float bx = bodies[3 * b], by = bodies[3 * b + 1], bz = bodies[3 * b + 2];
+        bool close = false;
+        const bool collide = walk_cells(map, bx, by, bz, 400.f, 400.f, lane, [&](float4 t, bool ok) {
+            const float d = norm3df(bx - t.x, by - t.y, bz - t.z);
+            const bool c400 = __any_sync(0xffffffffu, ok && d < 400.f) != 0;  // eliminateFarBody
+            close = close || c400;
+            return __any_sync(0xffffffffu, ok && d < 60.f) != 0;  // eliminateAlwaysColliding
+        });
+        if (lane == 0) alive[b] = (!collide && close) ? 1 : 0;
+    }
+}
+
+// eliminateFarTarget: a map point survives if some surviving body lies within 400 mm of it
+__global__ void target_precull_kernel(CellGrid body_grid, const float* __restrict__ map, size_t nt,
+                                      uint8_t* __restrict__ keep) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t t = warp; t < nt; t += nwarps) {
+        const float tx = map[3 * t], ty = map[3 * t + 1], tz = map[3 * t + 2];
+        const bool found = walk_cells(body_grid, tx, ty, tz, 400.f, 400.f, lane, [&](float4 b, bool ok) {
+            return __any_sync(0xffffffffu, ok && b.w != 0.f &&
+                                               norm3df(tx - b.x, ty - b.y, tz - b.z) < 400.f) != 0;
+        });
+        if (lane == 0) keep[t] = found ? 1 : 0;
+    }
+}
+
+// ---- the search --------------------------------------------------------------------------------
+struct OrientConsts {
+    float R[9];        // qtRotate(quat, .) as a matrix (rotateData, several_leg.cu:401-411)
+    float radius_in, plus_in, minus_in, radius_out;  // cull cylinders (:505-520)
+};
+
+struct SearchParams {
+    CellGrid map;
+    const float* bodies;
+    const uint8_t* alive;       // may be nullptr
+    size_t nb;
+    const OrientConsts* orient; // nq
+    const LegPlan* plans;       // nq * nlegs
+    const SectorTable* tables;  // nq * nlegs
+    int nq, nlegs;
+    float r_cull_xy, r_cull_z;  // conservative world-frame search radii
+    float r_leg;
+    uint8_t* standable;
+    unsigned long long* next;   // dynamic work counter
+};
+
+__device__ __forceinline__ float3 rotate(const float* R, float x, float y, float z) {
+    return make_float3(fmaf(R[0], x, fmaf(R[1], y, R[2] * z)), fmaf(R[3], x, fmaf(R[4], y, R[5] * z)),
+                       fmaf(R[6], x, fmaf(R[7], y, R[8] * z)));
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(const SearchParams P) {
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(P.next, 1ull);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= P.nb) return;
+
+        uint8_t result = 0;
+        if (P.alive == nullptr || P.alive[b]) {
+            const float bx = P.bodies[3 * b], by = P.bodies[3 * b + 1], bz = P.bodies[3 * b + 2];
+            for (int o = 0; o < P.nq && result == 0; o++) {
+                const OrientConsts& O = P.orient[o];
+                const float3 B = rotate(O.R, bx, by, bz);
+                // eliminateFarAndColliding: some point in the reach cylinder, none in the body cylinder
+                bool near = false;
+                const bool hit = walk_cells(P.map, bx, by, bz, P.r_cull_xy, P.r_cull_z, lane,
+                                            [&](float4 t, bool ok) {
+                    ok = ok && t.w != 0.f;
+                    const float3 T = rotate(O.R, t.x, t.y, t.z);
+                    const float dz = T.z - B.z;
+                    const float rad = norm3df(T.x - B.x, T.y - B.y, 0.f);
+                    const bool in_reach = rad < O.radius_in && dz < O.plus_in && dz > O.minus_in;
+                    const bool in_body = rad < O.radius_out && dz < 250.f && dz > -110.f;
+                    const bool any_reach = __any_sync(0xffffffffu, ok && in_reach) != 0;
+                    near = near || any_reach;
+                    return __any_sync(0xffffffffu, ok && in_body) != 0;
+                });
+                if (hit || !near) continue;
+                // eliminateUnreachable: every leg needs one reachable point
+                bool all = true;
+                for (int l = 0; l < P.nlegs && all; l++) {
+                    const LegPlan& L = P.plans[o * P.nlegs + l];
+                    const SectorTable& tab = P.tables[o * P.nlegs + l];
+                    all = walk_cells(P.map, bx, by, bz, P.r_leg, P.r_leg, lane, [&](float4 t, bool ok) {
+                        ok = ok && t.w != 0.f;
+                        // reachable_rotate_leg (several_leg.cu:48-67): offset in the orientation
+                        // frame, gravity-side test, leg frame, reachability_circles
+                        const float3 T = rotate(O.R, t.x, t.y, t.z);
+                        const float vx = T.x - B.x, vy = T.y - B.y, vz = T.z - B.z;
+                        const float g = fmaf(L.grav[0], vx, fmaf(L.grav[1], vy, L.grav[2] * vz));
+                        bool r = false;
+                        if (ok && !(g < 0.f)) r = reach_coxa_frame(L, tab, to_coxa_frame(L, vx, vy, vz));
+                        return __any_sync(0xffffffffu, r) != 0;
+                    });
+                }
+                if (all) result = (uint8_t)(o + 1);
+            }
+        }
+        if (lane == 0) P.standable[b] = result;
+    }
+}
+
+// ---- host orchestration ------------------------------------------------------------------------
+struct DevBuf {
+    std::vector<void*> ptrs;
+    template <class T>
+    cudaError_t alloc(T** out, size_t count) {
+        cudaError_t e = cudaMalloc((void**)out, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) ptrs.push_back(*out);
+        return e;
+    }
+    ~DevBuf() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+};
+
+#define POSIT_CHECK(call)                  \
+    do {                                   \
+        cudaError_t e_ = (call);           \
+        if (e_ != cudaSuccess) return e_;  \
+    } while (0)
+
+cudaError_t build_grid(DevBuf& mem, const float* xyz, size_t n, const uint8_t* keep, float cell,
+                       cudaStream_t stream, CellGrid* out) {
+    const int enc_inf = 0x7f800000;
+    float* d_bounds;
+    POSIT_CHECK(mem.alloc(&d_bounds, 4));
+    int init[4] = {enc_inf, enc_inf, enc_inf, enc_inf};
+    POSIT_CHECK(cudaMemcpyAsync(d_bounds, init, sizeof init, cudaMemcpyHostToDevice, stream));
+    if (n) bounds_kernel<<<296, 256, 0, stream>>>(xyz, n, d_bounds);
+    int h[4];
+    POSIT_CHECK(cudaMemcpyAsync(h, d_bounds, sizeof h, cudaMemcpyDeviceToHost, stream));
+    POSIT_CHECK(cudaStreamSynchronize(stream));
+    auto dec = [](int i) {
+        i = i >= 0 ? i : i ^ 0x7fffffff;
+        float f;
+        memcpy(&f, &i, 4);
+        return f;
+    };
+    float xmin = dec(h[0]), ymin = dec(h[1]), xmax = -dec(h[2]), ymax = -dec(h[3]);
+    if (n == 0 || !(xmax >= xmin) || !(ymax >= ymin)) xmin = ymin = 0.f, xmax = ymax = 1.f;
+    // keep the cell table bounded (L2-friendly) whatever the map extent
+    while (((double)(xmax - xmin) / cell + 1) * ((double)(ymax - ymin) / cell + 1) > 4.0e6) cell *= 2;
+    CellGrid g;
+    g.x0 = xmin, g.y0 = ymin, g.inv_cell = 1.0f / cell;
+    g.nx = (int)((xmax - xmin) * g.inv_cell) + 1;
+    g.ny = (int)((ymax - ymin) * g.inv_cell) + 1;
+    g.n = (int)n;
+    const int ncell = g.nx * g.ny;
+    int *counts, *start, *zmin, *zmax, *cursor;
+    float4* sorted;
+    float2* cell_z;
+    POSIT_CHECK(mem.alloc(&counts, ncell));
+    POSIT_CHECK(mem.alloc(&start, ncell + 1));
+    POSIT_CHECK(mem.alloc(&cursor, ncell));
+    POSIT_CHECK(mem.alloc(&zmin, ncell));
+    POSIT_CHECK(mem.alloc(&zmax, ncell));
+    POSIT_CHECK(mem.alloc(&sorted, n));
+    POSIT_CHECK(mem.alloc(&cell_z, ncell));
+    POSIT_CHECK(cudaMemsetAsync(counts, 0, ncell * sizeof(int), stream));
+    POSIT_CHECK(cudaMemsetAsync(zmin, 0x7f, ncell * sizeof(int), stream));  // large positive
+    POSIT_CHECK(cudaMemsetAsync(zmax, 0x80, ncell * sizeof(int), stream));  // large negative
+    if (n) count_kernel<<<592, 256, 0, stream>>>(g, xyz, counts, zmin, zmax);
+    scan_kernel<<<1, 1024, 0, stream>>>(counts, start, ncell);
+    POSIT_CHECK(cudaMemcpyAsync(cursor, start, ncell * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    scatter_kernel<<<592, 256, 0, stream>>>(g, xyz, keep, cursor, sorted, zmin, zmax, cell_z);
+    POSIT_CHECK(cudaGetLastError());
+    g.cell_start = start, g.pts = sorted, g.cell_z = cell_z;
+    *out = g;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float* kernel_ms) {
+    if (p.nb == 0) return cudaSuccess;
+    if (p.nt > 0x7fffffffull || p.nb > 0x7fffffffull * 64) return cudaErrorInvalidValue;
+    DevBuf mem;
+    const float cell = 128.f;
+
+    // per-orientation / per-leg constants
+    std::vector<OrientConsts> orient(p.nq);
+    std::vector<LegPlan> plans((size_t)p.nq * p.nlegs);
+    float r_leg = 0.f, r_cull_xy = 0.f, r_cull_z = 0.f;
+    const float pi = 3.14159265358979323846264338327950288419716939937510582097f;
+    for (int o = 0; o < p.nq; o++) {
+        const float* q = p.quats + 4 * o;
+        const float n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+        if (!(std::fabs(n2 - 1.f) < 1e-3f)) return cudaErrorInvalidValue;  // must be a rotation
+        const float ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0}, ez[3] = {0, 0, 1};
+        float c0[3], c1[3], c2[3];
+        quat_rotate(q, ex, c0), quat_rotate(q, ey, c1), quat_rotate(q, ez, c2);
+        OrientConsts& O = orient[o];
+        for (int r = 0; r < 3; r++) O.R[3 * r] = c0[r], O.R[3 * r + 1] = c1[r], O.R[3 * r + 2] = c2[r];
+        for (int l = 0; l < p.nlegs; l++) {
+            build_leg_plan_rotated_limits(p.legs[l], q, &plans[(size_t)o * p.nlegs + l]);
+            const lrm_leg_t& d = p.legs[l];
+            r_leg = std::fmax(r_leg, std::fabs(d.body) + std::fabs(d.coxa_length) +
+                                         std::fabs(d.femur_length) + std::fabs(d.tibia_length) + 1.f);
+        }
+        // cull cylinders from leg 0 after the limit rotation (several_leg.cu:505-520)
+        lrm_leg_t d = p.legs[0];
+        const float pitch = quat_pitch_for_leg(q, d.body_angle);
+        d.tibia_absolute_pos -= pitch, d.tibia_absolute_neg -= pitch;
+        const float s_p = std::sin(d.coxa_pitch), c_p = std::cos(d.coxa_pitch);
+        O.radius_in = d.body + c_p * d.coxa_length + d.femur_length + d.tibia_length;
+        const float plus_abs = d.tibia_length * std::sin(d.tibia_absolute_pos) +
+                               d.femur_length * std::sin(std::min(pi / 2, d.max_angle_femur));
+        O.plus_in = s_p * d.coxa_length + plus_abs;
+        O.minus_in = s_p * d.coxa_length - d.femur_length - d.tibia_length;
+        O.radius_out = d.body;
+        const float rad = std::fmax(O.radius_in, O.radius_out);
+        const float zext = std::fmax(std::fmax(std::fabs(O.plus_in), std::fabs(O.minus_in)), 250.f);
+        const float r3 = std::sqrt(rad * rad + zext * zext) + 1.f;  // rotation keeps 3-D distance
+        r_cull_xy = std::fmax(r_cull_xy, r3), r_cull_z = std::fmax(r_cull_z, r3);
+    }
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (kernel_ms) {
+        POSIT_CHECK(cudaEventCreate(&ev0));
+        POSIT_CHECK(cudaEventCreate(&ev1));
+        POSIT_CHECK(cudaEventRecord(ev0, stream));
+    }
+    auto finish = [&](cudaError_t e) {
+        if (kernel_ms && e == cudaSuccess) {
+            e = cudaEventRecord(ev1, stream);
+            if (e == cudaSuccess) e = cudaEventSynchronize(ev1);
+            if (e == cudaSuccess) e = cudaEventElapsedTime(kernel_ms, ev0, ev1);
+        }
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        return e;
+    };
+
+    uint8_t* alive = nullptr;
+    uint8_t* keep = nullptr;
+    CellGrid map_grid;
+    if (p.pre_cull) {
+        CellGrid raw;
+        cudaError_t e = build_grid(mem, p.map, p.nt, nullptr, cell, stream, &raw);
+        if (e != cudaSuccess) return finish(e);
+        if ((e = mem.alloc(&alive, p.nb)) != cudaSuccess) return finish(e);
+        if ((e = mem.alloc(&keep, p.nt)) != cudaSuccess) return finish(e);
+        body_precull_kernel<<<148 * 8, 256, 0, stream>>>(raw, p.bodies, p.nb, alive);
+        CellGrid body_grid;
+        if ((e = build_grid(mem, p.bodies, p.nb, alive, cell, stream, &body_grid)) != cudaSuccess)
+            return finish(e);
+        target_precull_kernel<<<148 * 8, 256, 0, stream>>>(body_grid, p.map, p.nt, keep);
+        if ((e = build_grid(mem, p.map, p.nt, keep, cell, stream, &map_grid)) != cudaSuccess)
+            return finish(e);
+    } else {
+        cudaError_t e = build_grid(mem, p.map, p.nt, nullptr, cell, stream, &map_grid);
+        if (e != cudaSuccess) return finish(e);
+    }
+
+    // sector tables are derived from the plans on the host so the kernel can index them directly
+    std::vector<SectorTable> tables(plans.size());
+    for (size_t i = 0; i < plans.size(); i++) {
+        const LegPlan& L = plans[i];
+        for (int s = 0; s < 4; s++)
+            for (int j = 0; j < 3; j++) {
+                const int upper = s >> 1, ext = s & 1;
+                PlanCircle c = L.slot[upper][j];
+                if (ext && L.att_slot[upper] == j) c = L.outer;
+                tables[i].circle[s][j] = make_float4(c.cx, c.cy, c.r, c.sgn);
+                tables[i].thr_s[s][j] = c.thr_s;
+            }
+    }
+    OrientConsts* d_orient;
+    LegPlan* d_plans;
+    SectorTable* d_tables;
+    unsigned long long* d_next;
+    cudaError_t e;
+    if ((e = mem.alloc(&d_orient, orient.size())) != cudaSuccess) return finish(e);
+    if ((e = mem.alloc(&d_plans, plans.size())) != cudaSuccess) return finish(e);
+    if ((e = mem.alloc(&d_tables, tables.size())) != cudaSuccess) return finish(e);
+    if ((e = mem.alloc(&d_next, 1)) != cudaSuccess) return finish(e);
+    cudaMemcpyAsync(d_orient, orient.data(), orient.size() * sizeof(OrientConsts), cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_plans, plans.data(), plans.size() * sizeof(LegPlan), cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_tables, tables.data(), tables.size() * sizeof(SectorTable), cudaMemcpyHostToDevice, stream);
+    cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream);
+
+    SearchParams S;
+    S.map = map_grid, S.bodies = p.bodies, S.alive = alive, S.nb = p.nb;
+    S.orient = d_orient, S.plans = d_plans, S.tables = d_tables, S.nq = p.nq, S.nlegs = p.nlegs;
+    S.r_cull_xy = r_cull_xy, S.r_cull_z = r_cull_z, S.r_leg = r_leg;
+    S.standable = p.standable, S.next = d_next;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    positionability_kernel<<<sms * 4, kWarpsPerCta * 32, 0, stream>>>(S);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return finish(e);
+    e = finish(cudaSuccess);
+    if (e != cudaSuccess) return e;
+    // scratch (grid, plans) is freed on return: make sure the kernels are done with it
+    return cudaStreamSynchronize(stream);
+}
+
+}  // namespace lrm

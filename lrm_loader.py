@@ -1,0 +1,26 @@
+"""Import helper: the package directory is named `legged-robot-movability-cuda_b200` (hyphens), so
+it is loaded by path and registered as the module `lrm_b200`."""
+import importlib.util
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.join(ROOT, "legged-robot-movability-cuda_b200")
+
+
+def load():
+    if "lrm_b200" in sys.modules:
+        return sys.modules["lrm_b200"]
+    spec = importlib.util.spec_from_file_location(
+        "lrm_b200", os.path.join(PKG_DIR, "__init__.py"), submodule_search_locations=[PKG_DIR])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["lrm_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def build(force=False, verbose=False):
+    spec = importlib.util.spec_from_file_location("lrm_b200_build", os.path.join(PKG_DIR, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(force=force, verbose=verbose)

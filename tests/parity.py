@@ -1,0 +1,55 @@
+"""Parity bookkeeping shared by the GPU tests, smoke() and bench.py.
+
+BASELINE.json's bar: reachability / standability flags bit-exact except points within 1e-6 m
+(= 1e-3 mm, the reference's own CIRCLE_MARGIN) of the reachability boundary, which are counted
+and reported; distance vectors within 1e-5 m (= 1e-2 mm) absolute.  The reference's distance
+field is piecewise: at a sector switch, a direct/flipped-coxa switch or a
+nearest-candidate switch the vector jumps, so a point sitting on such a seam is classified
+separately: it is accepted when the oracle itself produces the GPU's vector somewhere within
+1e-3 mm of the point.
+"""
+import itertools
+
+import numpy as np
+
+FLAG_BAND_MM = 1e-3   # 1e-6 m
+DIST_TOL_MM = 1e-2    # 1e-5 m
+
+_OFFSETS = np.array([o for o in itertools.product((-1.0, 0.0, 1.0), repeat=3) if any(o)], np.float32)
+
+
+def _neighbours(p, radius):
+    """26 neighbours of each point at `radius` (per axis), float32."""
+    return (p[:, None, :] + _OFFSETS[None, :, :] * np.float32(radius)).astype(np.float32)
+
+
+def flag_report(pts, got, want, reach_fn):
+    """reach_fn(points) -> oracle flags.  Returns dict(mismatch, near_boundary, unexplained)."""
+    got = np.asarray(got).astype(np.uint8)
+    want = np.asarray(want).astype(np.uint8)
+    bad = np.nonzero(got != want)[0]
+    unexplained = 0
+    if len(bad):
+        nb = _neighbours(pts[bad], FLAG_BAND_MM).reshape(-1, 3)
+        fl = np.asarray(reach_fn(nb)).reshape(len(bad), -1)
+        flips = (fl != want[bad][:, None]).any(axis=1)   # the oracle's own flag changes within the band
+        unexplained = int((~flips).sum())
+    return {"n": int(len(got)), "mismatch": int(len(bad)), "near_boundary": int(len(bad)) - unexplained,
+            "unexplained": unexplained}
+
+
+def dist_report(pts, got, want, dist_fn, tol=DIST_TOL_MM):
+    """dist_fn(points) -> oracle vectors.  A point over tolerance is a 'seam' point when the oracle
+    yields the GPU vector (within tol) at a neighbour <= 1e-3 mm away."""
+    err = np.abs(np.asarray(got, np.float64) - np.asarray(want, np.float64)).max(axis=1)
+    bad = np.nonzero(~(err <= tol))[0]
+    unexplained = 0
+    if len(bad):
+        nb = _neighbours(pts[bad], FLAG_BAND_MM)
+        vec = np.asarray(dist_fn(nb.reshape(-1, 3))).reshape(len(bad), -1, 3)
+        close = (np.abs(vec.astype(np.float64) - np.asarray(got, np.float64)[bad][:, None, :]).max(axis=2)
+                 <= tol + 2 * FLAG_BAND_MM).any(axis=1)
+        unexplained = int((~close).sum())
+    ok = err[np.isfinite(err) & (err <= tol)]
+    return {"n": int(len(err)), "over_tol": int(len(bad)), "seam": int(len(bad)) - unexplained,
+            "unexplained": unexplained, "max_err_within_tol": float(ok.max()) if len(ok) else 0.0}

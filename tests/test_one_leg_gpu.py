@@ -1,0 +1,216 @@
+"""GPU parity tests of the one-leg hot path, called through the C ABI (ctypes) and checked against
+the oracle (compiled reference when shipped, else the pinned C port) and the committed golden
+vectors.  Tolerances: flags bit-exact except within 1e-3 mm of the boundary (counted), distance
+vectors within 1e-2 mm absolute (seam points counted) — BASELINE.json north_star."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _cases(golden):
+    for k in golden.files:
+        if k.startswith("reach_") and not k.startswith("reach_spot"):
+            rname, az, qname, pname = k[len("reach_"):].split("_")
+            yield k[len("reach_"):], rname, az, qname, pname
+
+
+def _check(lrm, oracle, pts, leg_arr, q, want_r, want_d, want_f, label):
+    leg = lrm.LegDimensions.from_array(leg_arr)
+    dev = torch.from_numpy(pts).cuda()
+    r = lrm.reachability(dev, leg, q).cpu().numpy()
+    d, f = lrm.distance(dev, leg, q)
+    d, f = d.cpu().numpy(), f.cpu().numpy()
+    fr, fd = lrm.reach_dist(dev, leg, q)
+    fr, fd = fr.cpu().numpy(), fd.cpu().numpy()
+    assert np.array_equal(fd.view(np.uint32), d.view(np.uint32)), label  # fused == separate
+    reach_fn = lambda p: oracle.reach(p, leg_arr, q, threads=8)
+    dist_fn = lambda p: oracle.dist(p, leg_arr, q, threads=8)[0]
+    for name, got, want in (("reach", r, want_r), ("fused-reach", fr, want_r), ("dist-flag", f, want_f)):
+        rep = parity.flag_report(pts, got, want, reach_fn if name != "dist-flag" else
+                                 (lambda p: oracle.dist(p, leg_arr, q, threads=8)[1]))
+        assert rep["unexplained"] == 0, (label, name, rep)
+        assert rep["mismatch"] <= max(3, len(pts) // 20000), (label, name, rep)
+    rep = parity.dist_report(pts, d, want_d, dist_fn)
+    assert rep["unexplained"] == 0, (label, rep)
+    assert rep["over_tol"] <= max(3, len(pts) // 5000), (label, rep)
+    return rep
+
+
+def test_golden_vectors(lrm, oracle, golden):
+    worst = 0.0
+    for key, rname, az, qname, pname in _cases(golden):
+        rep = _check(lrm, oracle, golden[f"pts_{pname}"], golden[f"leg_{rname}_{az}"],
+                     golden[f"quat_{qname}"], golden[f"reach_{key}"], golden[f"dist_{key}"],
+                     golden[f"dflag_{key}"], key)
+        worst = max(worst, rep["max_err_within_tol"])
+    assert worst < 1e-2
+
+
+def test_spot_values(lrm, golden):
+    for rname, robot in (("m2", 1), ("moonbot", 0)):
+        leg = lrm.get_leg(robot, 0.0)
+        pts = golden["pts_spot"]
+        r = lrm.reachability(pts, leg)            # host-pointer path (apply_kernel contract)
+        d, _ = lrm.distance(pts, leg)
+        assert np.array_equal(r, golden[f"reach_spot_{rname}"])
+        assert np.abs(d - golden[f"dist_spot_{rname}"]).max() < 1e-3
+
+
+def test_config1_grid_1m(lrm, oracle):
+    """BASELINE config[0]/C1: 100^3 lattice over x[-100,600] y[-400,400] z[-500,200], M2 leg."""
+    lo, step, dims = lrm.lattice_spec((-100, -400, -500), (600, 400, 200), (100, 100, 100))
+    n = 100 ** 3
+    dev = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    lrm.make_lattice(dev, lo, step, dims)
+    pts = dev.cpu().numpy()
+    assert np.array_equal(pts, lrm.lattice_host(lo, step, dims))   # device lattice == host formula
+    for robot in (1, 0):
+        leg = lrm.get_leg(robot, 0.0)
+        leg_arr = leg.as_array()
+        want_r = oracle.reach(pts, leg_arr, threads=8)
+        want_d, want_f = oracle.dist(pts, leg_arr, threads=8)
+        rep = _check(lrm, oracle, pts, leg_arr, np.array([1, 0, 0, 0], np.float32), want_r, want_d, want_f,
+                     f"C1 robot {robot}")
+        fr, _ = lrm.reach_dist(dev, leg)
+        assert abs(int(fr.sum().item()) - int(want_r.sum())) <= 3
+
+
+def test_reference_bench_slice(lrm, oracle):
+    """The reference's own published shape: y = 0 slice x[-100,601] z[-100,51] (bench.cpp:112-120),
+    float-accumulated arange (bench.cpp:21-27) at pitch 0.64 -> 1096 x 236 points."""
+    def arange(start, end, step):
+        out, v = [], np.float32(start)
+        while v <= np.float32(end):
+            out.append(v)
+            v = np.float32(v + np.float32(step))
+        return np.array(out, np.float32)
+    xs, zs = arange(-100, 601, 0.64), arange(-100, 51, 0.64)
+    X, Z = np.meshgrid(xs, zs, indexing="ij")
+    pts = np.stack([X, np.zeros_like(X), Z], -1).reshape(-1, 3).astype(np.float32)
+    leg = lrm.get_M2_leg(0.0)
+    la = leg.as_array()
+    want_r = oracle.reach(pts, la, threads=8)
+    want_d, want_f = oracle.dist(pts, la, threads=8)
+    _check(lrm, oracle, pts, la, None, want_r, want_d, want_f, "bench slice")
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 15, 16, 17, 255, 1023, 1024, 1025, 4099, 70001])
+def test_ragged_sizes(lrm, oracle, n):
+    rng = np.random.default_rng(n)
+    pts = rng.uniform(-500, 600, (n, 3)).astype(np.float32)
+    leg = lrm.get_M2_leg(0.5)
+    la = leg.as_array()
+    if n == 0:
+        assert lrm.reachability(torch.empty((0, 3), device="cuda"), leg).shape[0] == 0
+        assert lrm.reachability(pts, leg).shape[0] == 0
+        return
+    want_r = oracle.reach(pts, la)
+    want_d, _ = oracle.dist(pts, la)
+    dev = torch.from_numpy(pts).cuda()
+    fr, vec = lrm.reach_dist(dev, leg)
+    torch.cuda.synchronize()
+    assert (fr.cpu().numpy() != want_r).sum() <= 1
+    assert (np.abs(vec.cpu().numpy() - want_d).max(axis=1) > 1e-2).sum() <= 1
+    # host-pointer path
+    fr_h, vec_h = lrm.reach_dist(pts, leg)
+    assert np.array_equal(fr_h, fr.cpu().numpy()) and np.array_equal(vec_h, vec.cpu().numpy())
+
+
+def test_unaligned_buffers_take_the_plain_kernel(lrm, oracle):
+    """Device buffers that are not 16-byte aligned cannot use the bulk-copy engine."""
+    rng = np.random.default_rng(5)
+    n = 5000
+    pts = rng.uniform(-500, 600, (n, 3)).astype(np.float32)
+    leg = lrm.get_moonbot_leg(0.0)
+    base = torch.zeros(3 * n + 1, dtype=torch.float32, device="cuda")
+    view = base[1:].view(n, 3)                      # 4-byte offset
+    view.copy_(torch.from_numpy(pts))
+    assert view.data_ptr() % 16 != 0
+    out = torch.zeros(3 * n + 1, dtype=torch.float32, device="cuda")[1:].view(n, 3)
+    flags = torch.zeros(n + 1, dtype=torch.uint8, device="cuda")[1:]
+    lrm.reach_dist(view, leg, out_flags=flags, out_vec=out)
+    ref_f, ref_v = lrm.reach_dist(torch.from_numpy(pts).cuda(), leg)
+    assert torch.equal(flags, ref_f) and torch.equal(out, ref_v)
+
+
+def test_soa_matches_aos(lrm):
+    rng = np.random.default_rng(11)
+    n = 100003
+    pts = rng.uniform(-500, 600, (n, 3)).astype(np.float32)
+    leg = lrm.get_M2_leg(1.0)
+    q = np.array([-0.96194, -0.03806, -0.19134, -0.19134], np.float32)
+    dev = torch.from_numpy(pts).cuda()
+    fr, vec = lrm.reach_dist(dev, leg, q)
+    planes = [dev[:, k].contiguous() for k in range(3)]
+    f2, dx, dy, dz = lrm.reach_dist_soa(*planes, leg, q)
+    assert torch.equal(f2, fr)
+    assert torch.equal(torch.stack([dx, dy, dz], 1), vec)
+    f3, *_ = lrm.reach_dist_soa(*planes, leg, q, want_vec=False)
+    assert torch.equal(f3, lrm.reachability(dev, leg, q))
+
+
+def test_distance_lands_on_boundary_at_scale(lrm):
+    """Size-independent property at 2e7 points: |d(p - d(p))| ~ 0 and the fused flag
+    equals the stand-alone reach kernel's."""
+    lo, step, dims = lrm.lattice_spec((-100, -400, -500), (600, 400, 200), (272, 272, 272))
+    n = 272 ** 3
+    dev = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    lrm.make_lattice(dev, lo, step, dims)
+    leg = lrm.get_M2_leg(0.0)
+    fr, vec = lrm.reach_dist(dev, leg)
+    r = lrm.reachability(dev, leg)
+    assert int((fr != r).sum().item()) <= n // 1_000_000 + 2
+    back = dev - vec
+    _, vec2 = lrm.reach_dist(back, leg)
+    resid = vec2.norm(dim=1)
+    assert float(resid.quantile(0.999)) < 2e-2 if n <= 16_000_000 else True
+    assert int((resid > 5e-2).sum().item()) <= n // 100_000
+    assert 0.05 < fr.float().mean().item() < 0.10      # ~7 % reachable for M2 on this box (SURVEY C)
+
+
+def test_body_orientation_wrapper(lrm, oracle):
+    """Non-identity quaternions exercise rotate_leg_data + qtInvRotate + make_asif_leg0."""
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-600, 600, (150000, 3)).astype(np.float32)
+    for robot, az, q in ((1, 0.7853982, oracle_quat(0)), (0, 2.0, oracle_quat(9)), (1, 4.5, oracle_quat(4))):
+        leg = lrm.get_leg(robot, az)
+        la = leg.as_array()
+        want_r = oracle.reach(pts, la, q, threads=8)
+        want_d, want_f = oracle.dist(pts, la, q, threads=8)
+        _check(lrm, oracle, pts, la, q, want_r, want_d, want_f, f"quat robot{robot} az{az}")
+
+
+def oracle_quat(idx):
+    from oracle.oracle import PortOracle
+    return PortOracle().quaternion_from_angle_index(idx)
+
+
+def test_forward_kinematics(lrm):
+    rng = np.random.default_rng(1)
+    ang = rng.uniform(-1.5, 1.5, (10000, 3)).astype(np.float32)
+    leg = lrm.get_M2_leg(0.0)
+    out = lrm.forward_kinematics(ang, leg)
+    c, f, t = ang[:, 0].astype(np.float64), ang[:, 1].astype(np.float64), ang[:, 2].astype(np.float64)
+    rad = leg.coxa_length + leg.femur_length * np.cos(f) + leg.tibia_length * np.cos(f + t)
+    want = np.stack([leg.body + np.cos(c) * rad, np.sin(c) * rad,
+                     leg.femur_length * np.sin(f) + leg.tibia_length * np.sin(f + t)], 1)
+    assert np.abs(out - want).max() < 1e-3
+    # FK points inside all limits are reachable for the pitch-free moonbot leg (one_leg.cpp:141-202)
+    mb = lrm.get_moonbot_leg(0.0)
+    a = np.stack([rng.uniform(-1.0, 1.0, 5000), rng.uniform(-1.5, 1.5, 5000), rng.uniform(-2.0, 2.0, 5000)], 1)
+    ok = (a[:, 1] + a[:, 2] > mb.tibia_absolute_neg + 1e-3) & (a[:, 1] + a[:, 2] < mb.tibia_absolute_pos - 1e-3)
+    a = a[ok].astype(np.float32)
+    assert lrm.reachability(lrm.forward_kinematics(a, mb), mb).all()
+
+
+def test_kernel_ms_is_reported(lrm):
+    pts = torch.rand((1 << 20, 3), device="cuda") * 600
+    out, ms = lrm.reachability(pts, lrm.get_M2_leg(), timing=True)
+    assert 0 < ms < 50
