@@ -6,69 +6,97 @@
 // circles.cu.h:48-78), re-derived so that nothing leg-constant is evaluated per point:
 //   * no atan2f / sincosf: every angle comparison is a cross-product sign test against a constant
 //     direction (AngleTest), and the coxa rotation uses the normalised (x, y) itself;
-//   * the 4 circles of a sector come from a 4-sector table (shared memory, float4 per circle)
-//     instead of being rebuilt from 8+ sin/cos per point into local memory;
-//   * circle validity is a compare on squared distances with the +-CIRCLE_MARGIN folded into the
-//     threshold; corner points are constants.
+//   * the circles of a sector come from a host-built 4-sector table staged in shared memory
+//     (two float4 per circle) instead of being rebuilt from 8+ sin/cos per point into local memory;
+//   * "does the projection on circle j satisfy the other circles" (12 circle tests per plane
+//     evaluation in the reference) is one dot product against the precomputed valid arc of
+//     circle j; corner points are constants;
+//   * the direct and the pi-flipped coxa solution share their yaw tests, and a solution whose
+//     plane evaluation provably duplicates the other one's (yaw beyond limit +- pi/2) is skipped.
 // Everything lives in registers; the only memory traffic is the point itself.
 #pragma once
 #include <cuda_runtime.h>
 
 #include "leg_plan.h"
 
+// The math below is plain FP32 and compiles for the host as well: tests/emu builds it into a
+// test-only emulator so the CPU test suite can check this file against the oracle without a GPU.
+// The product library only ever instantiates the __device__ side.
+#define LRM_HD __host__ __device__ __forceinline__
+
 namespace lrm {
+
+LRM_HD int f2i(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_int(f);
+#else
+    int i;
+    __builtin_memcpy(&i, &f, 4);
+    return i;
+#endif
+}
+// 1/sqrt(x), ~2 ulp, one MUFU.RSQ (denormal inputs flush to zero -> +inf, handled by callers)
+LRM_HD float fast_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
 
 constexpr float kMarginF = 0.001f;  // CIRCLE_MARGIN, settings.h:9
 
-// Sector table staged in shared memory by every CTA: [sector = upper*2 + ext][slot 1..3].
+// Sector table staged in shared memory by every CTA: a copy of LegPlan::sector.
+// row[sector][2*j]   = (cx, cy, r, sgn)      of slot j+1
+// row[sector][2*j+1] = (ax, ay, ah, inner_j) valid arc of slot j+1; 4th = j-th arc number of slot 0
+// row[sector][6]     = second valid arc of slot 0 (the inner circle)
+// Row stride 7 float4 = 28 words: lanes in different sectors hit different banks.
 struct SectorTable {
-    float4 circle[4][3];  // cx, cy, r, sgn
-    float thr_s[4][4];    // sgn * (r + sgn*eps)^2 ; 4th column pads the row to 16 B
+    float4 row[4][7];
 };
 
-__device__ __forceinline__ void fill_sector_table(const LegPlan& L, SectorTable* tab, int tid,
-                                                  int nthreads) {
-    for (int i = tid; i < 12; i += nthreads) {
-        const int sector = i / 3, j = i % 3;
-        const int upper = sector >> 1, ext = sector & 1;
-        PlanCircle c = L.slot[upper][j];
-        if (ext && L.att_slot[upper] == j) c = L.outer;
-        tab->circle[sector][j] = make_float4(c.cx, c.cy, c.r, c.sgn);
-        tab->thr_s[sector][j] = c.thr_s;
+LRM_HD void fill_sector_table(const LegPlan& L, SectorTable* tab, int tid, int nthreads) {
+    for (int i = tid; i < 28; i += nthreads) {
+        const int s = i / 7, k = i % 7;
+        const float* src = k < 6 ? &L.sector[s].slot[k >> 1][(k & 1) * 4] : L.sector[s].inner_b;
+        tab->row[s][k] = make_float4(src[0], src[1], src[2], src[3]);
     }
 }
 
-__device__ __forceinline__ bool angle_gt(const AngleTest& t, float X, float Y) {
+LRM_HD bool angle_gt(const AngleTest& t, float X, float Y) {
     const float cr = fmaf(t.c, Y, fmaf(t.ns, X, t.bias));
-    const bool up = (__float_as_int(Y) >= 0);  // !signbit(Y)
+    const bool up = (f2i(Y) >= 0);  // !signbit(Y)
     const bool pos = cr > 0.f;
     const bool lower = t.lower != 0;  // uniform; bitwise forms keep this branch-free
     return (up & pos) | (lower & (up | pos));
 }
 
-__device__ __forceinline__ int find_sector(const LegPlan& L, float X, float Y) {
+LRM_HD int find_sector(const LegPlan& L, float X, float Y) {
     const bool upper = angle_gt(L.middle, X, Y);
-    const bool more = upper ? angle_gt(L.sat[1], X, Y) : angle_gt(L.sat[0], X, Y);
+    const bool more0 = angle_gt(L.sat[0], X, Y), more1 = angle_gt(L.sat[1], X, Y);
+    const bool more = upper ? more1 : more0;
     const bool ext = upper != more;  // circles.cu.h:73-74
     return (upper ? 2 : 0) | (ext ? 1 : 0);
 }
 
-// one_leg.cu:65-89 on squared distances: sgn*|P-c|^2 < thr_s
-__device__ __forceinline__ bool circle_ok(float cx, float cy, float sgn, float thr_s, float x,
-                                          float y) {
+// validity of a point against one circle on squared distances (one_leg.cu:31-41):
+// attractive: |v| < r + eps, repulsive: |v| > r - eps
+LRM_HD bool circle_ok(float cx, float cy, float r, float sgn, float x, float y) {
     const float vx = x - cx, vy = y - cy;
-    return sgn * fmaf(vx, vx, vy * vy) < thr_s;
+    const float t = fmaf(sgn, kMarginF, r);
+    return sgn * fmaf(vx, vx, vy * vy) < sgn * t * t;
 }
 
 // eval_plane_circles<REACH_USECASE>, (X, Y) already relative to the femur joint.
-__device__ __forceinline__ bool plane_reach(const LegPlan& L, const SectorTable& tab, float X,
-                                            float Y) {
+LRM_HD bool plane_reach(const LegPlan& L, const SectorTable& tab, float X, float Y) {
     const int s = find_sector(L, X, Y);
     bool ok = L.inner.sgn * fmaf(X, X, Y * Y) < L.inner.thr_s;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        const float4 c = tab.circle[s][j];
-        ok = ok && circle_ok(c.x, c.y, c.w, tab.thr_s[s][j], X, Y);
+        const float4 c = tab.row[s][2 * j];
+        ok = ok & circle_ok(c.x, c.y, c.z, c.w, X, Y);
     }
     return ok;
 }
@@ -79,49 +107,68 @@ struct PlaneResult {
 };
 
 // eval_plane_circles<DIST_USECASE> = insert_circles + insert_intersecv2 + multi_circle_clamp.
-__device__ __forceinline__ PlaneResult plane_clamp(const LegPlan& L, const SectorTable& tab,
-                                                   float X, float Y) {
+// GENERIC = false: projections are validated against the precomputed arcs.
+// GENERIC = true : explicit cross-validation against the other three circles (any leg).
+template <bool GENERIC>
+LRM_HD PlaneResult plane_clamp(const LegPlan& L, const SectorTable& tab, float X, float Y) {
     const int s = find_sector(L, X, Y);
-    float cx[4], cy[4], r[4], sg[4], th[4];
-    cx[0] = 0.f, cy[0] = 0.f, r[0] = L.inner.r, sg[0] = L.inner.sgn, th[0] = L.inner.thr_s;
+    float cx[4], cy[4], r[4], sg[4], ax[4], ay[4], ah[4];
+    cx[0] = 0.f, cy[0] = 0.f, r[0] = L.inner.r, sg[0] = L.inner.sgn;
+    const float4 inner_b = tab.row[s][6];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-        const float4 c = tab.circle[s][j];
+        const float4 c = tab.row[s][2 * j];
+        const float4 a = tab.row[s][2 * j + 1];
         cx[j + 1] = c.x, cy[j + 1] = c.y, r[j + 1] = c.z, sg[j + 1] = c.w;
-        th[j + 1] = tab.thr_s[s][j];
+        ax[j + 1] = a.x, ay[j + 1] = a.y, ah[j + 1] = a.z;
+        if (j == 0) ax[0] = a.w;
+        if (j == 1) ay[0] = a.w;
+        if (j == 2) ah[0] = a.w;
     }
 
-    // project P on each circle (force_clamp_on_circle, one_leg.cu:42-63)
+    // project P on each circle (force_clamp_on_circle, one_leg.cu:42-63); a projection only counts
+    // if it satisfies the other circles (:122-123); the first strictly closer one wins (:133-140)
     float px[4], py[4], d[4];
+    bool cand[4];
     bool valid = true;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         float vx = X - cx[j], vy = Y - cy[j];
         const float m2 = fmaf(vx, vx, vy * vy);
-        float rinv = rsqrtf(m2);
+        float rinv = fast_rsqrt(m2);
         float m = m2 * rinv;
-        if (!(m >= kMarginF)) {  // also catches m2 == 0 (rinv = inf, m = NaN)
+        float len = m;
+        if (!(m >= kMarginF)) {  // P on the centre (also m2 == 0: rinv = inf, m = NaN)
             m = m2 > 0.f ? m : 0.f;
-            vx = 1.f, vy = 0.f, rinv = 1.f;
+            vx = 1.f, vy = 0.f, rinv = 1.f, len = 1.f;
         }
         d[j] = r[j] - m;
-        valid = valid && (sg[j] * d[j] > -kMarginF);  // (d >= 0) == attractive, or |d| < margin
+        valid = valid & (sg[j] * d[j] > -kMarginF);  // (d >= 0) == attractive, or |d| < margin
         const float k = r[j] * rinv;
         px[j] = fmaf(vx, k, cx[j]);
         py[j] = fmaf(vy, k, cy[j]);
+        // direction of the projection inside the valid arc of circle j
+        cand[j] = fmaf(vx, ax[j], vy * ay[j]) >= ah[j] * len;
+        if (j == 0) cand[0] = cand[0] | (fmaf(vx, inner_b.x, vy * inner_b.y) >= inner_b.z * len);
     }
-
-    // a projection only counts if it satisfies the other circles (one_leg.cu:122-123); the
-    // first strictly closer one wins (:133-140)
+    if (GENERIC) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k != j) ok = ok & circle_ok(cx[k], cy[k], r[k], sg[k], px[j], py[j]);
+            cand[j] = ok;
+        }
+    }
     float best_abs = 999999999999999.9f, bx = 0.f, by = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        bool ok = true;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (k != j) ok = ok && circle_ok(cx[k], cy[k], sg[k], th[k], px[j], py[j]);
         const float a = fabsf(d[j]);
-        if (ok && best_abs > a) best_abs = a, bx = px[j], by = py[j];
+        const bool take = cand[j] & (best_abs > a);
+        best_abs = take ? a : best_abs;
+        bx = take ? px[j] : bx;
+        by = take ? py[j] : by;
     }
     // corner points compete only when P itself is outside (one_leg.cu:109-118)
     if (!valid) {
@@ -131,7 +178,10 @@ __device__ __forceinline__ PlaneResult plane_clamp(const LegPlan& L, const Secto
             if (i < L.n_corners) {
                 const float wx = X - L.corner_x[i], wy = Y - L.corner_y[i];
                 const float w2 = fmaf(wx, wx, wy * wy);
-                if (best2 > w2) best2 = w2, bx = L.corner_x[i], by = L.corner_y[i];
+                const bool take = best2 > w2;
+                best2 = take ? w2 : best2;
+                bx = take ? L.corner_x[i] : bx;
+                by = take ? L.corner_y[i] : by;
             }
         }
     }
@@ -146,7 +196,7 @@ struct CoxaPoint {
     float x, y, z;  // point in the coxa frame
 };
 
-__device__ __forceinline__ CoxaPoint to_coxa_frame(const LegPlan& L, float x, float y, float z) {
+LRM_HD CoxaPoint to_coxa_frame(const LegPlan& L, float x, float y, float z) {
     CoxaPoint p;
     p.x = fmaf(L.M[0], x, fmaf(L.M[1], y, fmaf(L.M[2], z, L.t[0])));
     p.y = fmaf(L.M[3], x, fmaf(L.M[4], y, fmaf(L.M[5], z, L.t[1])));
@@ -155,15 +205,29 @@ __device__ __forceinline__ CoxaPoint to_coxa_frame(const LegPlan& L, float x, fl
 }
 
 // reachability_circles, one_leg.cu:280-319
-__device__ __forceinline__ bool reach_coxa_frame(const LegPlan& L, const SectorTable& tab,
-                                                 const CoxaPoint p) {
-    const bool flip = __float_as_int(p.x) < 0;  // signbit: mirrored through the coxa axis
+LRM_HD bool reach_coxa_frame(const LegPlan& L, const SectorTable& tab, const CoxaPoint p) {
+    const bool flip = f2i(p.x) < 0;  // signbit: mirrored through the coxa axis
     const float xf = flip ? -p.x : p.x;
     const float yf = flip ? -p.y : p.y;
-    if (angle_gt(L.over, xf, yf) || angle_gt(L.under, xf, -yf)) return false;
-    const float rho = sqrtf(fmaf(p.x, p.x, p.y * p.y));
+    if (angle_gt(L.over, xf, yf) | angle_gt(L.under, xf, -yf)) return false;
+    const float rho2 = fmaf(p.x, p.x, p.y * p.y);
+    const float rho = rho2 > 0.f ? rho2 * fast_rsqrt(rho2) : 0.f;
     const float X = (flip ? -rho : rho) - L.coxa_length;
     return plane_reach(L, tab, X, p.z);
+}
+
+// The yaw tests of finish_finding_closest (one_leg.cu:222-234) for the solution whose yaw is the
+// angle of (wx, wy).
+struct YawFlags {
+    bool mega, over, under, upper_lim;
+};
+LRM_HD YawFlags yaw_tests(const LegPlan& L, float wx, float wy) {
+    YawFlags f;
+    f.mega = angle_gt(L.mega_hi, wx, wy) | angle_gt(L.mega_lo, wx, -wy);
+    f.over = angle_gt(L.over, wx, wy);
+    f.under = angle_gt(L.under, wx, -wy);
+    f.upper_lim = angle_gt(L.mid, wx, wy);
+    return f;
 }
 
 struct BranchResult {
@@ -172,47 +236,39 @@ struct BranchResult {
     float n2;          // its squared norm
 };
 
-// finish_finding_closest<bool>, one_leg.cu:215-278, for the coxa solution whose yaw is the angle
-// of (wx, wy): (wx, wy) = (x, y) for the direct solution, (-x, 0 - y) for the flipped one.
-__device__ __forceinline__ BranchResult closest_for_branch(const LegPlan& L, const SectorTable& tab,
-                                                           const CoxaPoint p, float wx, float wy,
-                                                           float inv_rho) {
-    const bool mega = angle_gt(L.mega_hi, wx, wy) || angle_gt(L.mega_lo, wx, -wy);
-    const bool over = angle_gt(L.over, wx, wy);
-    const bool under = angle_gt(L.under, wx, -wy);
+// finish_finding_closest<bool>, one_leg.cu:215-278, for one coxa solution.
+// (ux, uy) = unit vector of the solution's un-saturated yaw (w / rho).
+template <bool GENERIC>
+LRM_HD BranchResult closest_for_branch(const LegPlan& L, const SectorTable& tab, const CoxaPoint p,
+                                       const YawFlags f, float ux, float uy) {
     // unit direction of the saturated yaw
-    float cs = wx * inv_rho, ss = wy * inv_rho;
-    if (inv_rho == 0.f) cs = 1.f, ss = 0.f;  // point on the coxa axis: yaw 0
-    if (mega) {
-        cs = -cs, ss = -ss;  // yaw -+ pi
-    } else if (under) {
+    float cs = ux, ss = uy;
+    if (f.mega) {
+        cs = -ux, ss = -uy;  // yaw -+ pi
+    } else if (f.under) {
         cs = L.cos_min, ss = L.sin_min;
-    } else if (over) {
+    } else if (f.over) {
         cs = L.cos_max, ss = L.sin_max;
     }
-    const bool saturated = mega || over || under;
+    const bool saturated = f.mega | f.over | f.under;
     const float xr = fmaf(p.x, cs, p.y * ss);
     const float yr = fmaf(p.y, cs, -p.x * ss);
 
-    const PlaneResult pl = plane_clamp(L, tab, xr - L.coxa_length, p.z);
-    float ux = pl.dx, uy = yr, uz = pl.dy;  // in the saturated-yaw frame
-    float n2 = fmaf(ux, ux, fmaf(uy, uy, uz * uz));
+    const PlaneResult pl = plane_clamp<GENERIC>(L, tab, xr - L.coxa_length, p.z);
+    const float qx = pl.dx, qy = yr, qz = pl.dy;  // in the saturated-yaw frame
+    const float n2 = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
 
     BranchResult out;
-    out.res = pl.valid && !saturated;
+    out.res = pl.valid & !saturated;
     // in-plane region reached but a coxa-limit half-plane is nearer (one_leg.cu:258-274)
-    const bool upper_lim = angle_gt(L.mid, wx, wy);
-    const float cl = upper_lim ? L.cos_max : L.cos_min;
-    const float sl = upper_lim ? L.sin_max : L.sin_min;
+    const float cl = f.upper_lim ? L.cos_max : L.cos_min;
+    const float sl = f.upper_lim ? L.sin_max : L.sin_min;
     const float yl = fmaf(p.y, cl, -p.x * sl);
-    if (pl.valid && !mega && n2 > yl * yl) {
-        out.vx = -yl * sl, out.vy = yl * cl, out.vz = 0.f, out.n2 = yl * yl;
-    } else {
-        out.vx = fmaf(ux, cs, -uy * ss);
-        out.vy = fmaf(ux, ss, uy * cs);
-        out.vz = uz;
-        out.n2 = n2;
-    }
+    const bool to_plane = pl.valid & !f.mega & (n2 > yl * yl);
+    out.vx = to_plane ? -yl * sl : fmaf(qx, cs, -qy * ss);
+    out.vy = to_plane ? yl * cl : fmaf(qx, ss, qy * cs);
+    out.vz = to_plane ? 0.f : qz;
+    out.n2 = to_plane ? yl * yl : n2;
     return out;
 }
 
@@ -223,19 +279,34 @@ struct DistResult {
 };
 
 // distance_circles (one_leg.cu:321-341) + the way back to the world frame.
-__device__ __forceinline__ DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab,
-                                                      const CoxaPoint p) {
+template <bool GENERIC>
+LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, const CoxaPoint p) {
     const float rho2 = fmaf(p.x, p.x, p.y * p.y);
-    const float inv_rho = rho2 > 0.f ? rsqrtf(rho2) : 0.f;
-    const BranchResult a = closest_for_branch(L, tab, p, p.x, p.y, inv_rho);
+    const float inv_rho = rho2 > 0.f ? fast_rsqrt(rho2) : 0.f;
+    // unit vector of the direct yaw; a point on the coxa axis has yaw 0 (atan2f(0, 0))
+    const float ux = rho2 > 0.f ? p.x * inv_rho : 1.f;
+    const float uy = rho2 > 0.f ? p.y * inv_rho : 0.f;
     // flipped yaw = yaw -+ pi: the angle of (-x, -y); "0 - y" keeps atan2f's +pi (not -pi) for
     // y = +0, x > 0, like coxangle + pi does in the reference (one_leg.cu:329)
-    const BranchResult b = closest_for_branch(L, tab, p, -p.x, 0.f - p.y, inv_rho);
+    const YawFlags fa = yaw_tests(L, p.x, p.y);
+    const YawFlags fb = yaw_tests(L, -p.x, 0.f - p.y);
+    // A solution beyond limit +- pi/2 is evaluated in the plane of the OTHER solution's yaw
+    // (one_leg.cu:225-226).  When that other solution is unsaturated both plane evaluations are
+    // identical and the mega one can never be preferred (it reports res = false and the same
+    // vector unless the other one found something nearer), so it is skipped.
+    const bool skip_a = fa.mega & !(fb.mega | fb.over | fb.under);
+    const bool skip_b = fb.mega & !(fa.mega | fa.over | fa.under);
+    BranchResult a, b;
+    a.res = b.res = false, a.vx = a.vy = a.vz = b.vx = b.vy = b.vz = 0.f, a.n2 = b.n2 = 0.f;
+    if (!skip_a) a = closest_for_branch<GENERIC>(L, tab, p, fa, ux, uy);
+    if (!skip_b) b = closest_for_branch<GENERIC>(L, tab, p, fb, -ux, -uy);
+    if (skip_a) a = b, a.res = false;
+    if (skip_b) b = a, b.res = false;
     const bool direct = (a.res == b.res) ? (a.n2 < b.n2) : a.res;
     const float vx = direct ? a.vx : b.vx, vy = direct ? a.vy : b.vy, vz = direct ? a.vz : b.vz;
     DistResult out;
-    out.flag = a.res || b.res;
-    out.reach = (__float_as_int(p.x) < 0) ? b.res : a.res;
+    out.flag = a.res | b.res;
+    out.reach = (f2i(p.x) < 0) ? b.res : a.res;
     out.dx = fmaf(L.Mo[0], vx, fmaf(L.Mo[1], vy, L.Mo[2] * vz));
     out.dy = fmaf(L.Mo[3], vx, fmaf(L.Mo[4], vy, L.Mo[5] * vz));
     out.dz = fmaf(L.Mo[6], vx, fmaf(L.Mo[7], vy, L.Mo[8] * vz));

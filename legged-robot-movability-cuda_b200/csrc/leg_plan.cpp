@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 namespace lrm {
 
@@ -174,6 +175,119 @@ void fill_planar(const lrm_leg_t& l, LegPlan* p) {
     }
 }
 
+// ---- valid arcs -------------------------------------------------------------------------------
+// For circle j of a sector: which directions phi around its centre put the point
+// c_j + r_j (cos phi, sin phi) inside every OTHER constraint of the sector?  Breakpoints are the
+// intersections with the other circles at their margin-adjusted radii; each elementary interval is
+// classified by testing its midpoint.  Returns the number of maximal valid arcs and the first one.
+struct Arc {
+    double lo, hi;  // hi > lo, hi - lo <= 2 pi
+};
+bool constraint_ok(const PlanCircle& k, double x, double y) {
+    const double dx = x - k.cx, dy = y - k.cy, m = std::sqrt(dx * dx + dy * dy);
+    return k.sgn > 0 ? (m < (double)k.r + kCircleMargin) : (m > (double)k.r - kCircleMargin);
+}
+int valid_arcs(const PlanCircle* set, int j, Arc* first /* room for 2 */) {
+    const PlanCircle& c = set[j];
+    std::vector<double> brk;
+    for (int k = 0; k < 4; k++) {
+        if (k == j) continue;
+        const double R = (double)set[k].r + (set[k].sgn > 0 ? kCircleMargin : -kCircleMargin);
+        const double dx = (double)set[k].cx - c.cx, dy = (double)set[k].cy - c.cy;
+        const double d = std::sqrt(dx * dx + dy * dy), r = c.r;
+        if (d <= 0 || R <= 0 || r <= 0) continue;
+        const double cosb = (r * r + d * d - R * R) / (2 * r * d);
+        if (cosb <= -1 || cosb >= 1) continue;
+        const double a = std::atan2(dy, dx), b = std::acos(cosb);
+        brk.push_back(a + b);
+        brk.push_back(a - b);
+    }
+    auto ok_at = [&](double phi) {
+        const double x = c.cx + (double)c.r * std::cos(phi), y = c.cy + (double)c.r * std::sin(phi);
+        for (int k = 0; k < 4; k++)
+            if (k != j && !constraint_ok(set[k], x, y)) return false;
+        return true;
+    };
+    if (brk.empty()) {
+        if (!ok_at(0.0)) return 0;
+        first->lo = 0, first->hi = 2 * M_PI;
+        return 1;
+    }
+    for (double& b : brk) {
+        b = std::fmod(b, 2 * M_PI);
+        if (b < 0) b += 2 * M_PI;
+    }
+    std::sort(brk.begin(), brk.end());
+    const size_t n = brk.size();
+    std::vector<char> good(n);
+    for (size_t i = 0; i < n; i++) {
+        const double lo = brk[i], hi = (i + 1 < n) ? brk[i + 1] : brk[0] + 2 * M_PI;
+        good[i] = ok_at(0.5 * (lo + hi)) ? 1 : 0;
+    }
+    // merge circularly: count starts of valid runs
+    int arcs = 0;
+    bool all = true;
+    for (size_t i = 0; i < n; i++) all = all && good[i];
+    if (all) {
+        first->lo = 0, first->hi = 2 * M_PI;
+        return 1;
+    }
+    for (size_t i = 0; i < n; i++) {
+        if (good[i] && !good[(i + n - 1) % n]) {
+            if (arcs < 2) {
+                size_t e = i;
+                while (good[(e + 1) % n]) e = (e + 1) % n;
+                first[arcs].lo = brk[i];
+                first[arcs].hi = brk[(e + 1) % n];
+                if (first[arcs].hi <= first[arcs].lo) first[arcs].hi += 2 * M_PI;
+            }
+            arcs++;
+        }
+    }
+    return arcs;
+}
+
+void fill_sector_rows(LegPlan* p) {
+    p->generic = 0;
+    for (int s = 0; s < 4; s++) {
+        const int upper = s >> 1, ext = s & 1;
+        PlanCircle set[4];
+        set[0] = p->inner;
+        for (int j = 0; j < 3; j++) {
+            set[j + 1] = p->slot[upper][j];
+            if (ext && p->att_slot[upper] == j) set[j + 1] = p->outer;
+        }
+        // arcs: [circle][0..1] -> (ax, ay, ah); only the inner circle may need two
+        float arc[4][2][3];
+        for (int j = 0; j < 4; j++) {
+            Arc a[2] = {{0, 0}, {0, 0}};
+            const int n = valid_arcs(set, j, a);
+            if (n > (j == 0 ? 2 : 1)) p->generic = 1;
+            for (int k = 0; k < 2; k++) {
+                if (k >= n) {
+                    arc[j][k][0] = 1.f, arc[j][k][1] = 0.f, arc[j][k][2] = 2.f;  // empty
+                    continue;
+                }
+                const double mid = 0.5 * (a[k].lo + a[k].hi), half = 0.5 * (a[k].hi - a[k].lo);
+                arc[j][k][0] = (float)std::cos(mid), arc[j][k][1] = (float)std::sin(mid);
+                arc[j][k][2] = half >= M_PI ? -2.f : (float)std::cos(half);
+            }
+        }
+        for (int j = 0; j < 3; j++) {
+            float* o = p->sector[s].slot[j];
+            const PlanCircle& c = set[j + 1];
+            o[0] = c.cx, o[1] = c.cy, o[2] = c.r, o[3] = c.sgn;
+            o[4] = arc[j + 1][0][0], o[5] = arc[j + 1][0][1], o[6] = arc[j + 1][0][2];
+            o[7] = arc[0][0][j];  // inner circle's first arc rides in the spare column
+        }
+        for (int k = 0; k < 3; k++) p->sector[s].inner_b[k] = arc[0][1][k];
+        p->sector[s].inner_b[3] = 0.f;
+    }
+    auto plain = [](const AngleTest& t) { return t.bias == 0.f && t.lower == 0; };
+    p->std_coxa = plain(p->over) && plain(p->under) && plain(p->mega_hi) && plain(p->mega_lo) &&
+                  plain(p->mid);
+}
+
 void store(const Mat3& m, float* out) {
     for (int i = 0; i < 9; i++) out[i] = (float)m.m[i];
 }
@@ -257,6 +371,7 @@ static void build_common(const lrm_leg_t& leg, const float* quat, bool points_in
     o.tibia_absolute_pos -= pitch;
     o.tibia_absolute_neg -= pitch;
     fill_planar(o, out);
+    fill_sector_rows(out);
 
     float qi[4];
     quat_invert(q, qi);

@@ -34,6 +34,19 @@ struct PlanCircle {
 
 constexpr int kMaxCorners = 10;
 
+// One row of the 4-sector table the kernels stage in shared memory (sector = upper*2 + ext).
+// Per slot j = 1..3 eight floats: cx, cy, r, sgn, ax, ay, ah, spare.
+//   (ax, ay, ah): the part of circle j that satisfies the OTHER circles of the sector (the
+//   cross-validation of multi_circle_clamp, one_leg.cu:122-123) is an arc, stored as its bisector
+//   direction and the cosine of its half-angle:  projection valid  <=>  (P-c).(ax,ay) >= ah*|P-c|
+//   (ah = 2: never, ah = -2: always).
+//   spare of slots 1,2,3: the same three numbers for the inner circle (slot 0) of this sector,
+//   whose valid set can consist of two arcs; inner_b holds the second one (empty: ah = 2).
+struct SectorRow {
+    float slot[3][8];
+    float inner_b[4];
+};
+
 struct LegPlan {
     // world point -> coxa frame (qtInvRotate, Rz(-body_angle), x -= body, Ry(-coxa_pitch):
     // one_leg_global.cu:88-95,119-127, one_leg.cu:9-24) as one affine map p' = M p + t
@@ -66,6 +79,12 @@ struct LegPlan {
     PlanCircle outer;          // attractive form of the outer circle
     PlanCircle slot[2][3];     // [UpperRegion][slot-1]
     int32_t att_slot[2];       // which of slot[u][0..2] is the attractive one
+
+    // host-built shared-memory table (see SectorRow) + whether every valid set is a single arc;
+    // if not (exotic leg), the kernels fall back to explicit cross-validation (generic != 0).
+    SectorRow sector[4];
+    int32_t generic;
+    int32_t std_coxa;  // all five coxa yaw tests are the plain "upper, no bias" form
 
     // corner points of the planar workspace (insert_intersecv2, circles.cu.h:417-476), in
     // emission order (ties keep the earlier candidate, one_leg.cu:133)

@@ -35,7 +35,7 @@ struct alignas(128) StreamSmem {
     alignas(8) uint64_t full[kStages];
 };
 
-template <int MODE, bool SOA>
+template <int MODE, bool SOA, bool GENERIC>
 __device__ __forceinline__ void compute_point(const LegPlan& L, const SectorTable& tab,
                                               const float* in, float* vec, uint8_t* flag, int i,
                                               int stride_pts) {
@@ -49,7 +49,7 @@ __device__ __forceinline__ void compute_point(const LegPlan& L, const SectorTabl
     if (MODE == kModeReach) {
         flag[i] = reach_coxa_frame(L, tab, p) ? 1 : 0;
     } else {
-        const DistResult r = dist_coxa_frame(L, tab, p);
+        const DistResult r = dist_coxa_frame<GENERIC>(L, tab, p);
         if (SOA) {
             vec[i] = r.dx, vec[stride_pts + i] = r.dy, vec[2 * stride_pts + i] = r.dz;
         } else {
@@ -61,7 +61,7 @@ __device__ __forceinline__ void compute_point(const LegPlan& L, const SectorTabl
 }
 
 // AoS: in_x = xyz (N x 3), out_x = vectors (N x 3).  SoA: separate planes.
-template <int MODE, bool SOA>
+template <int MODE, bool SOA, bool GENERIC>
 __global__ void __launch_bounds__(kThreads)
     one_leg_stream_kernel(const __grid_constant__ LegPlan L, const float* __restrict__ in_x,
                           const float* __restrict__ in_y, const float* __restrict__ in_z,
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kThreads)
         uint8_t* flag = S.flag[ob];
 #pragma unroll 1
         for (int i = tid; i < (int)cnt; i += kThreads)
-            compute_point<MODE, SOA>(L, S.table, in, vec, flag, i, kTile);
+            compute_point<MODE, SOA, GENERIC>(L, S.table, in, vec, flag, i, kTile);
 
         bulk::fence_proxy_async();  // results written through the generic proxy -> bulk engine
         if (tid == 0) bulk::wait_group_read<0>();  // previous tile's store has drained its buffer
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads)
             } else {
                 xyz[0] = in_x[3 * i], xyz[1] = in_x[3 * i + 1], xyz[2] = in_x[3 * i + 2];
             }
-            compute_point<MODE, false>(L, S.table, xyz, v, &f, 0, 0);
+            compute_point<MODE, false, GENERIC>(L, S.table, xyz, v, &f, 0, 0);
             if (kVec) {
                 if (SOA) {
                     out_x[i] = v[0], out_y[i] = v[1], out_z[i] = v[2];
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kThreads)
 
 // Same math with plain per-thread global accesses: used when a caller's buffers are not 16-byte
 // aligned (the bulk engine's requirement) — still the GPU path, just without staging.
-template <int MODE>
+template <int MODE, bool GENERIC>
 __global__ void __launch_bounds__(kThreads)
     one_leg_plain_kernel(const __grid_constant__ LegPlan L, const float* __restrict__ xyz,
                          float* __restrict__ out_vec, uint8_t* __restrict__ out_flag, size_t n) {
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kThreads)
         float p[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
         float v[3];
         uint8_t f;
-        compute_point<MODE, false>(L, table, p, v, &f, 0, 0);
+        compute_point<MODE, false, GENERIC>(L, table, p, v, &f, 0, 0);
         if (MODE & kModeDist) {
             out_vec[3 * i] = v[0], out_vec[3 * i + 1] = v[1], out_vec[3 * i + 2] = v[2];
         }
@@ -237,22 +237,25 @@ int sm_count() {
     return g_sm_count;
 }
 
-template <int MODE, bool SOA>
-cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy, const float* iz,
+template <int MODE, bool SOA, bool GENERIC>
+cudaError_t launch_stream_impl(const LegPlan& plan, const float* ix, const float* iy, const float* iz,
                           float* ox, float* oy, float* oz, uint8_t* flag, size_t n,
                           cudaStream_t stream) {
-    auto kernel = one_leg_stream_kernel<MODE, SOA>;
+    auto kernel = one_leg_stream_kernel<MODE, SOA, GENERIC>;
     constexpr size_t smem = sizeof(StreamSmem<MODE>) + 128;
-    static bool configured = false;
-    static int ctas_per_sm = 1;
-    if (!configured) {
+    // per-device: the attribute belongs to the device's copy of the function
+    static int ctas_per_sm_dev[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& ctas_per_sm = ctas_per_sm_dev[dev & 63];
+    if (ctas_per_sm == 0) {
         cudaError_t e =
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kThreads, smem);
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem);
         if (e != cudaSuccess) return e;
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-        configured = true;
+        ctas_per_sm = occ < 1 ? 1 : occ;
     }
     const size_t tiles = ((n & ~size_t(15)) + kTile - 1) / kTile;
     size_t grid = (size_t)sm_count() * ctas_per_sm;
@@ -262,6 +265,17 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
     return cudaGetLastError();
 }
 
+// reach-only never cross-validates, so only the distance modes have a generic instantiation
+template <int MODE, bool SOA>
+cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy, const float* iz,
+                          float* ox, float* oy, float* oz, uint8_t* flag, size_t n,
+                          cudaStream_t stream) {
+    if (MODE != kModeReach && plan.generic)
+        return launch_stream_impl<MODE, SOA, MODE != kModeReach>(plan, ix, iy, iz, ox, oy, oz, flag,
+                                                                 n, stream);
+    return launch_stream_impl<MODE, SOA, false>(plan, ix, iy, iz, ox, oy, oz, flag, n, stream);
+}
+
 template <int MODE>
 cudaError_t launch_plain(const LegPlan& plan, const float* xyz, float* out_vec, uint8_t* flag,
                          size_t n, cudaStream_t stream) {
@@ -269,7 +283,12 @@ cudaError_t launch_plain(const LegPlan& plan, const float* xyz, float* out_vec, 
     const size_t cap = (size_t)sm_count() * 16;
     if (grid > cap) grid = cap;
     if (grid == 0) grid = 1;
-    one_leg_plain_kernel<MODE><<<(unsigned)grid, kThreads, 0, stream>>>(plan, xyz, out_vec, flag, n);
+    if (MODE != kModeReach && plan.generic)
+        one_leg_plain_kernel<MODE, MODE != kModeReach>
+            <<<(unsigned)grid, kThreads, 0, stream>>>(plan, xyz, out_vec, flag, n);
+    else
+        one_leg_plain_kernel<MODE, false>
+            <<<(unsigned)grid, kThreads, 0, stream>>>(plan, xyz, out_vec, flag, n);
     return cudaGetLastError();
 }
 

@@ -436,17 +436,7 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
 
     // sector tables are derived from the plans on the host so the kernel can index them directly
     std::vector<SectorTable> tables(plans.size());
-    for (size_t i = 0; i < plans.size(); i++) {
-        const LegPlan& L = plans[i];
-        for (int s = 0; s < 4; s++)
-            for (int j = 0; j < 3; j++) {
-                const int upper = s >> 1, ext = s & 1;
-                PlanCircle c = L.slot[upper][j];
-                if (ext && L.att_slot[upper] == j) c = L.outer;
-                tables[i].circle[s][j] = make_float4(c.cx, c.cy, c.r, c.sgn);
-                tables[i].thr_s[s][j] = c.thr_s;
-            }
-    }
+    for (size_t i = 0; i < plans.size(); i++) fill_sector_table(plans[i], &tables[i], 0, 1);
     OrientConsts* d_orient;
     LegPlan* d_plans;
     SectorTable* d_tables;

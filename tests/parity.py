@@ -6,7 +6,8 @@ and reported; distance vectors within 1e-5 m (= 1e-2 mm) absolute.  The referenc
 field is piecewise: at a sector switch, a direct/flipped-coxa switch or a
 nearest-candidate switch the vector jumps, so a point sitting on such a seam is classified
 separately: it is accepted when the oracle itself produces the GPU's vector somewhere within
-1e-3 mm of the point.
+1e-3 mm of the point, or when the GPU's vector has the reference's length (within tolerance) and
+ends on the reachability edge (an equally-near boundary point: a tie).
 """
 import itertools
 
@@ -45,10 +46,24 @@ def dist_report(pts, got, want, dist_fn, tol=DIST_TOL_MM):
     bad = np.nonzero(~(err <= tol))[0]
     unexplained = 0
     if len(bad):
-        nb = _neighbours(pts[bad], FLAG_BAND_MM)
-        vec = np.asarray(dist_fn(nb.reshape(-1, 3))).reshape(len(bad), -1, 3)
-        close = (np.abs(vec.astype(np.float64) - np.asarray(got, np.float64)[bad][:, None, :]).max(axis=2)
-                 <= tol + 2 * FLAG_BAND_MM).any(axis=1)
+        g = np.asarray(got, np.float64)[bad]
+        close = np.zeros(len(bad), bool)
+        for radius in (FLAG_BAND_MM, FLAG_BAND_MM / 4, FLAG_BAND_MM / 16):
+            nb = _neighbours(pts[bad], radius)
+            vec = np.asarray(dist_fn(nb.reshape(-1, 3))).reshape(len(bad), -1, 3)
+            close |= (np.abs(vec.astype(np.float64) - g[:, None, :]).max(axis=2)
+                      <= tol + 2 * FLAG_BAND_MM).any(axis=1)
+        # a tie: the GPU vector has the reference's length and ends on the reachability edge, i.e. it
+        # points at another boundary point that is equally near (within tol)
+        same_len = np.abs(np.linalg.norm(g, axis=1) -
+                          np.linalg.norm(np.asarray(want, np.float64)[bad], axis=1)) <= tol
+        landing = (pts[bad].astype(np.float64) - g).astype(np.float32)
+        land_err = np.linalg.norm(np.asarray(dist_fn(landing), np.float64), axis=1)
+        # yardstick: how well the reference's own vector lands (exactly, unless the caller's
+        # quaternion is not unit length, in which case the reference's frames are not isometric)
+        ref_landing = (pts[bad].astype(np.float64) - np.asarray(want, np.float64)[bad]).astype(np.float32)
+        ref_err = np.linalg.norm(np.asarray(dist_fn(ref_landing), np.float64), axis=1)
+        close |= same_len & (land_err <= np.maximum(tol, 1.5 * ref_err))
         unexplained = int((~close).sum())
     ok = err[np.isfinite(err) & (err <= tol)]
     return {"n": int(len(err)), "over_tol": int(len(bad)), "seam": int(len(bad)) - unexplained,

