@@ -65,17 +65,20 @@ LRM_HD void fill_sector_table(const LegPlan& L, SectorTable* tab, int tid, int n
     }
 }
 
-LRM_HD bool angle_gt(const AngleTest& t, float X, float Y) {
+// 1.0f when atan2f(Y, .) lies in [0, pi] (sign bit of Y clear), else 0.0f
+LRM_HD float up_flag(float Y) { return f2i(Y) >= 0 ? 1.f : 0.f; }
+
+// atan2f(Y, X) > theta, see AngleTest: 3 FFMA + 1 FSETP, no predicate logic
+LRM_HD bool angle_gt(const AngleTest& t, float X, float Y, float upf) {
     const float cr = fmaf(t.c, Y, fmaf(t.ns, X, t.bias));
-    const bool up = (f2i(Y) >= 0);  // !signbit(Y)
-    const bool pos = cr > 0.f;
-    const bool lower = t.lower != 0;  // uniform; bitwise forms keep this branch-free
-    return (up & pos) | (lower & (up | pos));
+    return cr > fmaf(upf, -kAngleBig, t.thr_dn);
 }
+LRM_HD bool angle_gt(const AngleTest& t, float X, float Y) { return angle_gt(t, X, Y, up_flag(Y)); }
 
 LRM_HD int find_sector(const LegPlan& L, float X, float Y) {
-    const bool upper = angle_gt(L.middle, X, Y);
-    const bool more0 = angle_gt(L.sat[0], X, Y), more1 = angle_gt(L.sat[1], X, Y);
+    const float upf = up_flag(Y);
+    const bool upper = angle_gt(L.middle, X, Y, upf);
+    const bool more0 = angle_gt(L.sat[0], X, Y, upf), more1 = angle_gt(L.sat[1], X, Y, upf);
     const bool more = upper ? more1 : more0;
     const bool ext = upper != more;  // circles.cu.h:73-74
     return (upper ? 2 : 0) | (ext ? 1 : 0);
@@ -138,7 +141,7 @@ LRM_HD PlaneResult plane_clamp(const LegPlan& L, const SectorTable& tab, float X
         float rinv = fast_rsqrt(m2);
         float m = m2 * rinv;
         float len = m;
-        if (!(m >= kMarginF)) {  // P on the centre (also m2 == 0: rinv = inf, m = NaN)
+        if (__builtin_expect(!(m >= kMarginF), 0)) {  // P on the centre (m2 == 0: m = NaN)
             m = m2 > 0.f ? m : 0.f;
             vx = 1.f, vy = 0.f, rinv = 1.f, len = 1.f;
         }
@@ -209,7 +212,7 @@ LRM_HD bool reach_coxa_frame(const LegPlan& L, const SectorTable& tab, const Cox
     const bool flip = f2i(p.x) < 0;  // signbit: mirrored through the coxa axis
     const float xf = flip ? -p.x : p.x;
     const float yf = flip ? -p.y : p.y;
-    if (angle_gt(L.over, xf, yf) | angle_gt(L.under, xf, -yf)) return false;
+    if (angle_gt(L.over, xf, yf) | angle_gt(L.under, xf, -yf)) return false;  // outside the yaw limits
     const float rho2 = fmaf(p.x, p.x, p.y * p.y);
     const float rho = rho2 > 0.f ? rho2 * fast_rsqrt(rho2) : 0.f;
     const float X = (flip ? -rho : rho) - L.coxa_length;
@@ -221,13 +224,30 @@ LRM_HD bool reach_coxa_frame(const LegPlan& L, const SectorTable& tab, const Cox
 struct YawFlags {
     bool mega, over, under, upper_lim;
 };
-LRM_HD YawFlags yaw_tests(const LegPlan& L, float wx, float wy) {
-    YawFlags f;
-    f.mega = angle_gt(L.mega_hi, wx, wy) | angle_gt(L.mega_lo, wx, -wy);
-    f.over = angle_gt(L.over, wx, wy);
-    f.under = angle_gt(L.under, wx, -wy);
-    f.upper_lim = angle_gt(L.mid, wx, wy);
-    return f;
+
+// Both coxa solutions at once.  The direct one has yaw = angle of (x, y), the flipped one
+// yaw -+ pi = angle of (-x, 0 - y) ("0 - y" keeps atan2f's +pi, not -pi, for y = +0, x > 0, like
+// coxangle + pi does in the reference, one_leg.cu:329).  For a test with cross product
+// ip = c*Y + ns*X the flipped solution sees -ip, so each inner product is shared:
+//   direct:  ip + bias > thr(up)      <=>  ip >  thr(up_d) - bias
+//   flipped: bias - ip > thr(up)      <=>  ip <  bias - thr(up_f)
+LRM_HD void yaw_pair(const AngleTest& t, float ip, float up_d, float up_f, bool& d, bool& f) {
+    const float k = t.thr_dn - t.bias;  // uniform
+    d = ip > fmaf(up_d, -kAngleBig, k);
+    f = ip < fmaf(up_f, kAngleBig, -k);
+}
+LRM_HD void yaw_tests_both(const LegPlan& L, float x, float y, YawFlags& a, YawFlags& b) {
+    const float yf = 0.f - y;
+    // "greater" tests look at (X, Y), "less" tests at (X, -Y)
+    const float up_d = up_flag(y), up_dn = up_flag(-y);
+    const float up_f = up_flag(yf), up_fn = up_flag(-yf);
+    bool hi_d, hi_f, lo_d, lo_f;
+    yaw_pair(L.mega_hi, fmaf(L.mega_hi.c, y, L.mega_hi.ns * x), up_d, up_f, hi_d, hi_f);
+    yaw_pair(L.mega_lo, fmaf(L.mega_lo.c, -y, L.mega_lo.ns * x), up_dn, up_fn, lo_d, lo_f);
+    a.mega = hi_d | lo_d, b.mega = hi_f | lo_f;
+    yaw_pair(L.over, fmaf(L.over.c, y, L.over.ns * x), up_d, up_f, a.over, b.over);
+    yaw_pair(L.under, fmaf(L.under.c, -y, L.under.ns * x), up_dn, up_fn, a.under, b.under);
+    yaw_pair(L.mid, fmaf(L.mid.c, y, L.mid.ns * x), up_d, up_f, a.upper_lim, b.upper_lim);
 }
 
 struct BranchResult {
@@ -286,10 +306,8 @@ LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, cons
     // unit vector of the direct yaw; a point on the coxa axis has yaw 0 (atan2f(0, 0))
     const float ux = rho2 > 0.f ? p.x * inv_rho : 1.f;
     const float uy = rho2 > 0.f ? p.y * inv_rho : 0.f;
-    // flipped yaw = yaw -+ pi: the angle of (-x, -y); "0 - y" keeps atan2f's +pi (not -pi) for
-    // y = +0, x > 0, like coxangle + pi does in the reference (one_leg.cu:329)
-    const YawFlags fa = yaw_tests(L, p.x, p.y);
-    const YawFlags fb = yaw_tests(L, -p.x, 0.f - p.y);
+    YawFlags fa, fb;
+    yaw_tests_both(L, p.x, p.y, fa, fb);
     // A solution beyond limit +- pi/2 is evaluated in the plane of the OTHER solution's yaw
     // (one_leg.cu:225-226).  When that other solution is unsaturated both plane evaluations are
     // identical and the mega one can never be preferred (it reports res = false and the same

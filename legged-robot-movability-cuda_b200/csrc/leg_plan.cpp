@@ -62,6 +62,7 @@ AngleTest make_angle_gt(double theta) {
         t.bias = 0;
         t.lower = theta < 0 ? 1u : 0u;
     }
+    t.thr_dn = t.lower ? 0.f : kAngleBig;
     return t;
 }
 AngleTest make_angle_lt(double theta) { return make_angle_gt(-theta); }  // apply to (X, -Y)

@@ -19,9 +19,14 @@ namespace lrm {
 //   theta in [0, pi):  up && cr > 0        theta in [-pi, 0):  up || cr > 0
 // bias is 0 except for thresholds outside (-pi, pi): always-true / always-false.
 // "angle < theta" is built as  atan2f(-Y, X) > -theta  (atan2f is odd in Y, signed zeros included).
+// Branch-free device form:  cr > thr  with  thr = thr_dn - up * kAngleBig, where
+//   thr_dn = kAngleBig for the first kind (so thr = 0 when up, +big otherwise) and
+//   thr_dn = 0         for the second     (so thr = -big when up, 0 otherwise).
+constexpr float kAngleBig = 1.0e30f;
 struct AngleTest {
     float c, ns, bias;
     uint32_t lower;
+    float thr_dn;
 };
 
 // Circle in the femur plane with its validity rule folded into one compare:

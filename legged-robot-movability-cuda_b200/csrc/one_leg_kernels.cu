@@ -67,9 +67,10 @@ __global__ void __launch_bounds__(kThreads)
                           const float* __restrict__ in_y, const float* __restrict__ in_z,
                           float* __restrict__ out_x, float* __restrict__ out_y,
                           float* __restrict__ out_z, uint8_t* __restrict__ out_flag, size_t n) {
-    extern __shared__ unsigned char smem_raw[];
-    auto& S = *reinterpret_cast<StreamSmem<MODE>*>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    // keep the pointer provably in the shared window (LDS/STS, not generic LD/ST): no integer
+    // round-trip on the address; the bulk engine only needs 16-byte alignment
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    auto& S = *reinterpret_cast<StreamSmem<MODE>*>(smem_raw);
     const int tid = threadIdx.x;
 
     const size_t n_bulk = n & ~size_t(15);  // points that move through the bulk engine
@@ -242,7 +243,7 @@ cudaError_t launch_stream_impl(const LegPlan& plan, const float* ix, const float
                           float* ox, float* oy, float* oz, uint8_t* flag, size_t n,
                           cudaStream_t stream) {
     auto kernel = one_leg_stream_kernel<MODE, SOA, GENERIC>;
-    constexpr size_t smem = sizeof(StreamSmem<MODE>) + 128;
+    constexpr size_t smem = sizeof(StreamSmem<MODE>);
     // per-device: the attribute belongs to the device's copy of the function
     static int ctas_per_sm_dev[64] = {0};
     int dev = 0;

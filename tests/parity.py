@@ -39,7 +39,7 @@ def flag_report(pts, got, want, reach_fn):
             "unexplained": unexplained}
 
 
-def dist_report(pts, got, want, dist_fn, tol=DIST_TOL_MM):
+def dist_report(pts, got, want, dist_fn, tol=DIST_TOL_MM, frame_slack=0.0):
     """dist_fn(points) -> oracle vectors.  A point over tolerance is a 'seam' point when the oracle
     yields the GPU vector (within tol) at a neighbour <= 1e-3 mm away."""
     err = np.abs(np.asarray(got, np.float64) - np.asarray(want, np.float64)).max(axis=1)
@@ -48,8 +48,13 @@ def dist_report(pts, got, want, dist_fn, tol=DIST_TOL_MM):
     if len(bad):
         g = np.asarray(got, np.float64)[bad]
         close = np.zeros(len(bad), bool)
-        for radius in (FLAG_BAND_MM, FLAG_BAND_MM / 4, FLAG_BAND_MM / 16):
-            nb = _neighbours(pts[bad], radius)
+        rng = np.random.default_rng(12345)
+        clouds = [_neighbours(pts[bad], radius) for radius in (FLAG_BAND_MM, FLAG_BAND_MM / 4, FLAG_BAND_MM / 16)]
+        # where two candidates are nearly tied the reference's own choice flips under sub-micron
+        # perturbations (float32 resolution of the two lengths): sample the 1e-3 mm ball as well
+        clouds.append((pts[bad][:, None, :] +
+                       rng.uniform(-FLAG_BAND_MM, FLAG_BAND_MM, (len(bad), 192, 3))).astype(np.float32))
+        for nb in clouds:
             vec = np.asarray(dist_fn(nb.reshape(-1, 3))).reshape(len(bad), -1, 3)
             close |= (np.abs(vec.astype(np.float64) - g[:, None, :]).max(axis=2)
                       <= tol + 2 * FLAG_BAND_MM).any(axis=1)
@@ -63,7 +68,10 @@ def dist_report(pts, got, want, dist_fn, tol=DIST_TOL_MM):
         # quaternion is not unit length, in which case the reference's frames are not isometric)
         ref_landing = (pts[bad].astype(np.float64) - np.asarray(want, np.float64)[bad]).astype(np.float32)
         ref_err = np.linalg.norm(np.asarray(dist_fn(ref_landing), np.float64), axis=1)
-        close |= same_len & (land_err <= np.maximum(tol, 1.5 * ref_err))
+        # frame_slack = | |q|^2 - 1 |: with a non-unit quaternion the reference's world<->leg maps
+        # are not isometric, so "on the edge" is only defined up to that relative distortion
+        allow = np.maximum(tol, 1.5 * ref_err) + 2.0 * frame_slack * np.linalg.norm(g, axis=1)
+        close |= same_len & (land_err <= allow)
         unexplained = int((~close).sum())
     ok = err[np.isfinite(err) & (err <= tol)]
     return {"n": int(len(err)), "over_tol": int(len(bad)), "seam": int(len(bad)) - unexplained,

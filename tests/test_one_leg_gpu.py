@@ -37,7 +37,8 @@ def _check(lrm, oracle, pts, leg_arr, q, want_r, want_d, want_f, label):
                                  (lambda p: oracle.dist(p, leg_arr, q, threads=8)[1]))
         assert rep["unexplained"] == 0, (label, name, rep)
         assert rep["mismatch"] <= max(3, len(pts) // 20000), (label, name, rep)
-    rep = parity.dist_report(pts, d, want_d, dist_fn)
+    slack = 0.0 if q is None else abs(float((np.asarray(q, np.float64) ** 2).sum()) - 1.0)
+    rep = parity.dist_report(pts, d, want_d, dist_fn, frame_slack=slack)
     assert rep["unexplained"] == 0, (label, rep)
     assert rep["over_tol"] <= max(3, len(pts) // 2000), (label, rep)
     return rep
