@@ -105,3 +105,19 @@ def test_product_never_references_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
     inc = open(os.path.join(ROOT, "include", "lrm_c.h")).read()
     assert "oracle_port" not in inc
+
+
+def test_compat_header_compiles(lrm, tmp_path):
+    """A reference-style call site (bench.cpp:120-152 shape) builds with plain g++ against
+    include/lrm_compat.hpp + liblrm_b200.so; without a GPU it must die like CUDA_CHECK_ERROR."""
+    import subprocess
+    exe = tmp_path / "compat_example"
+    libdir = os.path.dirname(lrm.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "compat_example.cpp"), "-L", libdir, "-llrm_b200",
+                    f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if lrm.lib().lrm_device_count() == 0:
+        assert r.returncode != 0 and "CUDA error in" in r.stderr
+    else:
+        assert r.returncode == 0 and "reachable" in r.stdout

@@ -24,6 +24,8 @@ def _cases(golden):
 def _check(lrm, oracle, pts, leg_arr, q, want_r, want_d, want_f, label):
     leg = lrm.LegDimensions.from_array(leg_arr)
     dev = torch.from_numpy(pts).cuda()
+    if q is None:
+        q = np.array([1, 0, 0, 0], np.float32)
     r = lrm.reachability(dev, leg, q).cpu().numpy()
     d, f = lrm.distance(dev, leg, q)
     d, f = d.cpu().numpy(), f.cpu().numpy()
