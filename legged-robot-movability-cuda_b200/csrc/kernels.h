@@ -25,6 +25,10 @@ cudaError_t launch_lattice(float* out, const float lo[3], const float step[3],
                            const uint32_t dims[3], size_t first, size_t count,
                            cudaStream_t stream);
 
+// Plane atlas of a plan (plane_atlas.cu): built on first use, cached per device.
+struct AtlasView;
+cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView* view);
+
 // Multi-leg positionability (positionability.cu).  All pointers are device pointers.
 struct PositParams {
     const float* bodies;   // nb x 3

@@ -195,6 +195,139 @@ LRM_HD PlaneResult plane_clamp(const LegPlan& L, const SectorTable& tab, float X
     return out;
 }
 
+// ---- plane atlas -------------------------------------------------------------------------------
+// plane_clamp is a function of the femur-plane point alone, and over most of the plane its outcome
+// is "P minus its projection on one particular circle" or "P minus one particular corner" with the
+// same winner over a whole neighbourhood.  The atlas is a regular grid over the plane holding, per
+// cell, that winner — but only for cells where a Lipschitz bound PROVES every decision of
+// plane_clamp (sector tests, validity of P against each circle, arc membership of each projection,
+// every pairwise "who is nearer") keeps its sign over the whole cell.  Such a cell is "pure": the
+// result for any point in it is a handful of FMAs.  Points in impure cells (or off the atlas) take
+// the full evaluation, so the atlas never changes a result, it only skips work.
+//
+// cell byte: bit 7 set = impure; else bit 6 = P valid, bits 4-5 = sector, bits 0-3 = winner
+// (0-3 circle slot, 4-13 corner index + 4, 15 = no candidate at all).
+struct AtlasView {
+    const signed char* cells;
+    float x0, y0, inv_cell;
+    int w, h;
+};
+constexpr int kAtlasNone = 15;
+
+struct PlaneProbe {
+    int label;     // bits 0-6 as above (never has bit 7)
+    float safety;  // every decision keeps its sign within this distance of the probed point
+};
+
+// signed distance of (X, Y) to the decision boundary of an AngleTest, conservatively
+LRM_HD float angle_margin(const AngleTest& t, float X, float Y) {
+    if (t.c == 0.f && t.ns == 0.f) return 3.0e38f;  // constant outcome
+    const float cr = fmaf(t.c, Y, t.ns * X);         // distance to the threshold line
+    return fminf(fabsf(cr), fabsf(Y));               // ... or to the X axis, where `up` flips
+}
+
+// plane_clamp<false> instrumented: same arithmetic, plus the smallest decision margin.
+LRM_HD PlaneProbe plane_probe(const LegPlan& L, const SectorTable& tab, float X, float Y) {
+    float safety = fminf(angle_margin(L.middle, X, Y),
+                         fminf(angle_margin(L.sat[0], X, Y), angle_margin(L.sat[1], X, Y)));
+    const int s = find_sector(L, X, Y);
+    float cx[4], cy[4], r[4], sg[4], ax[4], ay[4], ah[4];
+    cx[0] = 0.f, cy[0] = 0.f, r[0] = L.inner.r, sg[0] = L.inner.sgn;
+    const float4 inner_b = tab.row[s][6];
+    for (int j = 0; j < 3; j++) {
+        const float4 c = tab.row[s][2 * j];
+        const float4 a = tab.row[s][2 * j + 1];
+        cx[j + 1] = c.x, cy[j + 1] = c.y, r[j + 1] = c.z, sg[j + 1] = c.w;
+        ax[j + 1] = a.x, ay[j + 1] = a.y, ah[j + 1] = a.z;
+        if (j == 0) ax[0] = a.w;
+        if (j == 1) ay[0] = a.w;
+        if (j == 2) ah[0] = a.w;
+    }
+    float key[4];
+    bool cand[4];
+    bool valid = true;
+    auto arc_margin = [&](float g, float h) {  // g = dot - h*m ; |h| > 1 means constant outcome
+        return fabsf(h) > 1.f ? 3.0e38f : 0.5f * fabsf(g);
+    };
+    for (int j = 0; j < 4; j++) {
+        const float vx = X - cx[j], vy = Y - cy[j];
+        const float m = sqrtf(fmaf(vx, vx, vy * vy));
+        safety = fminf(safety, m - kMarginF);  // the "on the centre" special case
+        const float d = r[j] - m;
+        key[j] = fabsf(d);
+        const float v = sg[j] * d + kMarginF;
+        valid = valid & (v > 0.f);
+        safety = fminf(safety, fabsf(v));
+        const float g = fmaf(vx, ax[j], vy * ay[j]) - ah[j] * m;
+        cand[j] = g >= 0.f;
+        safety = fminf(safety, arc_margin(g, ah[j]));
+        if (j == 0) {
+            const float g2 = fmaf(vx, inner_b.x, vy * inner_b.y) - inner_b.z * m;
+            cand[0] = cand[0] | (g2 >= 0.f);
+            safety = fminf(safety, arc_margin(g2, inner_b.z));
+        }
+    }
+    // winner and its lead over every other eligible candidate (each distance is 1-Lipschitz)
+    int win = kAtlasNone;
+    float best = 3.0e38f;
+    for (int j = 0; j < 4; j++)
+        if (cand[j] && key[j] < best) best = key[j], win = j;
+    float ckey[kMaxCorners];
+    if (!valid)
+        for (int i = 0; i < L.n_corners; i++) {
+            const float wx = X - L.corner_x[i], wy = Y - L.corner_y[i];
+            ckey[i] = sqrtf(fmaf(wx, wx, wy * wy));
+            if (ckey[i] < best) best = ckey[i], win = 4 + i;
+        }
+    for (int j = 0; j < 4; j++)
+        if (cand[j] && j != win) safety = fminf(safety, 0.5f * (key[j] - best));
+    if (!valid)
+        for (int i = 0; i < L.n_corners; i++)
+            if (4 + i != win) safety = fminf(safety, 0.5f * (ckey[i] - best));
+    if (win >= 4 && win != kAtlasNone) safety = fminf(safety, best - 0.01f);  // keep off the corner itself
+    if (win == kAtlasNone) safety = fminf(safety, 0.f);  // "nothing qualifies" is never certified
+    PlaneProbe out;
+    out.label = (valid ? 0x40 : 0) | (s << 4) | win;
+    out.safety = safety;
+    return out;
+}
+
+// winner table staged next to the sector table: entry [sector*16 + winner] = (cx, cy, r, 0)
+struct WinnerTable {
+    float4 e[64];
+};
+LRM_HD void fill_winner_table(const LegPlan& L, WinnerTable* w, int tid, int nthreads) {
+    for (int i = tid; i < 64; i += nthreads) {
+        const int s = i >> 4, k = i & 15;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k == 0) e = make_float4(0.f, 0.f, L.inner.r, 0.f);
+        else if (k < 4) e = make_float4(L.sector[s].slot[k - 1][0], L.sector[s].slot[k - 1][1],
+                                        L.sector[s].slot[k - 1][2], 0.f);
+        else if (k - 4 < L.n_corners) e = make_float4(L.corner_x[k - 4], L.corner_y[k - 4], 0.f, 0.f);
+        w->e[i] = e;
+    }
+}
+
+// Fast plane evaluation; returns false when the cell is impure / off the atlas (caller must run
+// plane_clamp).  P - (c + r v/|v|) = v (1 - r/|v|); a corner is a circle of radius 0.
+LRM_HD bool plane_lookup(const AtlasView& A, const WinnerTable& W, float X, float Y, PlaneResult& out) {
+    const int ix = (int)floorf((X - A.x0) * A.inv_cell), iy = (int)floorf((Y - A.y0) * A.inv_cell);
+    if ((unsigned)ix >= (unsigned)A.w || (unsigned)iy >= (unsigned)A.h) return false;
+#ifdef __CUDA_ARCH__
+    const int label = __ldg(A.cells + (size_t)iy * A.w + ix);
+#else
+    const int label = A.cells[(size_t)iy * A.w + ix];
+#endif
+    if (label < 0) return false;
+    const float4 e = W.e[label & 63];
+    const float vx = X - e.x, vy = Y - e.y;
+    const float k = 1.f - e.z * fast_rsqrt(fmaf(vx, vx, vy * vy));
+    out.valid = (label & 0x40) != 0;
+    out.dx = vx * k;
+    out.dy = vy * k;
+    return true;
+}
+
 struct CoxaPoint {
     float x, y, z;  // point in the coxa frame
 };
@@ -258,9 +391,12 @@ struct BranchResult {
 
 // finish_finding_closest<bool>, one_leg.cu:215-278, for one coxa solution.
 // (ux, uy) = unit vector of the solution's un-saturated yaw (w / rho).
-template <bool GENERIC>
+// ATLAS: take the plane evaluation from the atlas; `ok` is cleared when the cell is not certified
+// (the caller then redoes the whole point with ATLAS = false).
+template <bool GENERIC, bool ATLAS>
 LRM_HD BranchResult closest_for_branch(const LegPlan& L, const SectorTable& tab, const CoxaPoint p,
-                                       const YawFlags f, float ux, float uy) {
+                                       const YawFlags f, float ux, float uy, const AtlasView* A,
+                                       const WinnerTable* W, bool& ok) {
     // unit direction of the saturated yaw
     float cs = ux, ss = uy;
     if (f.mega) {
@@ -274,7 +410,13 @@ LRM_HD BranchResult closest_for_branch(const LegPlan& L, const SectorTable& tab,
     const float xr = fmaf(p.x, cs, p.y * ss);
     const float yr = fmaf(p.y, cs, -p.x * ss);
 
-    const PlaneResult pl = plane_clamp<GENERIC>(L, tab, xr - L.coxa_length, p.z);
+    PlaneResult pl;
+    if (ATLAS) {
+        pl.valid = false, pl.dx = pl.dy = 0.f;
+        if (!plane_lookup(*A, *W, xr - L.coxa_length, p.z, pl)) ok = false;
+    } else {
+        pl = plane_clamp<GENERIC>(L, tab, xr - L.coxa_length, p.z);
+    }
     const float qx = pl.dx, qy = yr, qz = pl.dy;  // in the saturated-yaw frame
     const float n2 = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
 
@@ -299,8 +441,11 @@ struct DistResult {
 };
 
 // distance_circles (one_leg.cu:321-341) + the way back to the world frame.
-template <bool GENERIC>
-LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, const CoxaPoint p) {
+// With ATLAS the return value is only meaningful when `ok` stays true.
+template <bool GENERIC, bool ATLAS = false>
+LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, const CoxaPoint p,
+                                  const AtlasView* A = nullptr, const WinnerTable* W = nullptr,
+                                  bool* ok_out = nullptr) {
     const float rho2 = fmaf(p.x, p.x, p.y * p.y);
     const float inv_rho = rho2 > 0.f ? fast_rsqrt(rho2) : 0.f;
     // unit vector of the direct yaw; a point on the coxa axis has yaw 0 (atan2f(0, 0))
@@ -316,8 +461,10 @@ LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, cons
     const bool skip_b = fb.mega & !(fa.mega | fa.over | fa.under);
     BranchResult a, b;
     a.res = b.res = false, a.vx = a.vy = a.vz = b.vx = b.vy = b.vz = 0.f, a.n2 = b.n2 = 0.f;
-    if (!skip_a) a = closest_for_branch<GENERIC>(L, tab, p, fa, ux, uy);
-    if (!skip_b) b = closest_for_branch<GENERIC>(L, tab, p, fb, -ux, -uy);
+    bool ok = true;
+    if (!skip_a) a = closest_for_branch<GENERIC, ATLAS>(L, tab, p, fa, ux, uy, A, W, ok);
+    if (!skip_b) b = closest_for_branch<GENERIC, ATLAS>(L, tab, p, fb, -ux, -uy, A, W, ok);
+    if (ATLAS) *ok_out = ok;
     if (skip_a) a = b, a.res = false;
     if (skip_b) b = a, b.res = false;
     const bool direct = (a.res == b.res) ? (a.n2 < b.n2) : a.res;

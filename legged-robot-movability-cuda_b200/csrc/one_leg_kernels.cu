@@ -24,6 +24,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kTile = 1024;  // points per tile (multiple of 16 keeps every bulk copy 16-B sized)
 constexpr int kStages = 2;
+constexpr size_t kAtlasMinPoints = size_t(1) << 22;
 static_assert(kTile % kThreads == 0 && kTile % 16 == 0, "tile shape");
 
 template <int MODE>
@@ -32,13 +33,18 @@ struct alignas(128) StreamSmem {
     float vec[(MODE & kModeDist) ? 2 : 1][(MODE & kModeDist) ? 3 * kTile : 4];
     uint8_t flag[2][kTile];
     alignas(16) SectorTable table;
+    alignas(16) WinnerTable winners;   // atlas fast path
+    uint16_t queue[kTile];              // points of the current tile the atlas could not certify
+    int qcount[2];
     alignas(8) uint64_t full[kStages];
 };
 
-template <int MODE, bool SOA, bool GENERIC>
-__device__ __forceinline__ void compute_point(const LegPlan& L, const SectorTable& tab,
+// Returns false only with ATLAS when the point could not be certified (nothing is written then).
+template <int MODE, bool SOA, bool GENERIC, bool ATLAS = false>
+__device__ __forceinline__ bool compute_point(const LegPlan& L, const SectorTable& tab,
                                               const float* in, float* vec, uint8_t* flag, int i,
-                                              int stride_pts) {
+                                              int stride_pts, const AtlasView* A = nullptr,
+                                              const WinnerTable* W = nullptr) {
     float x, y, z;
     if (SOA) {
         x = in[i], y = in[stride_pts + i], z = in[2 * stride_pts + i];
@@ -49,7 +55,9 @@ __device__ __forceinline__ void compute_point(const LegPlan& L, const SectorTabl
     if (MODE == kModeReach) {
         flag[i] = reach_coxa_frame(L, tab, p) ? 1 : 0;
     } else {
-        const DistResult r = dist_coxa_frame<GENERIC>(L, tab, p);
+        bool ok = true;
+        const DistResult r = dist_coxa_frame<GENERIC, ATLAS>(L, tab, p, A, W, &ok);
+        if (ATLAS && !ok) return false;
         if (SOA) {
             vec[i] = r.dx, vec[stride_pts + i] = r.dy, vec[2 * stride_pts + i] = r.dz;
         } else {
@@ -58,15 +66,17 @@ __device__ __forceinline__ void compute_point(const LegPlan& L, const SectorTabl
         // MODE dist: distance_global's bool; MODE both: reachability_global's bool
         flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
     }
+    return true;
 }
 
 // AoS: in_x = xyz (N x 3), out_x = vectors (N x 3).  SoA: separate planes.
-template <int MODE, bool SOA, bool GENERIC>
+template <int MODE, bool SOA, bool GENERIC, bool ATLAS>
 __global__ void __launch_bounds__(kThreads)
-    one_leg_stream_kernel(const __grid_constant__ LegPlan L, const float* __restrict__ in_x,
-                          const float* __restrict__ in_y, const float* __restrict__ in_z,
-                          float* __restrict__ out_x, float* __restrict__ out_y,
-                          float* __restrict__ out_z, uint8_t* __restrict__ out_flag, size_t n) {
+    one_leg_stream_kernel(const __grid_constant__ LegPlan L, const AtlasView atlas,
+                          const float* __restrict__ in_x, const float* __restrict__ in_y,
+                          const float* __restrict__ in_z, float* __restrict__ out_x,
+                          float* __restrict__ out_y, float* __restrict__ out_z,
+                          uint8_t* __restrict__ out_flag, size_t n) {
     // keep the pointer provably in the shared window (LDS/STS, not generic LD/ST): no integer
     // round-trip on the address; the bulk engine only needs 16-byte alignment
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -78,9 +88,11 @@ __global__ void __launch_bounds__(kThreads)
     constexpr bool kVec = (MODE & kModeDist) != 0;
 
     fill_sector_table(L, &S.table, tid, kThreads);
+    if (ATLAS) fill_winner_table(L, &S.winners, tid, kThreads);
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) bulk::mbar_init(&S.full[s], 1);
         bulk::fence_barrier_init();
+        S.qcount[0] = S.qcount[1] = 0;
     }
     __syncthreads();
 
@@ -119,9 +131,25 @@ __global__ void __launch_bounds__(kThreads)
         const float* in = S.in[stage];
         float* vec = S.vec[kVec ? ob : 0];
         uint8_t* flag = S.flag[ob];
+        if (ATLAS) {
+            // pass 1: every point through the atlas; the few it cannot certify are queued ...
 #pragma unroll 1
-        for (int i = tid; i < (int)cnt; i += kThreads)
-            compute_point<MODE, SOA, GENERIC>(L, S.table, in, vec, flag, i, kTile);
+            for (int i = tid; i < (int)cnt; i += kThreads)
+                if (!compute_point<MODE, SOA, false, true>(L, S.table, in, vec, flag, i, kTile, &atlas,
+                                                           &S.winners))
+                    S.queue[atomicAdd(&S.qcount[ob], 1)] = (uint16_t)i;
+            __syncthreads();
+            // ... pass 2: and redone with the full evaluation by densely packed warps
+            const int nq = S.qcount[ob];
+            if (tid == 0) S.qcount[ob ^ 1] = 0;
+#pragma unroll 1
+            for (int k = tid; k < nq; k += kThreads)
+                compute_point<MODE, SOA, false, false>(L, S.table, in, vec, flag, S.queue[k], kTile);
+        } else {
+#pragma unroll 1
+            for (int i = tid; i < (int)cnt; i += kThreads)
+                compute_point<MODE, SOA, GENERIC>(L, S.table, in, vec, flag, i, kTile);
+        }
 
         bulk::fence_proxy_async();  // results written through the generic proxy -> bulk engine
         if (tid == 0) bulk::wait_group_read<0>();  // previous tile's store has drained its buffer
@@ -238,11 +266,11 @@ int sm_count() {
     return g_sm_count;
 }
 
-template <int MODE, bool SOA, bool GENERIC>
-cudaError_t launch_stream_impl(const LegPlan& plan, const float* ix, const float* iy, const float* iz,
-                          float* ox, float* oy, float* oz, uint8_t* flag, size_t n,
-                          cudaStream_t stream) {
-    auto kernel = one_leg_stream_kernel<MODE, SOA, GENERIC>;
+template <int MODE, bool SOA, bool GENERIC, bool ATLAS>
+cudaError_t launch_stream_impl(const LegPlan& plan, const AtlasView& atlas, const float* ix,
+                               const float* iy, const float* iz, float* ox, float* oy, float* oz,
+                               uint8_t* flag, size_t n, cudaStream_t stream) {
+    auto kernel = one_leg_stream_kernel<MODE, SOA, GENERIC, ATLAS>;
     constexpr size_t smem = sizeof(StreamSmem<MODE>);
     // per-device: the attribute belongs to the device's copy of the function
     static int ctas_per_sm_dev[64] = {0};
@@ -262,7 +290,7 @@ cudaError_t launch_stream_impl(const LegPlan& plan, const float* ix, const float
     size_t grid = (size_t)sm_count() * ctas_per_sm;
     if (tiles < grid) grid = tiles;
     if (grid == 0) grid = 1;
-    kernel<<<(unsigned)grid, kThreads, smem, stream>>>(plan, ix, iy, iz, ox, oy, oz, flag, n);
+    kernel<<<(unsigned)grid, kThreads, smem, stream>>>(plan, atlas, ix, iy, iz, ox, oy, oz, flag, n);
     return cudaGetLastError();
 }
 
@@ -271,10 +299,24 @@ template <int MODE, bool SOA>
 cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy, const float* iz,
                           float* ox, float* oy, float* oz, uint8_t* flag, size_t n,
                           cudaStream_t stream) {
-    if (MODE != kModeReach && plan.generic)
-        return launch_stream_impl<MODE, SOA, MODE != kModeReach>(plan, ix, iy, iz, ox, oy, oz, flag,
-                                                                 n, stream);
-    return launch_stream_impl<MODE, SOA, false>(plan, ix, iy, iz, ox, oy, oz, flag, n, stream);
+    AtlasView none{};
+    if (MODE == kModeReach)
+        return launch_stream_impl<MODE, SOA, false, false>(plan, none, ix, iy, iz, ox, oy, oz, flag, n,
+                                                           stream);
+    constexpr bool kDist = MODE != kModeReach;
+    if (plan.generic)
+        return launch_stream_impl<MODE, SOA, kDist, false>(plan, none, ix, iy, iz, ox, oy, oz, flag, n,
+                                                           stream);
+    // the atlas pays for itself (16 Mi probes) only on large sweeps, or once it is cached
+    if (n >= kAtlasMinPoints) {
+        AtlasView atlas;
+        cudaError_t e = get_plane_atlas(plan, stream, &atlas);
+        if (e != cudaSuccess) return e;
+        return launch_stream_impl<MODE, SOA, false, kDist>(plan, atlas, ix, iy, iz, ox, oy, oz, flag, n,
+                                                           stream);
+    }
+    return launch_stream_impl<MODE, SOA, false, false>(plan, none, ix, iy, iz, ox, oy, oz, flag, n,
+                                                       stream);
 }
 
 template <int MODE>

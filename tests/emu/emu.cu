@@ -74,6 +74,48 @@ void emu_dist_generic(const float* xyz, size_t n, const lrm_leg_t* leg, const fl
     }
 }
 
+// The atlas path exactly as the streaming kernel runs it: certified cells take plane_lookup, the
+// rest fall back to the full evaluation.  Returns the number of points that fell back.
+size_t emu_dist_atlas(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, int dim,
+                      float cell, float* out_vec, uint8_t* out_flag, uint8_t* out_reach,
+                      size_t* pure_cells) {
+    lrm::LegPlan L;
+    lrm::build_leg_plan(*leg, quat, &L);
+    lrm::SectorTable tab;
+    host_table(L, &tab);
+    lrm::WinnerTable win;
+    lrm::fill_winner_table(L, &win, 0, 1);
+    const float origin = -0.5f * dim * cell;
+    signed char* cells = new signed char[(size_t)dim * dim];
+    const float need = cell * 0.70711f * 1.02f + 2.0e-3f;  // same rule as atlas_build_kernel
+    size_t pure = 0;
+    for (int iy = 0; iy < dim; iy++)
+        for (int ix = 0; ix < dim; ix++) {
+            const float X = origin + ((float)ix + 0.5f) * cell, Y = origin + ((float)iy + 0.5f) * cell;
+            const lrm::PlaneProbe pr = lrm::plane_probe(L, tab, X, Y);
+            const bool ok = pr.safety > need;
+            cells[(size_t)iy * dim + ix] = (signed char)(ok ? pr.label : 0x80);
+            pure += ok;
+        }
+    if (pure_cells) *pure_cells = pure;
+    lrm::AtlasView A{cells, origin, origin, 1.0f / cell, dim, dim};
+    size_t fallback = 0;
+    for (size_t i = 0; i < n; i++) {
+        const lrm::CoxaPoint p = lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        bool ok = true;
+        lrm::DistResult r = lrm::dist_coxa_frame<false, true>(L, tab, p, &A, &win, &ok);
+        if (!ok) {
+            r = lrm::dist_coxa_frame<false, false>(L, tab, p);
+            fallback++;
+        }
+        out_vec[3 * i] = r.dx, out_vec[3 * i + 1] = r.dy, out_vec[3 * i + 2] = r.dz;
+        if (out_flag) out_flag[i] = r.flag ? 1 : 0;
+        if (out_reach) out_reach[i] = r.reach ? 1 : 0;
+    }
+    delete[] cells;
+    return fallback;
+}
+
 int emu_plan_is_generic(const lrm_leg_t* leg, const float* quat) {
     lrm::LegPlan L;
     lrm::build_leg_plan(*leg, quat, &L);

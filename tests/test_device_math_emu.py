@@ -115,3 +115,30 @@ def test_arc_tables_cover_default_legs_and_match_cross_validation(emu, port):
             diff = np.abs(d - g).max(axis=1)
             worst = max(worst, int((diff > 1e-2).sum()))
             assert (diff > 1e-2).sum() <= 4, (robot, az, int((diff > 1e-2).sum()))
+
+
+def test_plane_atlas_never_changes_a_result(emu, port):
+    """The plane atlas (leg_math.cuh plane_probe / plane_lookup) is a pure accelerator: certified
+    cells must reproduce the full evaluation (flags identical, vectors to float rounding), and
+    enough cells must be certified for it to be worth having."""
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    emu.emu_dist_atlas.argtypes = [vp, sz, vp, vp, ctypes.c_int, ctypes.c_float, vp, vp, vp, vp]
+    emu.emu_dist_atlas.restype = ctypes.c_size_t
+    rng = np.random.default_rng(31)
+    pts = np.concatenate([rng.uniform([-100, -400, -500], [600, 400, 200], (60000, 3)),
+                          rng.uniform(-700, 700, (30000, 3))]).astype(np.float32)
+    cases = ((1, 0.0, [1, 0, 0, 0]), (0, 0.7853982, port.quaternion_from_angle_index(0)),
+             (1, 3.9269907, port.full_struct_orientations()[31]))
+    for robot, az, q in cases:
+        leg = port.get_leg(robot, az)
+        q = np.ascontiguousarray(q, np.float32)
+        _, base, bf, br = run_emu(emu, pts, leg, q)
+        out = np.zeros_like(pts)
+        fl = np.zeros(len(pts), np.uint8)
+        rf = np.zeros(len(pts), np.uint8)
+        pure = ctypes.c_size_t(0)
+        fb = emu.emu_dist_atlas(pts.ctypes.data, len(pts), leg.ctypes.data, q.ctypes.data, 1024, 2.0,
+                                out.ctypes.data, fl.ctypes.data, rf.ctypes.data, ctypes.byref(pure))
+        assert np.array_equal(fl, bf) and np.array_equal(rf, br)
+        assert np.abs(out - base).max() < 1e-3
+        assert pure.value > 0.85 * 1024 * 1024 and fb < 0.3 * len(pts), (pure.value, fb)
