@@ -308,24 +308,32 @@ LRM_HD void fill_winner_table(const LegPlan& L, WinnerTable* w, int tid, int nth
     }
 }
 
-// Fast plane evaluation; returns false when the cell is impure / off the atlas (caller must run
-// plane_clamp).  P - (c + r v/|v|) = v (1 - r/|v|); a corner is a circle of radius 0.
-LRM_HD bool plane_lookup(const AtlasView& A, const WinnerTable& W, float X, float Y, PlaneResult& out) {
+// Cells are stored in 8 x 4 blocks (one 32-byte sector each), so the points of a warp, which walk
+// a short line through the plane, touch a handful of sectors instead of one per lane.
+LRM_HD size_t atlas_index(int w, int ix, int iy) {
+    return ((size_t)((iy >> 2) * (w >> 3) + (ix >> 3)) << 5) | (size_t)(((iy & 3) << 3) | (ix & 7));
+}
+// Label of the cell holding (X, Y): >= 0 certified, < 0 impure or off the atlas.
+LRM_HD int atlas_label(const AtlasView& A, float X, float Y) {
     const int ix = (int)floorf((X - A.x0) * A.inv_cell), iy = (int)floorf((Y - A.y0) * A.inv_cell);
-    if ((unsigned)ix >= (unsigned)A.w || (unsigned)iy >= (unsigned)A.h) return false;
+    if ((unsigned)ix >= (unsigned)A.w || (unsigned)iy >= (unsigned)A.h) return -1;
 #ifdef __CUDA_ARCH__
-    const int label = __ldg(A.cells + (size_t)iy * A.w + ix);
+    return __ldg(A.cells + atlas_index(A.w, ix, iy));
 #else
-    const int label = A.cells[(size_t)iy * A.w + ix];
+    return A.cells[atlas_index(A.w, ix, iy)];
 #endif
-    if (label < 0) return false;
+}
+// Plane evaluation of a certified cell: P - (c + r v/|v|) = v (1 - r/|v|); a corner is a circle
+// of radius 0.
+LRM_HD PlaneResult plane_from_label(const WinnerTable& W, int label, float X, float Y) {
     const float4 e = W.e[label & 63];
     const float vx = X - e.x, vy = Y - e.y;
     const float k = 1.f - e.z * fast_rsqrt(fmaf(vx, vx, vy * vy));
+    PlaneResult out;
     out.valid = (label & 0x40) != 0;
     out.dx = vx * k;
     out.dy = vy * k;
-    return true;
+    return out;
 }
 
 struct CoxaPoint {
@@ -389,46 +397,42 @@ struct BranchResult {
     float n2;          // its squared norm
 };
 
-// finish_finding_closest<bool>, one_leg.cu:215-278, for one coxa solution.
-// (ux, uy) = unit vector of the solution's un-saturated yaw (w / rho).
-// ATLAS: take the plane evaluation from the atlas; `ok` is cleared when the cell is not certified
-// (the caller then redoes the whole point with ATLAS = false).
-template <bool GENERIC, bool ATLAS>
-LRM_HD BranchResult closest_for_branch(const LegPlan& L, const SectorTable& tab, const CoxaPoint p,
-                                       const YawFlags f, float ux, float uy, const AtlasView* A,
-                                       const WinnerTable* W, bool& ok) {
-    // unit direction of the saturated yaw
-    float cs = ux, ss = uy;
+// finish_finding_closest<bool>, one_leg.cu:215-278, for one coxa solution, in two halves around
+// the plane evaluation.  (ux, uy) = unit vector of the solution's un-saturated yaw (w / rho).
+struct BranchPrep {
+    float cs, ss;  // unit direction of the saturated yaw
+    float X, yr;   // femur-plane abscissa of the point and its out-of-plane offset
+    bool saturated;
+};
+LRM_HD BranchPrep branch_prep(const LegPlan& L, const CoxaPoint p, const YawFlags f, float ux,
+                              float uy) {
+    BranchPrep b;
+    b.cs = ux, b.ss = uy;
     if (f.mega) {
-        cs = -ux, ss = -uy;  // yaw -+ pi
+        b.cs = -ux, b.ss = -uy;  // yaw -+ pi
     } else if (f.under) {
-        cs = L.cos_min, ss = L.sin_min;
+        b.cs = L.cos_min, b.ss = L.sin_min;
     } else if (f.over) {
-        cs = L.cos_max, ss = L.sin_max;
+        b.cs = L.cos_max, b.ss = L.sin_max;
     }
-    const bool saturated = f.mega | f.over | f.under;
-    const float xr = fmaf(p.x, cs, p.y * ss);
-    const float yr = fmaf(p.y, cs, -p.x * ss);
-
-    PlaneResult pl;
-    if (ATLAS) {
-        pl.valid = false, pl.dx = pl.dy = 0.f;
-        if (!plane_lookup(*A, *W, xr - L.coxa_length, p.z, pl)) ok = false;
-    } else {
-        pl = plane_clamp<GENERIC>(L, tab, xr - L.coxa_length, p.z);
-    }
-    const float qx = pl.dx, qy = yr, qz = pl.dy;  // in the saturated-yaw frame
+    b.saturated = f.mega | f.over | f.under;
+    b.X = fmaf(p.x, b.cs, p.y * b.ss) - L.coxa_length;
+    b.yr = fmaf(p.y, b.cs, -p.x * b.ss);
+    return b;
+}
+LRM_HD BranchResult branch_finish(const LegPlan& L, const CoxaPoint p, const YawFlags f,
+                                  const BranchPrep b, const PlaneResult pl) {
+    const float qx = pl.dx, qy = b.yr, qz = pl.dy;  // in the saturated-yaw frame
     const float n2 = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
-
     BranchResult out;
-    out.res = pl.valid & !saturated;
+    out.res = pl.valid & !b.saturated;
     // in-plane region reached but a coxa-limit half-plane is nearer (one_leg.cu:258-274)
     const float cl = f.upper_lim ? L.cos_max : L.cos_min;
     const float sl = f.upper_lim ? L.sin_max : L.sin_min;
     const float yl = fmaf(p.y, cl, -p.x * sl);
     const bool to_plane = pl.valid & !f.mega & (n2 > yl * yl);
-    out.vx = to_plane ? -yl * sl : fmaf(qx, cs, -qy * ss);
-    out.vy = to_plane ? yl * cl : fmaf(qx, ss, qy * cs);
+    out.vx = to_plane ? -yl * sl : fmaf(qx, b.cs, -qy * b.ss);
+    out.vy = to_plane ? yl * cl : fmaf(qx, b.ss, qy * b.cs);
     out.vz = to_plane ? 0.f : qz;
     out.n2 = to_plane ? yl * yl : n2;
     return out;
@@ -441,7 +445,8 @@ struct DistResult {
 };
 
 // distance_circles (one_leg.cu:321-341) + the way back to the world frame.
-// With ATLAS the return value is only meaningful when `ok` stays true.
+// ATLAS: plane evaluations come from the atlas; *ok_out is cleared (and the result is garbage)
+// when a needed cell is not certified — the caller then redoes the point with ATLAS = false.
 template <bool GENERIC, bool ATLAS = false>
 LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, const CoxaPoint p,
                                   const AtlasView* A = nullptr, const WinnerTable* W = nullptr,
@@ -459,12 +464,24 @@ LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, cons
     // vector unless the other one found something nearer), so it is skipped.
     const bool skip_a = fa.mega & !(fb.mega | fb.over | fb.under);
     const bool skip_b = fb.mega & !(fa.mega | fa.over | fa.under);
+    const BranchPrep pa = branch_prep(L, p, fa, ux, uy);
+    const BranchPrep pb = branch_prep(L, p, fb, -ux, -uy);
     BranchResult a, b;
-    a.res = b.res = false, a.vx = a.vy = a.vz = b.vx = b.vy = b.vz = 0.f, a.n2 = b.n2 = 0.f;
-    bool ok = true;
-    if (!skip_a) a = closest_for_branch<GENERIC, ATLAS>(L, tab, p, fa, ux, uy, A, W, ok);
-    if (!skip_b) b = closest_for_branch<GENERIC, ATLAS>(L, tab, p, fb, -ux, -uy, A, W, ok);
-    if (ATLAS) *ok_out = ok;
+    if (ATLAS) {
+        // both labels are requested before either is consumed (two L2/L1 loads in flight)
+        const int la = skip_a ? 0 : atlas_label(*A, pa.X, p.z);
+        const int lb = skip_b ? 0 : atlas_label(*A, pb.X, p.z);
+        if ((la | lb) < 0) {
+            *ok_out = false;
+            return DistResult{};
+        }
+        a = branch_finish(L, p, fa, pa, plane_from_label(*W, la, pa.X, p.z));
+        b = branch_finish(L, p, fb, pb, plane_from_label(*W, lb, pb.X, p.z));
+    } else {
+        a.res = b.res = false, a.vx = a.vy = a.vz = b.vx = b.vy = b.vz = 0.f, a.n2 = b.n2 = 0.f;
+        if (!skip_a) a = branch_finish(L, p, fa, pa, plane_clamp<GENERIC>(L, tab, pa.X, p.z));
+        if (!skip_b) b = branch_finish(L, p, fb, pb, plane_clamp<GENERIC>(L, tab, pb.X, p.z));
+    }
     if (skip_a) a = b, a.res = false;
     if (skip_b) b = a, b.res = false;
     const bool direct = (a.res == b.res) ? (a.n2 < b.n2) : a.res;

@@ -74,6 +74,116 @@ struct EventPair {
     }
 };
 
+
+// ---- pipelined staging for host-pointer calls --------------------------------------------------
+constexpr size_t kChunkPoints = size_t(1) << 23;  // 8 Mi points: 96 MiB up, 104 MiB down
+constexpr int kSlots = 3;
+
+struct Staging {
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    cudaEvent_t uploaded[kSlots] = {}, computed[kSlots] = {}, drained[kSlots] = {};
+    cudaEvent_t k0[kSlots] = {}, k1[kSlots] = {};
+    float* d_in[kSlots] = {};
+    float* d_vec[kSlots] = {};
+    uint8_t* d_flag[kSlots] = {};
+    cudaError_t init(size_t chunk, int nslots, bool want_vec, bool want_flag) {
+        cudaError_t e;
+        if ((e = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        for (int i = 0; i < nslots; i++) {
+            if ((e = cudaEventCreateWithFlags(&uploaded[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreate(&k0[i])) != cudaSuccess) return e;
+            if ((e = cudaEventCreate(&k1[i])) != cudaSuccess) return e;
+            if ((e = cudaMalloc((void**)&d_in[i], chunk * 12)) != cudaSuccess) return e;
+            if (want_vec && (e = cudaMalloc((void**)&d_vec[i], chunk * 12)) != cudaSuccess) return e;
+            if (want_flag && (e = cudaMalloc((void**)&d_flag[i], chunk)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    ~Staging() {
+        for (int i = 0; i < kSlots; i++) {
+            if (d_in[i]) cudaFree(d_in[i]);
+            if (d_vec[i]) cudaFree(d_vec[i]);
+            if (d_flag[i]) cudaFree(d_flag[i]);
+            if (uploaded[i]) cudaEventDestroy(uploaded[i]);
+            if (computed[i]) cudaEventDestroy(computed[i]);
+            if (drained[i]) cudaEventDestroy(drained[i]);
+            if (k0[i]) cudaEventDestroy(k0[i]);
+            if (k1[i]) cudaEventDestroy(k1[i]);
+        }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_cmp) cudaStreamDestroy(s_cmp);
+        if (s_out) cudaStreamDestroy(s_out);
+    }
+};
+
+int staged_one_leg(int mode, const lrm::LegPlan& plan, const float* xyz, size_t n, float* out_xyz,
+                   uint8_t* flags, cudaStream_t user_stream, float* kernel_ms) {
+    const bool want_vec = (mode & lrm::kModeDist) != 0;
+    const bool want_flag = flags != nullptr;
+    const size_t chunk = n < kChunkPoints ? n : kChunkPoints;
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    Staging st;
+    LRM_CUDA(st.init(chunk, nchunks < (size_t)kSlots ? (int)nchunks : kSlots, want_vec, want_flag),
+             "staging buffers");
+    // order after whatever the caller queued on its stream
+    cudaEvent_t begin;
+    LRM_CUDA(cudaEventCreateWithFlags(&begin, cudaEventDisableTiming), "cudaEventCreate");
+    cudaEventRecord(begin, user_stream);
+    cudaStreamWaitEvent(st.s_in, begin, 0);
+    cudaStreamWaitEvent(st.s_cmp, begin, 0);
+    cudaStreamWaitEvent(st.s_out, begin, 0);
+    cudaEventDestroy(begin);
+
+    double total_ms = 0.0;
+    for (size_t c = 0; c < nchunks; c++) {
+        const int slot = (int)(c % kSlots);
+        const size_t first = c * chunk, cnt = (n - first < chunk) ? n - first : chunk;
+        if (c >= (size_t)kSlots) {
+            // the slot is free once its previous download has drained; collect its kernel time
+            LRM_CUDA(cudaEventSynchronize(st.drained[slot]), "pipeline drain");
+            float ms = 0.f;
+            if (kernel_ms && cudaEventElapsedTime(&ms, st.k0[slot], st.k1[slot]) == cudaSuccess) total_ms += ms;
+        }
+        LRM_CUDA(cudaMemcpyAsync(st.d_in[slot], xyz + 3 * first, cnt * 12, cudaMemcpyHostToDevice, st.s_in),
+                 "H2D points");
+        cudaEventRecord(st.uploaded[slot], st.s_in);
+        cudaStreamWaitEvent(st.s_cmp, st.uploaded[slot], 0);
+        cudaEventRecord(st.k0[slot], st.s_cmp);
+        LRM_CUDA(lrm::launch_one_leg_aos(mode, plan, st.d_in[slot], st.d_vec[slot], st.d_flag[slot], cnt,
+                                         st.s_cmp),
+                 "one-leg kernel launch");
+        cudaEventRecord(st.k1[slot], st.s_cmp);
+        cudaEventRecord(st.computed[slot], st.s_cmp);
+        cudaStreamWaitEvent(st.s_out, st.computed[slot], 0);
+        if (want_vec)
+            LRM_CUDA(cudaMemcpyAsync(out_xyz + 3 * first, st.d_vec[slot], cnt * 12, cudaMemcpyDeviceToHost,
+                                     st.s_out),
+                     "D2H vectors");
+        if (want_flag)
+            LRM_CUDA(cudaMemcpyAsync(flags + first, st.d_flag[slot], cnt, cudaMemcpyDeviceToHost, st.s_out),
+                     "D2H flags");
+        cudaEventRecord(st.drained[slot], st.s_out);
+        // (the next upload into this slot is issued only after the host has seen drained[slot],
+        // which implies this chunk's kernel has finished with d_in[slot])
+    }
+    LRM_CUDA(cudaStreamSynchronize(st.s_out), "pipeline synchronize");
+    LRM_CUDA(cudaStreamSynchronize(st.s_cmp), "pipeline synchronize");
+    if (kernel_ms) {
+        const size_t tail = nchunks < (size_t)kSlots ? nchunks : (size_t)kSlots;
+        for (size_t k = 0; k < tail; k++) {
+            const int slot = (int)((nchunks - 1 - k) % kSlots);
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, st.k0[slot], st.k1[slot]) == cudaSuccess) total_ms += ms;
+        }
+        *kernel_ms = (float)total_ms;
+    }
+    return LRM_OK;
+}
+
 // Shared body of lrm_reach / lrm_dist / lrm_reach_dist.
 int one_leg_call(int mode, const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat,
                  float* out_xyz, uint8_t* flags, int on_device, void* stream_v, float* kernel_ms) {
@@ -97,33 +207,17 @@ int one_leg_call(int mode, const float* xyz, size_t n, const lrm_leg_t* leg, con
         return LRM_OK;
     }
 
-    // host pointers: apply_kernel's malloc / H2D / kernel / D2H / free
+    // host pointers: apply_kernel's malloc / H2D / kernel / D2H / free (cross_compiled.cu:41-77),
+    // pipelined: the array is cut into chunks so that the upload of chunk k+1, the kernel of chunk
+    // k and the download of chunk k-1 overlap on three streams (full-duplex PCIe when the caller's
+    // buffers are pinned; with pageable memory the copies serialise but stay correct).
     int count = 0;
     cudaError_t ce = cudaGetDeviceCount(&count);
     if (ce != cudaSuccess || count == 0)
         return cuda_fail(ce != cudaSuccess ? ce : cudaErrorNoDevice,
                          "no CUDA device (this library has no CPU path)");
-    DeviceScratch scratch;
-    float *d_in = nullptr, *d_vec = nullptr;
-    uint8_t* d_flag = nullptr;
-    LRM_CUDA(scratch.alloc((void**)&d_in, n * 12), "cudaMalloc input");
-    if (mode & lrm::kModeDist) LRM_CUDA(scratch.alloc((void**)&d_vec, n * 12), "cudaMalloc vectors");
-    if (flags) LRM_CUDA(scratch.alloc((void**)&d_flag, n), "cudaMalloc flags");
-    LRM_CUDA(cudaMemcpyAsync(d_in, xyz, n * 12, cudaMemcpyHostToDevice, stream), "H2D points");
-    {
-        EventPair ev;
-        LRM_CUDA(ev.start(stream, kernel_ms != nullptr), "cudaEventRecord");
-        LRM_CUDA(lrm::launch_one_leg_aos(mode, plan, d_in, d_vec, d_flag, n, stream),
-                 "one-leg kernel launch");
-        LRM_CUDA(ev.stop(stream, kernel_ms), "one-leg kernel");
-    }
-    if (d_vec)
-        LRM_CUDA(cudaMemcpyAsync(out_xyz, d_vec, n * 12, cudaMemcpyDeviceToHost, stream),
-                 "D2H vectors");
-    if (d_flag)
-        LRM_CUDA(cudaMemcpyAsync(flags, d_flag, n, cudaMemcpyDeviceToHost, stream), "D2H flags");
-    LRM_CUDA(cudaStreamSynchronize(stream), "stream synchronize");
-    return LRM_OK;
+    if (n == 0) return LRM_OK;
+    return staged_one_leg(mode, plan, xyz, n, out_xyz, flags, stream, kernel_ms);
 }
 
 }  // namespace

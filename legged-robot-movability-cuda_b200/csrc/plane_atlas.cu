@@ -35,7 +35,7 @@ __global__ void atlas_build_kernel(const __grid_constant__ LegPlan L, signed cha
         const int ix = (int)(i % dim), iy = (int)(i / dim);
         const float X = origin + ((float)ix + 0.5f) * cell, Y = origin + ((float)iy + 0.5f) * cell;
         const PlaneProbe pr = plane_probe(L, table, X, Y);
-        cells[i] = (signed char)(pr.safety > need ? pr.label : 0x80);
+        cells[atlas_index(dim, ix, iy)] = (signed char)(pr.safety > need ? pr.label : 0x80);
     }
 }
 

@@ -94,7 +94,7 @@ size_t emu_dist_atlas(const float* xyz, size_t n, const lrm_leg_t* leg, const fl
             const float X = origin + ((float)ix + 0.5f) * cell, Y = origin + ((float)iy + 0.5f) * cell;
             const lrm::PlaneProbe pr = lrm::plane_probe(L, tab, X, Y);
             const bool ok = pr.safety > need;
-            cells[(size_t)iy * dim + ix] = (signed char)(ok ? pr.label : 0x80);
+            cells[lrm::atlas_index(dim, ix, iy)] = (signed char)(ok ? pr.label : 0x80);
             pure += ok;
         }
     if (pure_cells) *pure_cells = pure;
