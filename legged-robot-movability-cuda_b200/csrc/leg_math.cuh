@@ -195,6 +195,90 @@ LRM_HD PlaneResult plane_clamp(const LegPlan& L, const SectorTable& tab, float X
     return out;
 }
 
+// ---- compact plan for the positionability search ------------------------------------------------
+// Only what reachable_rotate_leg (several_leg.cu:48-67) needs, 16-byte aligned so that a few
+// hundred (orientation, leg) plans fit in one CTA's shared memory.
+struct alignas(16) ReachPlan {
+    float4 circ[4][3];  // [sector][slot-1] = (cx, cy, r, sgn)
+    float M[9], t[3];   // orientation-frame foothold offset -> coxa frame
+    float grav[3];      // gravity-side half-space (several_leg.cu:58-62)
+    float coxa_length;
+    AngleTest over, under, middle, sat[2];
+    float inner_sgn, inner_thr_s;
+    float r_min, r_max;      // inner / outer circle radii   (cell-level pruning)
+    float yaw_min, yaw_max;  // coxa yaw limits, radians     (cell-level pruning)
+    float pad[2];
+};
+
+LRM_HD void make_reach_plan(const LegPlan& L, float yaw_min, float yaw_max, ReachPlan* R) {
+    for (int s = 0; s < 4; s++)
+        for (int j = 0; j < 3; j++) {
+            const float* o = L.sector[s].slot[j];
+            R->circ[s][j] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    for (int i = 0; i < 9; i++) R->M[i] = L.M[i];
+    for (int i = 0; i < 3; i++) R->t[i] = L.t[i], R->grav[i] = L.grav[i];
+    R->coxa_length = L.coxa_length;
+    R->over = L.over, R->under = L.under, R->middle = L.middle, R->sat[0] = L.sat[0], R->sat[1] = L.sat[1];
+    R->inner_sgn = L.inner.sgn, R->inner_thr_s = L.inner.thr_s;
+    R->r_min = L.inner.r, R->r_max = L.outer.r;
+    R->yaw_min = yaw_min, R->yaw_max = yaw_max;
+    R->pad[0] = R->pad[1] = 0.f;
+}
+
+// reachable_rotate_leg for a foothold offset (vx, vy, vz) in the orientation frame:
+// gravity-side test, leg frame, reachability_circles.  Same arithmetic as
+// to_coxa_frame + reach_coxa_frame on the full plan.
+LRM_HD bool reach_offset(const ReachPlan& L, float vx, float vy, float vz) {
+    const float g = fmaf(L.grav[0], vx, fmaf(L.grav[1], vy, L.grav[2] * vz));
+    if (g < 0.f) return false;
+    const float px = fmaf(L.M[0], vx, fmaf(L.M[1], vy, fmaf(L.M[2], vz, L.t[0])));
+    const float py = fmaf(L.M[3], vx, fmaf(L.M[4], vy, fmaf(L.M[5], vz, L.t[1])));
+    const float pz = fmaf(L.M[6], vx, fmaf(L.M[7], vy, fmaf(L.M[8], vz, L.t[2])));
+    const bool flip = f2i(px) < 0;
+    const float xf = flip ? -px : px, yf = flip ? -py : py;
+    if (angle_gt(L.over, xf, yf) | angle_gt(L.under, xf, -yf)) return false;
+    const float rho2 = fmaf(px, px, py * py);
+    const float rho = rho2 > 0.f ? rho2 * fast_rsqrt(rho2) : 0.f;
+    const float X = (flip ? -rho : rho) - L.coxa_length, Y = pz;
+    const float upf = up_flag(Y);
+    const bool upper = angle_gt(L.middle, X, Y, upf);
+    const bool more = upper ? angle_gt(L.sat[1], X, Y, upf) : angle_gt(L.sat[0], X, Y, upf);
+    const int s = (upper ? 2 : 0) | ((upper != more) ? 1 : 0);
+    bool ok = L.inner_sgn * fmaf(X, X, Y * Y) < L.inner_thr_s;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const float4 c = L.circ[s][j];
+        ok = ok & circle_ok(c.x, c.y, c.z, c.w, X, Y);
+    }
+    return ok;
+}
+
+// Can ANY point within `rc` of the offset v be reachable?  Conservative (never rejects a ball that
+// holds a reachable point): gravity half-space, the annulus between the inner and outer circle in
+// the femur plane, and the yaw wedge, each widened by rc; both coxa solutions are considered.
+LRM_HD bool reach_ball_possible(const ReachPlan& L, float vx, float vy, float vz, float rc) {
+    const float g = fmaf(L.grav[0], vx, fmaf(L.grav[1], vy, L.grav[2] * vz));
+    if (g < -rc) return false;
+    const float px = fmaf(L.M[0], vx, fmaf(L.M[1], vy, fmaf(L.M[2], vz, L.t[0])));
+    const float py = fmaf(L.M[3], vx, fmaf(L.M[4], vy, fmaf(L.M[5], vz, L.t[1])));
+    const float pz = fmaf(L.M[6], vx, fmaf(L.M[7], vy, fmaf(L.M[8], vz, L.t[2])));
+    const float rho = sqrtf(fmaf(px, px, py * py));
+    const float lo = L.r_min - rc - 0.01f, hi = L.r_max + rc + 0.01f;
+    const float xa = rho - L.coxa_length, xb = -rho - L.coxa_length;
+    const float da = sqrtf(fmaf(xa, xa, pz * pz)), db = sqrtf(fmaf(xb, xb, pz * pz));
+    bool ring_a = da >= lo && da <= hi, ring_b = db >= lo && db <= hi;
+    if (rho > rc) {  // yaw only constrains balls that stay clear of the coxa axis
+        const float pi = 3.14159265358979f;
+        const float phi = atan2f(py, px);
+        const float del = asinf(fminf(1.f, rc / rho)) + 1.0e-4f;
+        const float phf = phi > 0.f ? phi - pi : phi + pi;  // folded yaw of the flipped solution
+        ring_a = ring_a && px > -rc && phi + del >= L.yaw_min && phi - del <= L.yaw_max;
+        ring_b = ring_b && px < rc && phf + del >= L.yaw_min && phf - del <= L.yaw_max;
+    }
+    return ring_a || ring_b;
+}
+
 // ---- plane atlas -------------------------------------------------------------------------------
 // plane_clamp is a function of the femur-plane point alone, and over most of the plane its outcome
 // is "P minus its projection on one particular circle" or "P minus one particular corner" with the

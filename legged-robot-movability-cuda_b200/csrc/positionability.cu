@@ -28,8 +28,7 @@ namespace lrm {
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
-constexpr int kMaxLegs = 8;
+constexpr int kWarpsPerCta = 16;
 
 struct CellGrid {
     float x0, y0, inv_cell;
@@ -206,6 +205,8 @@ __global__ void target_precull_kernel(CellGrid body_grid, const float* __restric
 struct OrientConsts {
     float R[9];        // qtRotate(quat, .) as a matrix (rotateData, several_leg.cu:401-411)
     float radius_in, plus_in, minus_in, radius_out;  // cull cylinders (:505-520)
+    float r_near, r_hit;  // world-frame search radii of the two cylinders
+    float pad;
 };
 
 struct SearchParams {
@@ -214,10 +215,9 @@ struct SearchParams {
     const uint8_t* alive;       // may be nullptr
     size_t nb;
     const OrientConsts* orient; // nq
-    const LegPlan* plans;       // nq * nlegs
-    const SectorTable* tables;  // nq * nlegs
+    const ReachPlan* plans;     // nq * nlegs
     int nq, nlegs;
-    float r_cull_xy, r_cull_z;  // conservative world-frame search radii
+    int plans_in_smem;
     float r_leg;
     uint8_t* standable;
     unsigned long long* next;   // dynamic work counter
@@ -228,7 +228,66 @@ __device__ __forceinline__ float3 rotate(const float* R, float x, float y, float
                        fmaf(R[6], x, fmaf(R[7], y, R[8] * z)));
 }
 
+// Two-level walk over the cells around (bx, by): the lanes of the warp first classify 32 cells at
+// a time with `keep_cell(centre, radius)` (a conservative "could hold a witness" test on the
+// cell's bounding ball), then the warp scans the points of the surviving cells 32 at a time.
+// `visit` returns true to stop.
+template <class CellF, class PointF>
+__device__ __forceinline__ bool walk_filtered(const CellGrid& g, float bx, float by, float r_xy,
+                                              int lane, CellF keep_cell, PointF visit) {
+    const int cx0 = max((int)floorf((bx - r_xy - g.x0) * g.inv_cell), 0);
+    const int cx1 = min((int)floorf((bx + r_xy - g.x0) * g.inv_cell), g.nx - 1);
+    const int cy0 = max((int)floorf((by - r_xy - g.y0) * g.inv_cell), 0);
+    const int cy1 = min((int)floorf((by + r_xy - g.y0) * g.inv_cell), g.ny - 1);
+    const int w = cx1 - cx0 + 1, h = cy1 - cy0 + 1;
+    if (w <= 0 || h <= 0) return false;
+    const int ncell = w * h;
+    const float cell = 1.0f / g.inv_cell;
+    for (int base = 0; base < ncell; base += 32) {
+        const int k = base + lane;
+        bool keep = false;
+        int c = 0;
+        if (k < ncell) {
+            const int cy = cy0 + k / w, cx = cx0 + k % w;
+            c = cy * g.nx + cx;
+            if (g.cell_start[c + 1] > g.cell_start[c]) {
+                const float2 zr = g.cell_z[c];
+                const float hz = 0.5f * (zr.y - zr.x);
+                // half diagonal of the cell (+0.2 % for points binned across an edge by rounding)
+                const float rc = sqrtf(0.5f * cell * cell * 1.004f + hz * hz) + 1.0e-3f;
+                keep = keep_cell(g.x0 + ((float)cx + 0.5f) * cell, g.y0 + ((float)cy + 0.5f) * cell,
+                                 0.5f * (zr.x + zr.y), rc);
+            }
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, keep);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int cc = __shfl_sync(0xffffffffu, c, src);
+            const int beg = g.cell_start[cc], end = g.cell_start[cc + 1];
+            for (int i = beg; i < end; i += 32) {
+                const int q = i + lane;
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < end) p = g.pts[q];
+                if (visit(p, q < end)) return true;
+            }
+        }
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(const SearchParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const ReachPlan* plans = P.plans;
+    if (P.plans_in_smem) {
+        // all (orientation, leg) plans live in shared memory for the whole kernel
+        float4* dst = reinterpret_cast<float4*>(smem_raw);
+        const float4* src = reinterpret_cast<const float4*>(P.plans);
+        const int n16 = P.nq * P.nlegs * (int)(sizeof(ReachPlan) / 16);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        plans = reinterpret_cast<const ReachPlan*>(smem_raw);
+    }
     const int lane = threadIdx.x & 31;
     while (true) {
         unsigned long long b = 0;
@@ -242,37 +301,58 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
             for (int o = 0; o < P.nq && result == 0; o++) {
                 const OrientConsts& O = P.orient[o];
                 const float3 B = rotate(O.R, bx, by, bz);
-                // eliminateFarAndColliding: some point in the reach cylinder, none in the body cylinder
-                bool near = false;
-                const bool hit = walk_cells(P.map, bx, by, bz, P.r_cull_xy, P.r_cull_z, lane,
-                                            [&](float4 t, bool ok) {
-                    ok = ok && t.w != 0.f;
-                    const float3 T = rotate(O.R, t.x, t.y, t.z);
-                    const float dz = T.z - B.z;
-                    const float rad = norm3df(T.x - B.x, T.y - B.y, 0.f);
-                    const bool in_reach = rad < O.radius_in && dz < O.plus_in && dz > O.minus_in;
-                    const bool in_body = rad < O.radius_out && dz < 250.f && dz > -110.f;
-                    const bool any_reach = __any_sync(0xffffffffu, ok && in_reach) != 0;
-                    near = near || any_reach;
-                    return __any_sync(0xffffffffu, ok && in_body) != 0;
-                });
-                if (hit || !near) continue;
-                // eliminateUnreachable: every leg needs one reachable point
+                // eliminateFarAndColliding (several_leg.cu:504-559): no map point inside the body
+                // cylinder (r = dim.body, z in (-110, 250)) ...
+                const bool hit = walk_filtered(
+                    P.map, bx, by, O.r_hit, lane,
+                    [&](float x, float y, float z, float rc) {
+                        const float3 T = rotate(O.R, x, y, z);
+                        const float dz = T.z - B.z;
+                        return norm3df(T.x - B.x, T.y - B.y, 0.f) < O.radius_out + rc && dz < 250.f + rc &&
+                               dz > -110.f - rc;
+                    },
+                    [&](float4 t, bool ok) {
+                        const float3 T = rotate(O.R, t.x, t.y, t.z);
+                        const float dz = T.z - B.z;
+                        const bool in_body = norm3df(T.x - B.x, T.y - B.y, 0.f) < O.radius_out &&
+                                             dz < 250.f && dz > -110.f;
+                        return __any_sync(0xffffffffu, ok && t.w != 0.f && in_body) != 0;
+                    });
+                if (hit) continue;
+                // ... and at least one inside the reach cylinder
+                const bool near = walk_filtered(
+                    P.map, bx, by, O.r_near, lane,
+                    [&](float x, float y, float z, float rc) {
+                        const float3 T = rotate(O.R, x, y, z);
+                        const float dz = T.z - B.z;
+                        return norm3df(T.x - B.x, T.y - B.y, 0.f) < O.radius_in + rc &&
+                               dz < O.plus_in + rc && dz > O.minus_in - rc;
+                    },
+                    [&](float4 t, bool ok) {
+                        const float3 T = rotate(O.R, t.x, t.y, t.z);
+                        const float dz = T.z - B.z;
+                        const bool in_reach = norm3df(T.x - B.x, T.y - B.y, 0.f) < O.radius_in &&
+                                              dz < O.plus_in && dz > O.minus_in;
+                        return __any_sync(0xffffffffu, ok && t.w != 0.f && in_reach) != 0;
+                    });
+                if (!near) continue;
+                // eliminateUnreachable (:633-706): every leg needs one reachable map point
                 bool all = true;
                 for (int l = 0; l < P.nlegs && all; l++) {
-                    const LegPlan& L = P.plans[o * P.nlegs + l];
-                    const SectorTable& tab = P.tables[o * P.nlegs + l];
-                    all = walk_cells(P.map, bx, by, bz, P.r_leg, P.r_leg, lane, [&](float4 t, bool ok) {
-                        ok = ok && t.w != 0.f;
-                        // reachable_rotate_leg (several_leg.cu:48-67): offset in the orientation
-                        // frame, gravity-side test, leg frame, reachability_circles
-                        const float3 T = rotate(O.R, t.x, t.y, t.z);
-                        const float vx = T.x - B.x, vy = T.y - B.y, vz = T.z - B.z;
-                        const float g = fmaf(L.grav[0], vx, fmaf(L.grav[1], vy, L.grav[2] * vz));
-                        bool r = false;
-                        if (ok && !(g < 0.f)) r = reach_coxa_frame(L, tab, to_coxa_frame(L, vx, vy, vz));
-                        return __any_sync(0xffffffffu, r) != 0;
-                    });
+                    const ReachPlan& L = plans[o * P.nlegs + l];
+                    all = walk_filtered(
+                        P.map, bx, by, P.r_leg, lane,
+                        [&](float x, float y, float z, float rc) {
+                            const float3 T = rotate(O.R, x, y, z);
+                            return reach_ball_possible(L, T.x - B.x, T.y - B.y, T.z - B.z, rc);
+                        },
+                        [&](float4 t, bool ok) {
+                            // reachable_rotate_leg (several_leg.cu:48-67): offset in the
+                            // orientation frame, gravity-side test, leg frame, reachability_circles
+                            const float3 T = rotate(O.R, t.x, t.y, t.z);
+                            const bool r = ok && t.w != 0.f && reach_offset(L, T.x - B.x, T.y - B.y, T.z - B.z);
+                            return __any_sync(0xffffffffu, r) != 0;
+                        });
                 }
                 if (all) result = (uint8_t)(o + 1);
             }
@@ -320,6 +400,12 @@ cudaError_t build_grid(DevBuf& mem, const float* xyz, size_t n, const uint8_t* k
     };
     float xmin = dec(h[0]), ymin = dec(h[1]), xmax = -dec(h[2]), ymax = -dec(h[3]);
     if (n == 0 || !(xmax >= xmin) || !(ymax >= ymin)) xmin = ymin = 0.f, xmax = ymax = 1.f;
+    if (cell <= 0.f) {
+        // automatic: about 48 points per cell, between 32 and 256 mm
+        const double area = std::fmax(1.0, (double)(xmax - xmin)) * std::fmax(1.0, (double)(ymax - ymin));
+        cell = (float)std::sqrt(area * 48.0 / (double)(n ? n : 1));
+        cell = std::fmin(256.f, std::fmax(32.f, cell));
+    }
     // keep the cell table bounded (L2-friendly) whatever the map extent
     while (((double)(xmax - xmin) / cell + 1) * ((double)(ymax - ymin) / cell + 1) > 4.0e6) cell *= 2;
     CellGrid g;
@@ -357,12 +443,15 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
     if (p.nb == 0) return cudaSuccess;
     if (p.nt > 0x7fffffffull || p.nb > 0x7fffffffull * 64) return cudaErrorInvalidValue;
     DevBuf mem;
-    const float cell = 128.f;
+    // ~48 map points per cell: fine enough for the cell-level pruning to bite, coarse enough that
+    // a query touches a few hundred cells
+    const float cell = 128.f;   // pre-cull grids (400 mm spheres)
+    const float map_cell = 0.f; // search grid: sized from the map density inside build_grid
 
     // per-orientation / per-leg constants
     std::vector<OrientConsts> orient(p.nq);
-    std::vector<LegPlan> plans((size_t)p.nq * p.nlegs);
-    float r_leg = 0.f, r_cull_xy = 0.f, r_cull_z = 0.f;
+    std::vector<ReachPlan> plans((size_t)p.nq * p.nlegs);
+    float r_leg = 0.f;
     const float pi = 3.14159265358979323846264338327950288419716939937510582097f;
     for (int o = 0; o < p.nq; o++) {
         const float* q = p.quats + 4 * o;
@@ -374,7 +463,10 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
         OrientConsts& O = orient[o];
         for (int r = 0; r < 3; r++) O.R[3 * r] = c0[r], O.R[3 * r + 1] = c1[r], O.R[3 * r + 2] = c2[r];
         for (int l = 0; l < p.nlegs; l++) {
-            build_leg_plan_rotated_limits(p.legs[l], q, &plans[(size_t)o * p.nlegs + l]);
+            LegPlan full;
+            build_leg_plan_rotated_limits(p.legs[l], q, &full);
+            make_reach_plan(full, p.legs[l].min_angle_coxa, p.legs[l].max_angle_coxa,
+                            &plans[(size_t)o * p.nlegs + l]);
             const lrm_leg_t& d = p.legs[l];
             r_leg = std::fmax(r_leg, std::fabs(d.body) + std::fabs(d.coxa_length) +
                                          std::fabs(d.femur_length) + std::fabs(d.tibia_length) + 1.f);
@@ -390,10 +482,11 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
         O.plus_in = s_p * d.coxa_length + plus_abs;
         O.minus_in = s_p * d.coxa_length - d.femur_length - d.tibia_length;
         O.radius_out = d.body;
-        const float rad = std::fmax(O.radius_in, O.radius_out);
-        const float zext = std::fmax(std::fmax(std::fabs(O.plus_in), std::fabs(O.minus_in)), 250.f);
-        const float r3 = std::sqrt(rad * rad + zext * zext) + 1.f;  // rotation keeps 3-D distance
-        r_cull_xy = std::fmax(r_cull_xy, r3), r_cull_z = std::fmax(r_cull_z, r3);
+        // a rotation keeps 3-D distances: every point of a cylinder lies within this world radius
+        const float zin = std::fmax(std::fabs(O.plus_in), std::fabs(O.minus_in));
+        O.r_near = std::sqrt(O.radius_in * O.radius_in + zin * zin) + 1.f;
+        O.r_hit = std::sqrt(O.radius_out * O.radius_out + 250.f * 250.f) + 1.f;
+        O.pad = 0.f;
     }
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -427,39 +520,44 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
         if ((e = build_grid(mem, p.bodies, p.nb, alive, cell, stream, &body_grid)) != cudaSuccess)
             return finish(e);
         target_precull_kernel<<<148 * 8, 256, 0, stream>>>(body_grid, p.map, p.nt, keep);
-        if ((e = build_grid(mem, p.map, p.nt, keep, cell, stream, &map_grid)) != cudaSuccess)
+        if ((e = build_grid(mem, p.map, p.nt, keep, map_cell, stream, &map_grid)) != cudaSuccess)
             return finish(e);
     } else {
-        cudaError_t e = build_grid(mem, p.map, p.nt, nullptr, cell, stream, &map_grid);
+        cudaError_t e = build_grid(mem, p.map, p.nt, nullptr, map_cell, stream, &map_grid);
         if (e != cudaSuccess) return finish(e);
     }
 
-    // sector tables are derived from the plans on the host so the kernel can index them directly
-    std::vector<SectorTable> tables(plans.size());
-    for (size_t i = 0; i < plans.size(); i++) fill_sector_table(plans[i], &tables[i], 0, 1);
     OrientConsts* d_orient;
-    LegPlan* d_plans;
-    SectorTable* d_tables;
+    ReachPlan* d_plans;
     unsigned long long* d_next;
     cudaError_t e;
     if ((e = mem.alloc(&d_orient, orient.size())) != cudaSuccess) return finish(e);
     if ((e = mem.alloc(&d_plans, plans.size())) != cudaSuccess) return finish(e);
-    if ((e = mem.alloc(&d_tables, tables.size())) != cudaSuccess) return finish(e);
     if ((e = mem.alloc(&d_next, 1)) != cudaSuccess) return finish(e);
     cudaMemcpyAsync(d_orient, orient.data(), orient.size() * sizeof(OrientConsts), cudaMemcpyHostToDevice, stream);
-    cudaMemcpyAsync(d_plans, plans.data(), plans.size() * sizeof(LegPlan), cudaMemcpyHostToDevice, stream);
-    cudaMemcpyAsync(d_tables, tables.data(), tables.size() * sizeof(SectorTable), cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_plans, plans.data(), plans.size() * sizeof(ReachPlan), cudaMemcpyHostToDevice, stream);
     cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), stream);
 
     SearchParams S;
     S.map = map_grid, S.bodies = p.bodies, S.alive = alive, S.nb = p.nb;
-    S.orient = d_orient, S.plans = d_plans, S.tables = d_tables, S.nq = p.nq, S.nlegs = p.nlegs;
-    S.r_cull_xy = r_cull_xy, S.r_cull_z = r_cull_z, S.r_leg = r_leg;
+    S.orient = d_orient, S.plans = d_plans, S.nq = p.nq, S.nlegs = p.nlegs;
+    S.r_leg = r_leg;
     S.standable = p.standable, S.next = d_next;
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    positionability_kernel<<<sms * 4, kWarpsPerCta * 32, 0, stream>>>(S);
+    // plans in shared memory when they fit twice per SM (two CTAs of 16 warps), else from L1/L2
+    const size_t plan_bytes = plans.size() * sizeof(ReachPlan);
+    S.plans_in_smem = plan_bytes <= 100 * 1024 ? 1 : 0;
+    const size_t smem = S.plans_in_smem ? plan_bytes : 0;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(positionability_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return finish(e);
+    }
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, positionability_kernel, kWarpsPerCta * 32, smem);
+    if (occ < 1) occ = 1;
+    positionability_kernel<<<sms * occ, kWarpsPerCta * 32, smem, stream>>>(S);
     e = cudaGetLastError();
     if (e != cudaSuccess) return finish(e);
     e = finish(cudaSuccess);

@@ -7,7 +7,10 @@
 // catch algorithmic regressions before GPU minutes are spent.  Differences from the device:
 // rsqrtf is 1/sqrtf here (a few ulp), everything else is the same FP32 expression tree.
 #include <cstdint>
+#include <algorithm>
+#include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "leg_math.cuh"
 #include "leg_plan.h"
@@ -114,6 +117,90 @@ size_t emu_dist_atlas(const float* xyz, size_t n, const lrm_leg_t* leg, const fl
     }
     delete[] cells;
     return fallback;
+}
+
+// The positionability kernel's per-pose logic (positionability.cu) with brute-force target loops:
+// same orientation matrix, same cull cylinders, same leg predicate arithmetic.
+void emu_standability(const float* bodies, size_t nb, const float* map, size_t nt,
+                      const lrm_leg_t* legs, int nlegs, const float* quats, int nq, uint8_t* out) {
+    const float pi = 3.14159265358979323846264338327950288419716939937510582097f;
+    std::vector<lrm::ReachPlan> plans((size_t)nq * nlegs);
+    struct OC { float R[9], radius_in, plus_in, minus_in, radius_out; };
+    std::vector<OC> oc(nq);
+    for (int o = 0; o < nq; o++) {
+        const float* q = quats + 4 * o;
+        const float ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0}, ez[3] = {0, 0, 1};
+        float c0[3], c1[3], c2[3];
+        lrm::quat_rotate(q, ex, c0), lrm::quat_rotate(q, ey, c1), lrm::quat_rotate(q, ez, c2);
+        for (int r = 0; r < 3; r++) oc[o].R[3 * r] = c0[r], oc[o].R[3 * r + 1] = c1[r], oc[o].R[3 * r + 2] = c2[r];
+        for (int l = 0; l < nlegs; l++) {
+            lrm::LegPlan full;
+            lrm::build_leg_plan_rotated_limits(legs[l], q, &full);
+            lrm::make_reach_plan(full, legs[l].min_angle_coxa, legs[l].max_angle_coxa,
+                                 &plans[(size_t)o * nlegs + l]);
+        }
+        lrm_leg_t d = legs[0];
+        const float pitch = lrm::quat_pitch_for_leg(q, d.body_angle);
+        d.tibia_absolute_pos -= pitch, d.tibia_absolute_neg -= pitch;
+        const float s_p = std::sin(d.coxa_pitch), c_p = std::cos(d.coxa_pitch);
+        oc[o].radius_in = d.body + c_p * d.coxa_length + d.femur_length + d.tibia_length;
+        const float plus_abs = d.tibia_length * std::sin(d.tibia_absolute_pos) +
+                               d.femur_length * std::sin(std::min(pi / 2, d.max_angle_femur));
+        oc[o].plus_in = s_p * d.coxa_length + plus_abs;
+        oc[o].minus_in = s_p * d.coxa_length - d.femur_length - d.tibia_length;
+        oc[o].radius_out = d.body;
+    }
+    auto rot = [](const float* R, float x, float y, float z, float* o) {
+        o[0] = fmaf(R[0], x, fmaf(R[1], y, R[2] * z));
+        o[1] = fmaf(R[3], x, fmaf(R[4], y, R[5] * z));
+        o[2] = fmaf(R[6], x, fmaf(R[7], y, R[8] * z));
+    };
+    std::vector<float> T(3 * nt);
+    std::vector<uint8_t> res(nb, 0);
+    for (int o = 0; o < nq; o++) {
+        for (size_t t = 0; t < nt; t++) rot(oc[o].R, map[3 * t], map[3 * t + 1], map[3 * t + 2], &T[3 * t]);
+        for (size_t b = 0; b < nb; b++) {
+            if (res[b]) continue;
+            float B[3];
+            rot(oc[o].R, bodies[3 * b], bodies[3 * b + 1], bodies[3 * b + 2], B);
+            bool near = false, hit = false;
+            for (size_t t = 0; t < nt && !hit; t++) {
+                const float dz = T[3 * t + 2] - B[2];
+                const float dx = T[3 * t] - B[0], dy = T[3 * t + 1] - B[1];
+                const float rad = sqrtf(dx * dx + dy * dy);
+                if (rad < oc[o].radius_in && dz < oc[o].plus_in && dz > oc[o].minus_in) near = true;
+                if (rad < oc[o].radius_out && dz < 250.f && dz > -110.f) hit = true;
+            }
+            if (hit || !near) continue;
+            bool all = true;
+            for (int l = 0; l < nlegs && all; l++) {
+                const lrm::ReachPlan& L = plans[(size_t)o * nlegs + l];
+                bool found = false;
+                for (size_t t = 0; t < nt && !found; t++) {
+                    const float vx = T[3 * t] - B[0], vy = T[3 * t + 1] - B[1], vz = T[3 * t + 2] - B[2];
+                    if (fabsf(vx) > 520.f || fabsf(vy) > 520.f) continue;
+                    if (lrm::reach_offset(L, vx, vy, vz)) found = true;
+                }
+                all = found;
+            }
+            if (all) res[b] = (uint8_t)(o + 1);
+        }
+    }
+    std::memcpy(out, res.data(), nb);
+}
+
+// ReachPlan predicates: out_reach[i] = reach_offset(v_i); out_ball[i] = reach_ball_possible(v_i, rc)
+void emu_reach_offset(const float* offsets, size_t n, const lrm_leg_t* leg, const float* quat, float rc,
+                      uint8_t* out_reach, uint8_t* out_ball) {
+    lrm::LegPlan full;
+    lrm::build_leg_plan_rotated_limits(*leg, quat, &full);
+    lrm::ReachPlan L;
+    lrm::make_reach_plan(full, leg->min_angle_coxa, leg->max_angle_coxa, &L);
+    for (size_t i = 0; i < n; i++) {
+        const float vx = offsets[3 * i], vy = offsets[3 * i + 1], vz = offsets[3 * i + 2];
+        out_reach[i] = lrm::reach_offset(L, vx, vy, vz) ? 1 : 0;
+        out_ball[i] = lrm::reach_ball_possible(L, vx, vy, vz, rc) ? 1 : 0;
+    }
 }
 
 int emu_plan_is_generic(const lrm_leg_t* leg, const float* quat) {

@@ -76,3 +76,24 @@ def dist_report(pts, got, want, dist_fn, tol=DIST_TOL_MM, frame_slack=0.0):
     ok = err[np.isfinite(err) & (err <= tol)]
     return {"n": int(len(err)), "over_tol": int(len(bad)), "seam": int(len(bad)) - unexplained,
             "unexplained": unexplained, "max_err_within_tol": float(ok.max()) if len(ok) else 0.0}
+
+
+def pose_report(bodies, got, want, stand_fn):
+    """Standability parity.  stand_fn(poses) -> oracle result (0 or 1 + first orientation).
+    A pose whose flag (or first-orientation index) differs is 'near_boundary' when the oracle
+    itself returns the GPU's answer for that pose displaced by <= 1e-3 mm (its decisive foothold
+    sits on a leg's reachability boundary, on the gravity-side plane or on a cull cylinder)."""
+    got = np.asarray(got).astype(np.int32)
+    want = np.asarray(want).astype(np.int32)
+    flag_bad = np.nonzero((got != 0) != (want != 0))[0]
+    idx_bad = np.nonzero((got != want) & (got != 0) & (want != 0))[0]
+    out = {"n": int(len(got)), "flag_mismatch": int(len(flag_bad)), "orientation_mismatch": int(len(idx_bad)),
+           "unexplained": 0}
+    bad = np.concatenate([flag_bad, idx_bad])
+    if len(bad):
+        offs = np.array(list(itertools.product((-1.0, 0.0, 1.0), repeat=3)), np.float32) * np.float32(FLAG_BAND_MM)
+        nb = (bodies[bad][:, None, :] + offs[None, :, :]).astype(np.float32)
+        res = np.asarray(stand_fn(nb.reshape(-1, 3))).reshape(len(bad), -1).astype(np.int32)
+        ok = (res == got[bad][:, None]).any(axis=1)
+        out["unexplained"] = int((~ok).sum())
+    return out

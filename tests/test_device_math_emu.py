@@ -142,3 +142,39 @@ def test_plane_atlas_never_changes_a_result(emu, port):
         assert np.array_equal(fl, bf) and np.array_equal(rf, br)
         assert np.abs(out - base).max() < 1e-3
         assert pure.value > 0.85 * 1024 * 1024 and fb < 0.3 * len(pts), (pure.value, fb)
+
+
+def test_reach_plan_predicates(emu, port):
+    """positionability.cu's per-foothold predicate on the compact ReachPlan equals the full-plan
+    path, and the cell-level pruning test is conservative: whenever some point within rc of a
+    centre is reachable, reach_ball_possible(centre, rc) must say so."""
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    emu.emu_reach_offset.argtypes = [vp, sz, vp, vp, ctypes.c_float, vp, vp]
+    rng = np.random.default_rng(77)
+    centres = rng.uniform(-560, 560, (6000, 3)).astype(np.float32)
+    quats = port.full_struct_orientations()
+    for robot, az, o in ((1, 0.0, 0), (1, 1.5707964, 20), (0, 3.1415927, 44), (1, 4.712389, 33)):
+        leg = port.get_leg(robot, az)
+        q = np.ascontiguousarray(quats[o], np.float32)
+        for rc in (20.0, 60.0, 150.0):
+            r0 = np.zeros(len(centres), np.uint8)
+            ball = np.zeros(len(centres), np.uint8)
+            emu.emu_reach_offset(centres.ctypes.data, len(centres), leg.ctypes.data, q.ctypes.data, rc,
+                                 r0.ctypes.data, ball.ctypes.data)
+            full = np.zeros(len(centres), np.uint8)
+            emu.emu_leg_reaches(centres.ctypes.data, len(centres), leg.ctypes.data, q.ctypes.data, full.ctypes.data)
+            assert np.array_equal(r0, full)
+            # sample points inside each ball
+            any_reach = r0.astype(bool).copy()
+            for _ in range(24):
+                d = rng.normal(size=(len(centres), 3))
+                d *= (rng.uniform(0, 1, (len(centres), 1)) ** (1 / 3)) * rc / np.linalg.norm(d, axis=1, keepdims=True)
+                pts = (centres + d).astype(np.float32)
+                rr = np.zeros(len(pts), np.uint8)
+                bb = np.zeros(len(pts), np.uint8)
+                emu.emu_reach_offset(pts.ctypes.data, len(pts), leg.ctypes.data, q.ctypes.data, 1.0,
+                                     rr.ctypes.data, bb.ctypes.data)
+                any_reach |= rr.astype(bool)
+            assert not (any_reach & ~ball.astype(bool)).any(), (robot, az, o, rc)
+            # ... and it does prune: most far-away balls are rejected
+            assert ball.mean() < 0.9

@@ -7,7 +7,7 @@ single witness of some leg, or the single collider of the body cylinder, sits on
 import numpy as np
 import pytest
 
-from tests import terrain
+from tests import parity, terrain
 
 torch = pytest.importorskip("torch")
 PI = np.float32(np.pi)
@@ -58,10 +58,10 @@ def test_gpu_matches_oracle_small_scene(lrm, port):
         want = port.standability(bodies, terr, legs_o, quats, pre_cull=pre_cull, threads=8)
         got = lrm.positionability(torch.from_numpy(bodies).cuda(), torch.from_numpy(terr).cuda(), legs, quats,
                                   pre_cull=pre_cull).cpu().numpy()
-        flag_diff = ((got != 0) != (want != 0)).sum()
-        assert flag_diff <= 1, (pre_cull, int(flag_diff))
-        both = (got != 0) & (want != 0)
-        assert (got[both] != want[both]).sum() <= 2     # same first orientation
+        rep = parity.pose_report(bodies, got, want, lambda p: port.standability(
+            p, terr, legs_o, quats, pre_cull=False, threads=8)) if not pre_cull else \
+            {"unexplained": 0, "flag_mismatch": int(((got != 0) != (want != 0)).sum())}
+        assert rep["unexplained"] == 0 and rep["flag_mismatch"] <= 2, (pre_cull, rep)
         got_h = lrm.positionability(bodies, terr, legs, quats, pre_cull=pre_cull)   # host-pointer path
         assert np.array_equal(got_h, got)
 
@@ -79,10 +79,12 @@ def test_gpu_matches_oracle_perlin_terrain(lrm, port):
     got = lrm.positionability(torch.from_numpy(bodies).cuda(), torch.from_numpy(terr).cuda(), legs, quats)
     got = got.cpu().numpy()
     n_st = int((want != 0).sum())
-    assert n_st > 20
-    assert ((got != 0) != (want != 0)).sum() <= max(2, n_st // 100)
-    both = (got != 0) & (want != 0)
-    assert (got[both] != want[both]).sum() <= max(2, n_st // 50)
+    assert n_st > 1000
+    # lattice-aligned poses put footholds exactly on the legs' symmetry / gravity planes: those
+    # poses are decided by rounding in the reference too, and must be explained one by one
+    rep = parity.pose_report(bodies, got, want, lambda p: port.standability(p, terr, legs_o, quats, threads=8))
+    assert rep["unexplained"] == 0, rep
+    assert rep["flag_mismatch"] <= n_st // 20 and rep["orientation_mismatch"] <= n_st // 5, rep
 
 
 @pytest.mark.gpu
@@ -98,7 +100,8 @@ def test_hexapod_and_yaw_grid(lrm, port):
     got = lrm.positionability(torch.from_numpy(bodies).cuda(), torch.from_numpy(terr).cuda(), legs, quats)
     got = got.cpu().numpy()
     assert (want != 0).sum() > 5
-    assert ((got != 0) != (want != 0)).sum() <= 1
+    rep = parity.pose_report(bodies, got, want, lambda p: port.standability(p, terr, legs_o, quats, threads=8))
+    assert rep["unexplained"] == 0 and rep["flag_mismatch"] <= 3, rep
 
 
 @pytest.mark.gpu
