@@ -176,7 +176,9 @@ def run_b200(args):
     lo, step, dims = lrm.lattice_spec(LO, HI, (nx, ny, nz))
     dev = torch.device("cuda", local)
     pts = torch.empty((n, 3), dtype=torch.float32, device=dev)
-    lrm.make_lattice(pts, lo, step, dims, first=rank * n, count=n)   # this rank's contiguous slab
+    from importlib import import_module
+    first, count = import_module("lrm_b200.slabs").weak_slab(n, rank, world)
+    lrm.make_lattice(pts, lo, step, dims, first=first, count=count)   # this rank's contiguous slab
     flags = torch.empty(n, dtype=torch.uint8, device=dev)
     vec = torch.empty((n, 3), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream()

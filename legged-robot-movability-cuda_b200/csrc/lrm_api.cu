@@ -9,6 +9,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "kernels.h"
@@ -126,9 +127,34 @@ int staged_one_leg(int mode, const lrm::LegPlan& plan, const float* xyz, size_t 
     const bool want_flag = flags != nullptr;
     const size_t chunk = n < kChunkPoints ? n : kChunkPoints;
     const size_t nchunks = (n + chunk - 1) / chunk;
-    Staging st;
-    LRM_CUDA(st.init(chunk, nchunks < (size_t)kSlots ? (int)nchunks : kSlots, want_vec, want_flag),
-             "staging buffers");
+    // Large sweeps reuse one set of streams / events / device buffers per device for the life of
+    // the process (allocating ~600 MiB per call would cost as much as the copies); small calls
+    // use a throw-away set sized to the call, like apply_kernel's malloc + free.
+    static std::mutex pool_mutex;
+    static Staging* pool[64] = {nullptr};
+    std::unique_lock<std::mutex> lock(pool_mutex, std::defer_lock);
+    Staging local;
+    Staging* stp = &local;
+    if (chunk == kChunkPoints) {
+        lock.lock();
+        int dev = 0;
+        cudaGetDevice(&dev);
+        Staging*& slot = pool[dev & 63];
+        if (!slot) {
+            slot = new Staging();
+            cudaError_t e = slot->init(kChunkPoints, kSlots, true, true);
+            if (e != cudaSuccess) {
+                delete slot;
+                slot = nullptr;
+                return cuda_fail(e, "staging buffers");
+            }
+        }
+        stp = slot;
+    } else {
+        LRM_CUDA(local.init(chunk, nchunks < (size_t)kSlots ? (int)nchunks : kSlots, want_vec, want_flag),
+                 "staging buffers");
+    }
+    Staging& st = *stp;
     // order after whatever the caller queued on its stream
     cudaEvent_t begin;
     LRM_CUDA(cudaEventCreateWithFlags(&begin, cudaEventDisableTiming), "cudaEventCreate");
