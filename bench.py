@@ -249,7 +249,9 @@ def run_b200(args):
                        "reachable_points_rank0": reach_count},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_kind,
-                         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                         # ncu dram__bytes_read+write of this kernel (profiles/traffic.json, captured at
+                         # 1e9 points per launch; scaled per point for other sizes)
+                         "traffic": (traffic["dram_bytes_per_point"] * n) if traffic else None,
                          "kernel": "one_leg_stream_kernel<both,aos>", "kernel_ms": kernel_ms,
                          "bytes_per_point": BYTES_PER_POINT},
             "e2e": {"value": e2e_value, "unit": "Gpoints/s", "h2d_bytes_per_step": 12 * ne,
