@@ -136,6 +136,21 @@ LRM_API int lrm_positionability(const float* bodies, size_t nb, const float* map
                         const lrm_posit_opts_t* opts, uint8_t* standable, int on_device,
                         void* stream, float* kernel_ms);
 
+/* ---- body-space octree ------------------------------------------------------------------- */
+/* Replaces apply_oct (several_leg_octree.cu.h:4, several_leg_octree.cu:391-488): adaptive octree
+ * over BODY positions (root box +-5000 mm, settings.h:26; axes stop splitting below 100 mm,
+ * settings.h:17), refined `max_depth` times (the reference's compile-time MAX_DEPTH, settings.h:15,
+ * ships as 1).  A child node is valid when, for some foothold and orientation sample
+ * (octree_util.cu.h:184-198), all four legs mounted at k*pi/4 (settings.h:41-42) reach that same
+ * foothold; it stays "on edge" (and is refined next pass) when a leg's distance vector falls inside
+ * the child box.  Semantics are those of a sequential evaluation (flags OR-ed over all work items
+ * of a pass): the reference's own GPU result is racy (unsynchronised shared flags).
+ * Writes the centres of the valid leaf / raw nodes in the reference's traversal order
+ * (octree_util.cu:123-147) to out_xyz (host, capacity `cap` points) and their number to *count
+ * (which may exceed cap: call again with a larger buffer).  footholds: host or device pointer. */
+LRM_API int lrm_oct(const float* footholds, size_t nt, const lrm_leg_t* leg, int max_depth, float* out_xyz,
+            size_t cap, size_t* count, int on_device, void* stream, float* kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

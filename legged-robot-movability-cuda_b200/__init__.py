@@ -78,6 +78,7 @@ def lib():
         L.lrm_full_struct_orientations.argtypes = [vp, ci]
         L.lrm_positionability.argtypes = [vp, sz, vp, sz, legp, ci, vp, ci,
                                           ctypes.POINTER(PositOpts), vp, ci, vp, fp]
+        L.lrm_oct.argtypes = [vp, sz, legp, ci, vp, sz, ctypes.POINTER(ctypes.c_size_t), ci, vp, fp]
         _lib = L
     return _lib
 
@@ -301,6 +302,23 @@ def positionability(bodies, map_points, legs, quats=None, pre_cull=False, stream
         _check(lib().lrm_positionability(pb, nb, pm, nt, leg_arr, len(legs), quats.ctypes.data,
                                          quats.shape[0], ctypes.byref(opts), out.ctypes.data, 0, None, msp))
     return (out, ms.value) if timing else out
+
+
+def apply_oct(footholds, leg, max_depth=1, cap=1 << 16, stream=None, timing=False):
+    """Body-space octree positionability (apply_oct, several_leg_octree.cu:391-488): centres of the
+    valid leaf / raw nodes after `max_depth` refinement passes, (n, 3) float32 numpy array."""
+    dev, ptr, nt, keep = _prep_points(footholds)
+    ms, msp = _timing(timing)
+    while True:
+        out = np.empty((cap, 3), dtype=np.float32)
+        count = ctypes.c_size_t(0)
+        st = (_stream_ptr(stream) or _torch_stream()) if dev else None
+        _check(lib().lrm_oct(ptr, nt, ctypes.byref(leg), int(max_depth), out.ctypes.data, cap,
+                             ctypes.byref(count), dev, st, msp))
+        if count.value <= cap:
+            res = out[:count.value].copy()
+            return (res, ms.value) if timing else res
+        cap = count.value
 
 
 def robot_full_struct(body_map, target_map, legs):

@@ -4,6 +4,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "leg_plan.h"
 
 namespace lrm {
@@ -43,5 +45,10 @@ struct PositParams {
     uint8_t* standable;    // nb
 };
 cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float* kernel_ms);
+
+// Body-space octree (octree.cu).  d_footholds: device, nt x 3.  centres: xyz triples of the valid
+// leaf / raw nodes in the reference's traversal order.
+cudaError_t run_octree(const float* d_footholds, size_t nt, const lrm_leg_t& leg, int max_depth,
+                       std::vector<float>* centres, cudaStream_t stream, float* kernel_ms);
 
 }  // namespace lrm

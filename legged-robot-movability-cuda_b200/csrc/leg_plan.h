@@ -47,7 +47,7 @@ constexpr int kMaxCorners = 10;
 //   (ah = 2: never, ah = -2: always).
 //   spare of slots 1,2,3: the same three numbers for the inner circle (slot 0) of this sector,
 //   whose valid set can consist of two arcs; inner_b holds the second one (empty: ah = 2).
-struct SectorRow {
+struct alignas(16) SectorRow {
     float slot[3][8];
     float inner_b[4];
 };

@@ -425,4 +425,34 @@ int lrm_positionability(const float* bodies, size_t nb, const float* map, size_t
     return LRM_OK;
 }
 
+int lrm_oct(const float* footholds, size_t nt, const lrm_leg_t* leg, int max_depth, float* out_xyz,
+            size_t cap, size_t* count, int on_device, void* stream_v, float* kernel_ms) {
+    if (!leg || !count) return fail(LRM_ERR_INVALID, "leg / count is NULL");
+    if (nt && !footholds) return fail(LRM_ERR_INVALID, "footholds is NULL");
+    if (cap && !out_xyz) return fail(LRM_ERR_INVALID, "out_xyz is NULL");
+    if (max_depth < 0 || max_depth > 16) return fail(LRM_ERR_INVALID, "max_depth must be 0..16");
+    *count = 0;
+    if (kernel_ms) *kernel_ms = 0.f;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return cuda_fail(ce != cudaSuccess ? ce : cudaErrorNoDevice,
+                         "no CUDA device (this library has no CPU path)");
+    DeviceScratch scratch;
+    const float* d_foot = footholds;
+    if (!on_device) {
+        float* tmp = nullptr;
+        LRM_CUDA(scratch.alloc((void**)&tmp, nt * 12), "cudaMalloc footholds");
+        LRM_CUDA(cudaMemcpyAsync(tmp, footholds, nt * 12, cudaMemcpyHostToDevice, stream), "H2D footholds");
+        d_foot = tmp;
+    }
+    std::vector<float> centres;
+    LRM_CUDA(lrm::run_octree(d_foot, nt, *leg, max_depth, &centres, stream, kernel_ms), "octree");
+    *count = centres.size() / 3;
+    const size_t n = *count < cap ? *count : cap;
+    if (n) std::memcpy(out_xyz, centres.data(), n * 12);
+    return LRM_OK;
+}
+
 }  // extern "C"

@@ -84,6 +84,10 @@ class PortOracle(_Oracle):
         L.op_full_struct_orientations.argtypes = [_vp]
         L.op_quaternion_from_angle_index.argtypes = [ctypes.c_uint, _vp]
         L.op_standability.argtypes = [_vp, _sz, _vp, _sz, _vp, _ci, _vp, _ci, _ci, _vp, _ci]
+        L.op_apply_oct.argtypes = [_vp, _sz, _vp, _ci, _vp, _sz]
+        L.op_apply_oct.restype = _sz
+        L.op_create_child_box.argtypes = [_vp, ctypes.c_uint, _vp, _vp, _vp]
+        L.op_create_child_box.restype = ctypes.c_uint
 
     def get_leg(self, robot, azimuth=0.0):
         out = np.zeros(14, np.float32)
@@ -162,6 +166,25 @@ class PortOracle(_Oracle):
                                legs.ctypes.data, len(legs), quats.ctypes.data, len(quats),
                                1 if pre_cull else 0, out.ctypes.data, threads)
         return out
+
+
+    def apply_oct(self, footholds, leg, max_depth=1, cap=1 << 20):
+        """Sequential restatement of apply_oct (several_leg_octree.cu:391-488): centres of the
+        valid leaf / raw nodes after `max_depth` refinement passes."""
+        f = _as_f32(footholds, 3)
+        leg = leg_array(leg)
+        out = np.zeros((cap, 3), np.float32)
+        n = self.L.op_apply_oct(f.ctypes.data, len(f), leg.ctypes.data, max_depth, out.ctypes.data, cap)
+        assert n <= cap
+        return out[:n].copy()
+
+    def create_child_box(self, parent6, child, small3=(0, 0, 0)):
+        p = _as_f32(parent6)
+        s = np.ascontiguousarray(small3, np.uint8)
+        c = np.zeros(6, np.float32)
+        missing = ctypes.c_int(0)
+        r = self.L.op_create_child_box(p.ctypes.data, child, s.ctypes.data, c.ctypes.data, ctypes.byref(missing))
+        return r, c, missing.value
 
 
 class RefOracle(_Oracle):

@@ -6,7 +6,7 @@
  * double, glibc libm, no FMA contraction: build with -ffp-contract=off).  Each function cites the
  * reference file:line it follows.  It is pinned (bit-exact) against the compiled reference
  * (oracle/_ref/libref_oracle.so, built from /root/reference by oracle/Makefile) by
- * tests/test_oracle_pin.py in the build container, and against the committed golden vectors in
+ * tests/test_oracle_golden.py in the build container, and against the committed golden vectors in
  * tests/golden/ (generated from the compiled reference by tests/golden/make_golden.py) anywhere.
  *
  * The multi-leg part (op_standability) restates code that is __device__-only in the reference
@@ -763,4 +763,204 @@ void op_standability(const float* bodies, size_t nb, const float* targets, size_
         op_grid_free(&g);
     }
     free(todo); free(body_rot); free(targ_rot); free(legs_rot); free(targ); free(body_alive);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Body-space octree (several_leg_octree.cu, octree_util.cu.h) — sequential restatement.       */
+/* The reference builds this tree with dynamic parallelism, device malloc and unsynchronised   */
+/* shared flags, so its GPU result is not deterministic; this single-threaded      */
+/* restatement is the arbiter: flags are OR-ed over all work items of a pass and written after  */
+/* the pass, children already valid BEFORE the pass are skipped (several_leg_octree.cu:57-60).  */
+
+#define OP_MINBOX 100.0f       /* settings.h:17 */
+#define OP_DEADQUADRAN 128     /* settings.h:30 */
+#define OP_ROT_BELOW 50.0f     /* settings.h:32 */
+#define OP_CONVEX_RADIUS 100.0f
+
+typedef struct { op_f3 center, half; } op_box;
+
+static unsigned op_reverse_bits(unsigned b) { /* octree_util.cu.h:78-84 */
+    b = (((b & 0xaaaaaaaau) >> 1) | ((b & 0x55555555u) << 1));
+    b = (((b & 0xccccccccu) >> 2) | ((b & 0x33333333u) << 2));
+    b = (((b & 0xf0f0f0f0u) >> 4) | ((b & 0x0f0f0f0fu) << 4));
+    b = (((b & 0xff00ff00u) >> 8) | ((b & 0x00ff00ffu) << 8));
+    return (b >> 16) | (b << 16);
+}
+static unsigned op_shift_between(unsigned v, unsigned lo, unsigned up, unsigned shift) { /* :42-61 */
+    unsigned mask = ((1u << (up + 1)) - 1) ^ ((1u << lo) - 1);
+    unsigned in = v & mask;
+    unsigned sh = (in << shift) & mask;
+    return (v & ~mask) | sh;
+}
+/* octree_util.cu.h:105-151 with SUB_QUAD = 1 */
+static unsigned op_child_box(op_box parent, op_box* child, unsigned quad_count, unsigned index,
+                             const uint8_t* small, int* missing) {
+    *child = parent;
+    unsigned quadr = op_reverse_bits(index) >> (32 - quad_count);
+    float* off[3] = {&child->half.x, &child->half.y, &child->half.z};
+    unsigned sub = quadr & ((1u << quad_count) - 1 + (1u << quad_count));
+    float div[3] = {2, 2, 2};
+    unsigned upper = quad_count - 1;
+    *missing = 0;
+    for (unsigned q = 0; q < 3; q++) {
+        if (*off[q] < OP_MINBOX) {
+            (*missing)++;
+            if (((sub >> upper) & 1) && !small[q]) {
+                *missing = OP_DEADQUADRAN;
+                return 0;
+            }
+            sub = op_shift_between(sub, q, 3, 1);
+            if (small[q]) upper++;
+            div[q] = 1;
+        }
+    }
+    op_f3 old = child->half;
+    child->half.x = child->half.x / div[0];
+    child->half.y = child->half.y / div[1];
+    child->half.z = child->half.z / div[2];
+    op_f3 mv = {old.x - child->half.x, old.y - child->half.y, old.z - child->half.z};
+    if (sub & 1) mv.x *= -1; /* flipVectorOnQuad :91-103 */
+    if (sub & 2) mv.y *= -1;
+    if (sub & 4) mv.z *= -1;
+    child->center.x += mv.x; child->center.y += mv.y; child->center.z += mv.z;
+    return sub;
+}
+unsigned op_create_child_box(const float* parent6, unsigned child, const uint8_t* small3,
+                             float* child6, int* missing_quad) {
+    op_box p, c;
+    memcpy(&p, parent6, sizeof p);
+    unsigned r = op_child_box(p, &c, 3, child, small3, missing_quad);
+    memcpy(child6, &c, sizeof c);
+    return r;
+}
+static int op_in_box(op_f3 v, op_f3 half) { /* octree_util.cu.h:153-159 */
+    float ex = fabsf(half.x), ey = fabsf(half.y), ez = fabsf(half.z);
+    return ex >= v.x && ey >= v.y && ez >= v.z && -ex < v.x && -ey < v.y && -ez < v.z;
+}
+int op_is_in_box(const float* v3, const float* box6) {
+    op_f3 v = {v3[0], v3[1], v3[2]}, h = {box6[3], box6[4], box6[5]};
+    return op_in_box(v, h);
+}
+
+typedef struct op_node {
+    op_box box;
+    int validity, leaf, raw, on_edge;
+    struct op_node* children; /* 8 when allocated */
+} op_node;
+
+static int op_null_box(op_box b) {
+    return b.center.x == 0 && b.center.y == 0 && b.center.z == 0 && b.half.x == 0 && b.half.y == 0 &&
+           b.half.z == 0;
+}
+
+/* validity_child, several_leg_octree.cu:19-151 */
+static void op_validity_pass(op_node* parent, const op_f3* foot, size_t nt, const op_leg_t* leg) {
+    int on_edge[8] = {0}, valid_leaf[8] = {0}, valid[8] = {0};
+    const int rot = parent->box.half.x < OP_ROT_BELOW;
+    const float margin = rot ? 0.f : OP_ROT_BELOW / 3;
+    const int n_angle = rot ? 27 : 1;
+    const float reach = leg->body + leg->coxa_length + leg->femur_length + leg->tibia_length;
+    const op_f3 elong = {parent->box.half.x + reach, parent->box.half.y + reach, parent->box.half.z + reach};
+    for (int c = 0; c < 8; c++) {
+        op_node* node = &parent->children[c];
+        if (node->validity) continue; /* DEADQUADRAN or already processed */
+        const op_box nb = node->box;
+        const float edge_raw = nb.half.x * nb.half.x + nb.half.y * nb.half.y + nb.half.z * nb.half.z;
+        for (size_t t = 0; t < nt; t++) {
+            op_f3 vect = {foot[t].x - nb.center.x, foot[t].y - nb.center.y, foot[t].z - nb.center.z};
+            if (!op_in_box(vect, elong)) continue;
+            for (int a = 0; a < n_angle; a++) {
+                float q4[4];
+                op_quaternion_from_angle_index((unsigned)a, q4);
+                op_f4 quat = {q4[0], q4[1], q4[2], q4[3]};
+                int reach_count = 0, cross_count = 0;
+                for (int k = 0; k < 4; k++) {
+                    op_f3 v = vect;
+                    op_leg_t l = *leg;
+                    l.body_angle = OP_PI / 4 * k; /* LegMount, settings.h:41-42 */
+                    int sub = op_distance_global(&v, &l, quat);
+                    int cross;
+                    if (edge_raw > OP_CONVEX_RADIUS * OP_CONVEX_RADIUS)
+                        cross = op_in_box(v, nb.half); /* :99-103 (the margin box is built and dropped) */
+                    else
+                        cross = (v.x * v.x + v.y * v.y + v.z * v.z) < edge_raw + margin;
+                    cross_count += cross;
+                    reach_count += sub;
+                }
+                int edge = cross_count > 0;            /* LegCount - LegNumberForStab = 0 */
+                int reachability = parent->validity || reach_count >= 4;
+                if (edge) on_edge[c] = 1;
+                if (reachability) valid[c] = 1;
+                if (reachability && !edge) valid_leaf[c] = 1;
+            }
+        }
+    }
+    for (int c = 0; c < 8; c++) { /* :134-150 */
+        op_node* node = &parent->children[c];
+        if (valid[c]) node->validity = 1;
+        if (valid_leaf[c]) node->leaf = 1;
+        if (on_edge[c] && !valid_leaf[c]) node->on_edge = 1;
+    }
+}
+
+/* branchKernel, several_leg_octree.cu:241-377 */
+static void op_branch(op_node* parent, const op_f3* foot, size_t nt, const op_leg_t* leg) {
+    if (parent->raw) {
+        parent->children = (op_node*)calloc(8, sizeof(op_node));
+        const uint8_t small[3] = {0, 0, 0};
+        for (unsigned i = 0; i < 8; i++) {
+            op_node* node = &parent->children[i];
+            op_box nb;
+            int missing;
+            op_child_box(parent->box, &nb, 3, i, small, &missing);
+            if (missing == OP_DEADQUADRAN) {
+                node->leaf = 1; node->raw = 0; node->validity = 1; node->on_edge = 1;
+                memset(&node->box, 0, sizeof node->box);
+                continue;
+            }
+            node->on_edge = 0; node->validity = 0;
+            node->box = nb;
+            if (3 - missing <= 0) { node->leaf = 1; node->raw = 0; }
+            else { node->leaf = 0; node->raw = 1; }
+        }
+        parent->raw = 0;
+        op_validity_pass(parent, foot, nt, leg);
+        return;
+    }
+    for (int i = 0; i < 8; i++) { /* go deeper :296-313 */
+        op_node* node = &parent->children[i];
+        if (!node->on_edge) node->leaf = 1;
+        if (!node->leaf) op_branch(node, foot, nt, leg);
+    }
+}
+/* fill_recus, octree_util.cu:123-147 */
+static size_t op_collect(const op_node* node, float* out, size_t n, size_t cap) {
+    for (int i = 0; i < 8; i++) {
+        const op_node* ch = &node->children[i];
+        int endpoint = !(ch->leaf || ch->raw || op_null_box(ch->box));
+        int is_valid = !op_null_box(ch->box) && (ch->leaf || ch->raw) && ch->validity;
+        if (endpoint) n = op_collect(ch, out, n, cap);
+        else if (is_valid) {
+            if (n < cap) { out[3 * n] = ch->box.center.x; out[3 * n + 1] = ch->box.center.y; out[3 * n + 2] = ch->box.center.z; }
+            n++;
+        }
+    }
+    return n;
+}
+static void op_free_tree(op_node* node) {
+    if (!node->children) return;
+    for (int i = 0; i < 8; i++) op_free_tree(&node->children[i]);
+    free(node->children);
+}
+/* apply_oct, several_leg_octree.cu:391-488, with the compile-time MAX_DEPTH as a parameter */
+size_t op_apply_oct(const float* footholds, size_t nt, const op_leg_t* leg, int max_depth,
+                    float* out_xyz, size_t cap) {
+    op_node root;
+    memset(&root, 0, sizeof root);
+    root.box.half.x = root.box.half.y = root.box.half.z = 5000.f; /* settings.h:26 */
+    root.raw = 1;
+    for (int d = 0; d < max_depth; d++) op_branch(&root, (const op_f3*)footholds, nt, leg);
+    size_t n = root.children ? op_collect(&root, out_xyz, 0, cap) : 0;
+    op_free_tree(&root);
+    return n;
 }
