@@ -117,3 +117,32 @@ inline std::tuple<Array<float3>, Array<int>> robot_full_struct(Array<float3> bod
     delete[] flags;
     return std::make_tuple(out_body, out_count);
 }
+
+// several_leg_octree.cu.h:4 — apply_oct(footholds, dim, output&): like the reference it
+// delete[]s the caller's output.elements and replaces it with a new[] array of the valid leaf
+// centres (several_leg_octree.cu:469-472), and returns the elapsed kernel milliseconds.
+// MAX_DEPTH is a compile-time constant in the reference (settings.h:15, shipped as 1).
+#ifndef LRM_COMPAT_MAX_DEPTH
+#define LRM_COMPAT_MAX_DEPTH 1
+#endif
+inline float apply_oct(Array<float3> input, LegDimensions dim, Array<float3>& output) {
+    float ms = 0.f;
+    size_t count = 0, cap = 1024;
+    float* buf = new float[3 * cap];
+    int rc = lrm_oct(&input.elements->x, input.length, &dim, LRM_COMPAT_MAX_DEPTH, buf, cap, &count, 0,
+                     nullptr, &ms);
+    if (rc == LRM_OK && count > cap) {
+        delete[] buf;
+        cap = count;
+        buf = new float[3 * cap];
+        rc = lrm_oct(&input.elements->x, input.length, &dim, LRM_COMPAT_MAX_DEPTH, buf, cap, &count, 0,
+                     nullptr, &ms);
+    }
+    if (rc != LRM_OK) lrm_compat::die("apply_oct", rc);
+    delete[] output.elements;
+    output.length = count;
+    output.elements = new float3[count ? count : 1];
+    for (size_t i = 0; i < count; i++) output.elements[i] = {buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]};
+    delete[] buf;
+    return ms;
+}
