@@ -136,6 +136,15 @@ LRM_API int lrm_positionability(const float* bodies, size_t nb, const float* map
                         const lrm_posit_opts_t* opts, uint8_t* standable, int on_device,
                         void* stream, float* kernel_ms);
 
+/* Replaces apply_recurs<float3,LegDimensions,float3> (cross_compiled.cuh:9-10, cross_compiled.cu:82-139;
+ * recursive_kernel one_leg_global.cu:168-251, fillOutKernel octree_util.cu:9-26): adaptive octree of
+ * the single-leg distance field (root box +-5000 mm, MINBOXSIZE 100 mm), refined to `max_depth`
+ * (the reference's compile-time MAX_DEPTH), painted on the query points: out_xyz[i] =
+ * (depth of the leaf box containing p_i, 0, 0).  Points outside the root box are left untouched
+ * (the reference leaves uninitialised device memory there). */
+LRM_API int lrm_recurs(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, int max_depth,
+               float* out_xyz, int on_device, void* stream, float* kernel_ms);
+
 /* ---- body-space octree ------------------------------------------------------------------- */
 /* Replaces apply_oct (several_leg_octree.cu.h:4, several_leg_octree.cu:391-488): adaptive octree
  * over BODY positions (root box +-5000 mm, settings.h:26; axes stop splitting below 100 mm,

@@ -146,3 +146,13 @@ inline float apply_oct(Array<float3> input, LegDimensions dim, Array<float3>& ou
     delete[] buf;
     return ms;
 }
+
+// cross_compiled.cuh:9-10 — apply_recurs<float3, LegDimensions, float3>(input, dim, output)
+template <typename T_in = float3, typename param = LegDimensions, typename T_out = float3>
+inline float apply_recurs(const Array<float3> input, const LegDimensions dim, Array<float3> const output) {
+    float ms = 0.f;
+    int rc = lrm_recurs(&input.elements->x, input.length, &dim, nullptr, LRM_COMPAT_MAX_DEPTH,
+                        &output.elements->x, 0, nullptr, &ms);
+    if (rc != LRM_OK) lrm_compat::die("apply_recurs", rc);
+    return ms;
+}

@@ -78,6 +78,7 @@ def lib():
         L.lrm_full_struct_orientations.argtypes = [vp, ci]
         L.lrm_positionability.argtypes = [vp, sz, vp, sz, legp, ci, vp, ci,
                                           ctypes.POINTER(PositOpts), vp, ci, vp, fp]
+        L.lrm_recurs.argtypes = [vp, sz, legp, vp, ci, vp, ci, vp, fp]
         L.lrm_oct.argtypes = [vp, sz, legp, ci, vp, sz, ctypes.POINTER(ctypes.c_size_t), ci, vp, fp]
         _lib = L
     return _lib
@@ -302,6 +303,24 @@ def positionability(bodies, map_points, legs, quats=None, pre_cull=False, stream
         _check(lib().lrm_positionability(pb, nb, pm, nt, leg_arr, len(legs), quats.ctypes.data,
                                          quats.shape[0], ctypes.byref(opts), out.ctypes.data, 0, None, msp))
     return (out, ms.value) if timing else out
+
+
+def apply_recurs(points, leg, max_depth=1, quat=None, fill=-1.0, stream=None):
+    """Octree of the single-leg distance field painted on the query points (apply_recurs,
+    cross_compiled.cu:82-139): (leaf depth, 0, 0) per point, (fill, 0, 0) outside the root box."""
+    dev, ptr, n, keep = _prep_points(points)
+    q, qp = _quat_ptr(quat)
+    if dev:
+        import torch
+        out = torch.zeros((n, 3), dtype=torch.float32, device=points.device)
+        out[:, 0] = fill
+        st = _stream_ptr(stream) or _torch_stream()
+        _check(lib().lrm_recurs(ptr, n, ctypes.byref(leg), qp, int(max_depth), out.data_ptr(), 1, st, None))
+    else:
+        out = np.zeros((n, 3), dtype=np.float32)
+        out[:, 0] = fill
+        _check(lib().lrm_recurs(ptr, n, ctypes.byref(leg), qp, int(max_depth), out.ctypes.data, 0, None, None))
+    return out
 
 
 def apply_oct(footholds, leg, max_depth=1, cap=1 << 16, stream=None, timing=False):

@@ -21,6 +21,10 @@ cudaError_t launch_one_leg_aos(int mode, const LegPlan& plan, const float* xyz, 
 cudaError_t launch_one_leg_soa(const LegPlan& plan, const float* x, const float* y, const float* z,
                                float* dx, float* dy, float* dz, uint8_t* flag, size_t n,
                                cudaStream_t stream);
+// apply_recurs: (octree leaf depth, 0, 0) per point; points outside the +-5000 mm root box are
+// not written.
+cudaError_t launch_recurs(const LegPlan& plan, const float* xyz, float* out, size_t n, int max_depth,
+                          cudaStream_t stream);
 cudaError_t launch_forward_kine(const float* angles, const lrm_leg_t& leg, float* out, size_t n,
                                 cudaStream_t stream);
 cudaError_t launch_lattice(float* out, const float lo[3], const float step[3],

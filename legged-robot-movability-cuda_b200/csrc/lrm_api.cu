@@ -340,6 +340,45 @@ int lrm_forward_kine(const float* angles, size_t n, const lrm_leg_t* leg, float*
     return LRM_OK;
 }
 
+int lrm_recurs(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, int max_depth,
+               float* out_xyz, int on_device, void* stream_v, float* kernel_ms) {
+    if (!leg) return fail(LRM_ERR_INVALID, "leg is NULL");
+    if (n && (!xyz || !out_xyz)) return fail(LRM_ERR_INVALID, "NULL buffer");
+    if (max_depth < 0 || max_depth > 32) return fail(LRM_ERR_INVALID, "max_depth must be 0..32");
+    if (kernel_ms) *kernel_ms = 0.f;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    lrm::LegPlan plan;
+    lrm::build_leg_plan(*leg, quat, &plan);
+    DeviceScratch scratch;
+    const float* d_in = xyz;
+    float* d_out = out_xyz;
+    if (!on_device) {
+        int count = 0;
+        cudaError_t ce = cudaGetDeviceCount(&count);
+        if (ce != cudaSuccess || count == 0)
+            return cuda_fail(ce != cudaSuccess ? ce : cudaErrorNoDevice,
+                             "no CUDA device (this library has no CPU path)");
+        float* tmp = nullptr;
+        LRM_CUDA(scratch.alloc((void**)&tmp, n * 12), "cudaMalloc points");
+        LRM_CUDA(scratch.alloc((void**)&d_out, n * 12), "cudaMalloc output");
+        LRM_CUDA(cudaMemcpyAsync(tmp, xyz, n * 12, cudaMemcpyHostToDevice, stream), "H2D points");
+        // untouched entries keep the caller's values
+        LRM_CUDA(cudaMemcpyAsync(d_out, out_xyz, n * 12, cudaMemcpyHostToDevice, stream), "H2D output");
+        d_in = tmp;
+    }
+    {
+        EventPair ev;
+        LRM_CUDA(ev.start(stream, kernel_ms != nullptr), "cudaEventRecord");
+        LRM_CUDA(lrm::launch_recurs(plan, d_in, d_out, n, max_depth, stream), "recurs kernel launch");
+        LRM_CUDA(ev.stop(stream, kernel_ms), "recurs kernel");
+    }
+    if (!on_device) {
+        LRM_CUDA(cudaMemcpyAsync(out_xyz, d_out, n * 12, cudaMemcpyDeviceToHost, stream), "D2H output");
+        LRM_CUDA(cudaStreamSynchronize(stream), "stream synchronize");
+    }
+    return LRM_OK;
+}
+
 int lrm_make_lattice(float* out_xyz, const float lo[3], const float step[3], const uint32_t dims[3],
                      size_t first, size_t count, void* stream) {
     if (!lo || !step || !dims) return fail(LRM_ERR_INVALID, "NULL lattice description");

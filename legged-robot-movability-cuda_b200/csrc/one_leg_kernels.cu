@@ -238,6 +238,50 @@ __global__ void forward_kine_kernel_b200(const float* __restrict__ angles, lrm_l
     }
 }
 
+// apply_recurs / recursive_kernel / fillOutKernel (cross_compiled.cu:82-139,
+// one_leg_global.cu:168-251, octree_util.cu:9-26): an adaptive octree of the single-leg distance
+// field (root +-5000 mm, axes stop splitting below 100 mm) whose leaves paint (depth, 0, 0) on the
+// query points they contain.  The reference materialises the tree with dynamic parallelism and
+// runs one full pass over ALL query points per leaf.  The boxes tile space ((-h, h] per axis), so
+// here every point walks down its own branch without any tree: pick the child holding the point,
+// evaluate the distance field at its centre, stop when the reachability edge cannot cross the
+// child (|d| >= |half extents|), nothing was split, or the depth limit is hit.
+template <bool GENERIC>
+__global__ void __launch_bounds__(kThreads)
+    recurs_kernel(const __grid_constant__ LegPlan L, const float* __restrict__ xyz,
+                  float* __restrict__ out, size_t n, int max_depth) {
+    __shared__ SectorTable table;
+    fill_sector_table(L, &table, threadIdx.x, kThreads);
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        const float p[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
+        float c[3] = {0.f, 0.f, 0.f}, h[3] = {5000.f, 5000.f, 5000.f};  // BoxCenter / BoxSize, settings.h:25-26
+        bool inside = true;
+        for (int q = 0; q < 3; q++) inside = inside && (h[q] >= p[q] - c[q]) && (-h[q] < p[q] - c[q]);
+        if (!inside) continue;  // the reference paints nothing there either
+        int depth = 0;
+        while (true) {
+            int nsplit = 0;
+            for (int q = 0; q < 3; q++) {
+                if (fabsf(h[q]) < 100.f) continue;  // MIN_BOX: this axis is not split any more
+                const float nh = h[q] / 2.f, mv = h[q] - nh;
+                c[q] += (p[q] - c[q] > 0.f) ? mv : -mv;
+                h[q] = nh;
+                nsplit++;
+            }
+            const DistResult d = dist_coxa_frame<GENERIC>(L, table, to_coxa_frame(L, c[0], c[1], c[2]));
+            const bool edge_in_box = norm3df(d.dx, d.dy, d.dz) < norm3df(h[0], h[1], h[2]);
+            if (edge_in_box && nsplit > 0 && depth < max_depth) {
+                depth++;
+            } else {
+                break;
+            }
+        }
+        out[3 * i] = (float)depth, out[3 * i + 1] = 0.f, out[3 * i + 2] = 0.f;
+    }
+}
+
 // generate3DGrid (bench.cpp:30-50) on the device: x-major, z fastest
 __global__ void lattice_kernel(float* __restrict__ out, float3 lo, float3 step, uint32_t ny,
                                uint32_t nz, size_t first, size_t count) {
@@ -371,6 +415,18 @@ cudaError_t launch_one_leg_soa(const LegPlan& plan, const float* x, const float*
         return launch_stream<kModeReach, true>(plan, x, y, z, nullptr, nullptr, nullptr, flag, n,
                                                stream);
     return launch_stream<kModeBoth, true>(plan, x, y, z, dx, dy, dz, flag, n, stream);
+}
+
+cudaError_t launch_recurs(const LegPlan& plan, const float* xyz, float* out, size_t n, int max_depth,
+                          cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    size_t grid = (n + kThreads - 1) / kThreads;
+    if (grid > (size_t)sm_count() * 8) grid = (size_t)sm_count() * 8;
+    if (plan.generic)
+        recurs_kernel<true><<<(unsigned)grid, kThreads, 0, stream>>>(plan, xyz, out, n, max_depth);
+    else
+        recurs_kernel<false><<<(unsigned)grid, kThreads, 0, stream>>>(plan, xyz, out, n, max_depth);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_forward_kine(const float* angles, const lrm_leg_t& leg, float* out, size_t n,

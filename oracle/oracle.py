@@ -84,6 +84,7 @@ class PortOracle(_Oracle):
         L.op_full_struct_orientations.argtypes = [_vp]
         L.op_quaternion_from_angle_index.argtypes = [ctypes.c_uint, _vp]
         L.op_standability.argtypes = [_vp, _sz, _vp, _sz, _vp, _ci, _vp, _ci, _ci, _vp, _ci]
+        L.op_apply_recurs.argtypes = [_vp, _sz, _vp, _vp, _ci, _vp]
         L.op_apply_oct.argtypes = [_vp, _sz, _vp, _ci, _vp, _sz]
         L.op_apply_oct.restype = _sz
         L.op_create_child_box.argtypes = [_vp, ctypes.c_uint, _vp, _vp, _vp]
@@ -177,6 +178,18 @@ class PortOracle(_Oracle):
         n = self.L.op_apply_oct(f.ctypes.data, len(f), leg.ctypes.data, max_depth, out.ctypes.data, cap)
         assert n <= cap
         return out[:n].copy()
+
+    def apply_recurs(self, pts, leg, max_depth=1, quat=(1, 0, 0, 0), fill=-1.0):
+        """Sequential restatement of apply_recurs: (leaf depth, 0, 0) per point; points outside the
+        root box keep (fill, 0, 0)."""
+        pts = _as_f32(pts, 3)
+        leg = leg_array(leg)
+        q = _as_f32(quat)
+        out = np.zeros_like(pts)
+        out[:, 0] = fill
+        self.L.op_apply_recurs(pts.ctypes.data, len(pts), leg.ctypes.data, q.ctypes.data, max_depth,
+                               out.ctypes.data)
+        return out
 
     def create_child_box(self, parent6, child, small3=(0, 0, 0)):
         p = _as_f32(parent6)

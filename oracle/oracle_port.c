@@ -964,3 +964,43 @@ size_t op_apply_oct(const float* footholds, size_t nt, const op_leg_t* leg, int 
     op_free_tree(&root);
     return n;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Single-leg distance-field octree painted on the query array: recursive_kernel + fillOutKernel */
+/* (one_leg_global.cu:168-251, octree_util.cu:9-26) driven like apply_recurs                     */
+/* (cross_compiled.cu:82-139), sequentially.  Output: (depth of the leaf box holding the point,  */
+/* 0, 0); points outside the root box keep what the caller put in `out` (the reference leaves    */
+/* uninitialised device memory there).                                                           */
+static void op_recurs_node(op_box box, const op_f3* in, size_t n, const op_leg_t* leg, op_f4 quat,
+                           op_f3* out, int depth, int max_depth) {
+    uint8_t small[3] = {fabsf(box.half.x) < OP_MINBOX, fabsf(box.half.y) < OP_MINBOX,
+                        fabsf(box.half.z) < OP_MINBOX};
+    unsigned quad_count = 3 - small[0] - small[1] - small[2];
+    unsigned n_child = 1u << quad_count;
+    for (unsigned ci = 0; ci < n_child; ci++) {
+        op_box nb;
+        int missing;
+        op_child_box(box, &nb, quad_count, ci, small, &missing);
+        if (missing == OP_DEADQUADRAN) continue;
+        int too_small = (3 - missing) <= 0;
+        op_f3 d = nb.center;
+        op_distance_global(&d, leg, quat);
+        int edge_in_box = op_norm3(d) < op_norm3(nb.half);
+        if (edge_in_box && !too_small && depth < max_depth) {
+            op_recurs_node(nb, in, n, leg, quat, out, depth + 1, max_depth);
+        } else {
+            for (size_t i = 0; i < n; i++) { /* fillOutKernel */
+                op_f3 delta = {in[i].x - nb.center.x, in[i].y - nb.center.y, in[i].z - nb.center.z};
+                if (op_in_box(delta, nb.half)) { out[i].x = (float)depth; out[i].y = 0; out[i].z = 0; }
+            }
+        }
+    }
+}
+void op_apply_recurs(const float* xyz, size_t n, const op_leg_t* leg, const float* quat4, int max_depth,
+                     float* out_xyz) {
+    op_box root;
+    memset(&root, 0, sizeof root);
+    root.half.x = root.half.y = root.half.z = 5000.f;
+    op_f4 q = {quat4[0], quat4[1], quat4[2], quat4[3]};
+    op_recurs_node(root, (const op_f3*)xyz, n, leg, q, (op_f3*)out_xyz, 0, max_depth);
+}

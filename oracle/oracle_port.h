@@ -83,6 +83,11 @@ int op_is_in_box(const float* v3, const float* box6);
 size_t op_apply_oct(const float* footholds, size_t nt, const op_leg_t* leg, int max_depth,
                     float* out_xyz, size_t cap);
 
+/* apply_recurs (cross_compiled.cu:82-139): octree of the single-leg distance field painted on the
+ * query points, out = (leaf depth, 0, 0); points outside the +-5000 mm root box are left untouched. */
+void op_apply_recurs(const float* xyz, size_t n, const op_leg_t* leg, const float* quat4, int max_depth,
+                     float* out_xyz);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,3 +78,39 @@ def test_gpu_octree_matches_oracle(lrm, port):
     assert len(got_h) == len(lrm.apply_oct(torch.from_numpy(terr).cuda(), leg, 5))
     assert len(lrm.apply_oct(terr, lrm.get_M2_leg(0.0), 4)) == 0
     assert len(lrm.apply_oct(np.zeros((0, 3), np.float32), leg, 2)) == 0
+
+
+def test_oracle_recurs_depth_map(port):
+    """apply_recurs paints the octree depth of the single-leg distance field: deep boxes hug the
+    reachability edge, shallow ones are far from it."""
+    rng = np.random.default_rng(2)
+    pts = rng.uniform(-900, 900, (4000, 3)).astype(np.float32)
+    leg = port.get_leg(1, 0.0)
+    out = port.apply_recurs(pts, leg, 6)
+    assert set(np.unique(out[:, 1:]).tolist()) == {0.0}
+    d, _ = port.dist(pts, leg)
+    dist = np.linalg.norm(d, axis=1)
+    deep, shallow = out[:, 0] >= 6, out[:, 0] <= 3
+    assert deep.any() and shallow.any()
+    assert np.median(dist[deep]) < np.median(dist[shallow])
+    outside = port.apply_recurs(np.array([[6000, 0, 0], [0, -5000.0, 0]], np.float32), leg, 3)
+    assert outside[0, 0] == -1.0 and outside[1, 0] == -1.0   # (-h, h]: -5000 is outside
+
+
+@pytest.mark.gpu
+def test_gpu_recurs_matches_oracle(lrm, port):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(4)
+    pts = np.concatenate([rng.uniform(-900, 900, (20000, 3)), rng.uniform(-5200, 5200, (4000, 3))]).astype(np.float32)
+    for robot, az, q in ((1, 0.0, None), (0, 2.0, port.quaternion_from_angle_index(0))):
+        leg_o = port.get_leg(robot, az)
+        leg = lrm.LegDimensions.from_array(leg_o)
+        for depth in (1, 4, 7):
+            want = port.apply_recurs(pts, leg_o, depth, quat=[1, 0, 0, 0] if q is None else q)
+            got = lrm.apply_recurs(torch.from_numpy(pts).cuda(), leg, depth, quat=q).cpu().numpy()
+            # a box centre whose |d| ties with the box diagonal may flip one subtree
+            assert (got[:, 0] != want[:, 0]).sum() <= len(pts) // 500, (robot, depth)
+            assert np.array_equal(got[:, 1:], want[:, 1:])
+    got_h = lrm.apply_recurs(pts[:5000], lrm.get_M2_leg(0.0), 5)
+    want_h = port.apply_recurs(pts[:5000], port.get_leg(1, 0.0), 5)
+    assert (got_h[:, 0] != want_h[:, 0]).sum() <= 10
