@@ -95,7 +95,8 @@ LRM_API int lrm_reach_dist(const float* xyz, size_t n, const lrm_leg_t* leg, con
 
 /* SoA twins: x, y, z planes in / dx, dy, dz planes out (the layout of the reference's on-disk
  * protocol dist_input_t{x,y,z}.bin -> out_dist_x{x,y,z}.bin, several_leg.cpp:126-221).
- * Any output pointer may be NULL to skip that result.  Device pointers only. */
+ * dx/dy/dz may all be NULL to skip the vectors.  Device pointers only, every plane 16-byte aligned
+ * (the bulk-copy engine's requirement; misaligned planes are refused with LRM_ERR_CUDA). */
 LRM_API int lrm_reach_dist_soa(const float* x, const float* y, const float* z, size_t n,
                        const lrm_leg_t* leg, const float* quat, uint8_t* reach_flags, float* dx,
                        float* dy, float* dz, void* stream, float* kernel_ms);
