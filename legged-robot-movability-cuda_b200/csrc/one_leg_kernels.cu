@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kThreads)
         uint8_t* flag = S.flag[ob];
         if (ATLAS) {
             // pass 1: every point through the atlas; the few it cannot certify are queued ...
-#pragma unroll 1
+#pragma unroll 2
             for (int i = tid; i < (int)cnt; i += kThreads)
                 if (!compute_point<MODE, SOA, false, true>(L, S.table, in, vec, flag, i, kTile, &atlas,
                                                            &S.winners))
