@@ -196,6 +196,13 @@ def run_b200(args):
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with ClockSampler(local) as clocks:
+        # nvidia-smi needs a few hundred ms per sample: keep the GPU under the same load a little
+        # longer than the timed steps so that the clock record has several samples under load
+        t_load = time.perf_counter()
+        while time.perf_counter() - t_load < 0.6:
+            step_fn()
+            torch.cuda.synchronize()
+        barrier()
         ev[0].record(stream)
         for k in range(args.steps):
             step_fn()
