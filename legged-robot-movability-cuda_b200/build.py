@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblrm_b200.so")
-SOURCES = ["leg_plan.cpp", "one_leg_kernels.cu", "plane_atlas.cu", "positionability.cu", "octree.cu", "lrm_api.cu"]
+SOURCES = ["leg_plan.cpp", "fast_tables.cpp", "one_leg_kernels.cu", "plane_atlas.cu", "positionability.cu", "octree.cu", "lrm_api.cu"]
 HEADERS = ["leg_plan.h", "leg_math.cuh", "bulk_copy.cuh", "kernels.h", "cell_grid.cuh"]
 
 NVCC_FLAGS = [

@@ -46,6 +46,17 @@ LRM_HD float fast_rsqrt(float x) {
 #endif
 }
 
+// 1/x, ~1 ulp, one MUFU.RCP
+LRM_HD float fast_rcp(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
 constexpr float kMarginF = 0.001f;  // CIRCLE_MARGIN, settings.h:9
 
 // Sector table staged in shared memory by every CTA: a copy of LegPlan::sector.
@@ -289,14 +300,22 @@ LRM_HD bool reach_ball_possible(const ReachPlan& L, float vx, float vy, float vz
 // result for any point in it is a handful of FMAs.  Points in impure cells (or off the atlas) take
 // the full evaluation, so the atlas never changes a result, it only skips work.
 //
-// cell byte: bit 7 set = impure; else bit 6 = P valid, bits 4-5 = sector, bits 0-3 = winner
-// (0-3 circle slot, 4-13 corner index + 4, 15 = no candidate at all).
+// cell byte: 0 = impure (also what a texture fetch outside the atlas returns); otherwise bit 7 is
+// set and bit 6 = P valid, bits 4-5 = sector, bits 0-3 = winner (0-3 circle slot, 4-13 corner
+// index + 4; "no candidate at all" is never certified).
 struct AtlasView {
-    const signed char* cells;
-    float x0, y0, inv_cell;
+    const unsigned char* cells;  // 8 x 4 blocked copy (plain loads)
+    cudaTextureObject_t tex;     // the same cells as a 2-D texture (point sampling, border = 0)
+    float inv_cell, ox, oy;      // cell coordinates = P * inv_cell + (ox, oy)
     int w, h;
 };
 constexpr int kAtlasNone = 15;
+constexpr unsigned kAtlasPure = 0x80u;
+// a cell is certified when every decision margin at its centre exceeds
+// kAtlasNeedFactor * cell + kAtlasNeedSlack: the half diagonal (0.7071) widened by 1/128 of a
+// cell for the texture unit's fixed-point cell coordinates, plus float rounding of the margins
+constexpr float kAtlasNeedFactor = 0.70711f * 1.02f + 0.012f;
+constexpr float kAtlasNeedSlack = 2.0e-3f;
 
 struct PlaneProbe {
     int label;     // bits 0-6 as above (never has bit 7)
@@ -397,10 +416,16 @@ LRM_HD void fill_winner_table(const LegPlan& L, WinnerTable* w, int tid, int nth
 LRM_HD size_t atlas_index(int w, int ix, int iy) {
     return ((size_t)((iy >> 2) * (w >> 3) + (ix >> 3)) << 5) | (size_t)(((iy & 3) << 3) | (ix & 7));
 }
-// Label of the cell holding (X, Y): >= 0 certified, < 0 impure or off the atlas.
-LRM_HD int atlas_label(const AtlasView& A, float X, float Y) {
-    const int ix = (int)floorf((X - A.x0) * A.inv_cell), iy = (int)floorf((Y - A.y0) * A.inv_cell);
-    if ((unsigned)ix >= (unsigned)A.w || (unsigned)iy >= (unsigned)A.h) return -1;
+// Cell byte of the cell holding the point with cell coordinates (fx, fy); 0 when it is impure or
+// off the atlas.  TEX: one texture instruction does the floor, the bounds check and the blocked
+// addressing (unnormalised coordinates, point sampling, border colour 0).
+template <bool TEX>
+LRM_HD unsigned atlas_fetch(const AtlasView& A, float fx, float fy) {
+#ifdef __CUDA_ARCH__
+    if (TEX) return tex2D<unsigned char>(A.tex, fx, fy);
+#endif
+    const int ix = (int)floorf(fx), iy = (int)floorf(fy);
+    if ((unsigned)ix >= (unsigned)A.w || (unsigned)iy >= (unsigned)A.h) return 0u;
 #ifdef __CUDA_ARCH__
     return __ldg(A.cells + atlas_index(A.w, ix, iy));
 #else
@@ -409,12 +434,12 @@ LRM_HD int atlas_label(const AtlasView& A, float X, float Y) {
 }
 // Plane evaluation of a certified cell: P - (c + r v/|v|) = v (1 - r/|v|); a corner is a circle
 // of radius 0.
-LRM_HD PlaneResult plane_from_label(const WinnerTable& W, int label, float X, float Y) {
+LRM_HD PlaneResult plane_from_label(const WinnerTable& W, unsigned label, float X, float Y) {
     const float4 e = W.e[label & 63];
     const float vx = X - e.x, vy = Y - e.y;
     const float k = 1.f - e.z * fast_rsqrt(fmaf(vx, vx, vy * vy));
     PlaneResult out;
-    out.valid = (label & 0x40) != 0;
+    out.valid = (label & 0x40u) != 0;
     out.dx = vx * k;
     out.dy = vy * k;
     return out;
@@ -528,13 +553,9 @@ struct DistResult {
     float dx, dy, dz; // world-frame vector
 };
 
-// distance_circles (one_leg.cu:321-341) + the way back to the world frame.
-// ATLAS: plane evaluations come from the atlas; *ok_out is cleared (and the result is garbage)
-// when a needed cell is not certified — the caller then redoes the point with ATLAS = false.
-template <bool GENERIC, bool ATLAS = false>
-LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, const CoxaPoint p,
-                                  const AtlasView* A = nullptr, const WinnerTable* W = nullptr,
-                                  bool* ok_out = nullptr) {
+// distance_circles (one_leg.cu:321-341) + the way back to the world frame: the full evaluation.
+template <bool GENERIC>
+LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, const CoxaPoint p) {
     const float rho2 = fmaf(p.x, p.x, p.y * p.y);
     const float inv_rho = rho2 > 0.f ? fast_rsqrt(rho2) : 0.f;
     // unit vector of the direct yaw; a point on the coxa axis has yaw 0 (atan2f(0, 0))
@@ -551,21 +572,9 @@ LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, cons
     const BranchPrep pa = branch_prep(L, p, fa, ux, uy);
     const BranchPrep pb = branch_prep(L, p, fb, -ux, -uy);
     BranchResult a, b;
-    if (ATLAS) {
-        // both labels are requested before either is consumed (two L2/L1 loads in flight)
-        const int la = skip_a ? 0 : atlas_label(*A, pa.X, p.z);
-        const int lb = skip_b ? 0 : atlas_label(*A, pb.X, p.z);
-        if ((la | lb) < 0) {
-            *ok_out = false;
-            return DistResult{};
-        }
-        a = branch_finish(L, p, fa, pa, plane_from_label(*W, la, pa.X, p.z));
-        b = branch_finish(L, p, fb, pb, plane_from_label(*W, lb, pb.X, p.z));
-    } else {
-        a.res = b.res = false, a.vx = a.vy = a.vz = b.vx = b.vy = b.vz = 0.f, a.n2 = b.n2 = 0.f;
-        if (!skip_a) a = branch_finish(L, p, fa, pa, plane_clamp<GENERIC>(L, tab, pa.X, p.z));
-        if (!skip_b) b = branch_finish(L, p, fb, pb, plane_clamp<GENERIC>(L, tab, pb.X, p.z));
-    }
+    a.res = b.res = false, a.vx = a.vy = a.vz = b.vx = b.vy = b.vz = 0.f, a.n2 = b.n2 = 0.f;
+    if (!skip_a) a = branch_finish(L, p, fa, pa, plane_clamp<GENERIC>(L, tab, pa.X, p.z));
+    if (!skip_b) b = branch_finish(L, p, fb, pb, plane_clamp<GENERIC>(L, tab, pb.X, p.z));
     if (skip_a) a = b, a.res = false;
     if (skip_b) b = a, b.res = false;
     const bool direct = (a.res == b.res) ? (a.n2 < b.n2) : a.res;
@@ -577,6 +586,83 @@ LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, cons
     out.dy = fmaf(L.Mo[3], vx, fmaf(L.Mo[4], vy, L.Mo[5] * vz));
     out.dz = fmaf(L.Mo[6], vx, fmaf(L.Mo[7], vy, L.Mo[8] * vz));
     return out;
+}
+
+// ---- fast path: yaw-sector table + plane atlas --------------------------------------------------
+// Same arithmetic as dist_coxa_frame for everything that produces a number (plane direction,
+// plane abscissa, projection on the winner, limit-plane rule, final choice); the DECISIONS come
+// from two certified tables: the yaw-sector code of the point's direction (FastTables) and the
+// plane-atlas cell of each solution's plane point.  Returns false — nothing is written — when
+// either table cannot certify the point; the caller then runs dist_coxa_frame.
+struct FastView {
+    const YawSol* sol;          // [16]
+    const unsigned char* code;  // [kYawBins + 1]
+};
+
+// Diamond angle bin of a unit direction: d = uy / (|ux| + |uy|) in the right half plane, mirrored
+// to +-(2 - |d|) in the left one: monotone in atan2(uy, ux), -2 at -pi, +2 at +pi.
+LRM_HD int yaw_bin(float ux, float uy) {
+    const float d0 = uy * fast_rcp(fabsf(ux) + fabsf(uy));
+    const float d = f2i(ux) < 0 ? copysignf(2.f, uy) - d0 : d0;
+    return (int)fmaf(d, 0.25f * kYawBins, 0.5f * kYawBins);
+}
+
+LRM_HD BranchResult fast_branch(const CoxaPoint p, const YawSol& s, float cs, float ss,
+                                const PlaneResult pl) {
+    const float qx = pl.dx, qy = fmaf(p.y, cs, -p.x * ss), qz = pl.dy;  // in the plane's frame
+    const float n2 = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
+    // in-plane region reached but the coxa-limit half-plane is nearer (one_leg.cu:258-274);
+    // s.big = +inf switches the rule off for a mega-saturated yaw
+    const float yl = fmaf(p.y, s.cl, -p.x * s.sl);
+    const float yl2 = fmaf(yl, yl, s.big);
+    const bool to_plane = pl.valid & (n2 > yl2);
+    BranchResult out;
+    out.res = pl.valid & (s.nsat != 0.f);
+    out.vx = to_plane ? -yl * s.sl : fmaf(qx, cs, -qy * ss);
+    out.vy = to_plane ? yl * s.cl : fmaf(qx, ss, qy * cs);
+    out.vz = to_plane ? 0.f : qz;
+    out.n2 = to_plane ? yl2 : n2;
+    return out;
+}
+
+template <bool TEX>
+LRM_HD bool dist_fast(const LegPlan& L, const FastView& F, const AtlasView& A, const WinnerTable& W,
+                      const CoxaPoint p, DistResult* out) {
+    const float rho2 = fmaf(p.x, p.x, p.y * p.y);
+    if (!(rho2 > 1.0e-12f)) return false;  // on the coxa axis (or NaN): full evaluation
+    const float inv_rho = fast_rsqrt(rho2);
+    const float ux = p.x * inv_rho, uy = p.y * inv_rho;
+    const int bin = yaw_bin(ux, uy);
+    if ((unsigned)bin > (unsigned)kYawBins) return false;
+    const unsigned code = F.code[bin];
+    if (code == kYawImpure) return false;
+    const unsigned ia = code & 15u, ib = code >> 4;
+    const bool has_a = ia != (unsigned)kYawSkip, has_b = ib != (unsigned)kYawSkip;
+    const YawSol& sa = F.sol[has_a ? ia : 0u];
+    const YawSol& sb = F.sol[has_b ? ib : 0u];
+    const float csa = fmaf(sa.k, ux, sa.c_cs), ssa = fmaf(sa.k, uy, sa.c_ss);
+    const float csb = fmaf(sb.k, ux, sb.c_cs), ssb = fmaf(sb.k, uy, sb.c_ss);
+    const float Xa = fmaf(p.x, csa, p.y * ssa) - L.coxa_length;
+    const float Xb = fmaf(p.x, csb, p.y * ssb) - L.coxa_length;
+    // both cells are requested before either is consumed
+    const float fy = fmaf(p.z, A.inv_cell, A.oy);
+    const unsigned la = has_a ? atlas_fetch<TEX>(A, fmaf(Xa, A.inv_cell, A.ox), fy) : kAtlasPure;
+    const unsigned lb = has_b ? atlas_fetch<TEX>(A, fmaf(Xb, A.inv_cell, A.ox), fy) : kAtlasPure;
+    if (((la & lb) & kAtlasPure) == 0u) return false;
+    BranchResult a, b;
+    a.res = b.res = false, a.vx = a.vy = a.vz = b.vx = b.vy = b.vz = 0.f, a.n2 = b.n2 = 0.f;
+    if (has_a) a = fast_branch(p, sa, csa, ssa, plane_from_label(W, la, Xa, p.z));
+    if (has_b) b = fast_branch(p, sb, csb, ssb, plane_from_label(W, lb, Xb, p.z));
+    if (!has_a) a = b, a.res = false;
+    if (!has_b) b = a, b.res = false;
+    const bool direct = (a.res == b.res) ? (a.n2 < b.n2) : a.res;
+    const float vx = direct ? a.vx : b.vx, vy = direct ? a.vy : b.vy, vz = direct ? a.vz : b.vz;
+    out->flag = a.res | b.res;
+    out->reach = (f2i(p.x) < 0) ? b.res : a.res;
+    out->dx = fmaf(L.Mo[0], vx, fmaf(L.Mo[1], vy, L.Mo[2] * vz));
+    out->dy = fmaf(L.Mo[3], vx, fmaf(L.Mo[4], vy, L.Mo[5] * vz));
+    out->dz = fmaf(L.Mo[6], vx, fmaf(L.Mo[7], vy, L.Mo[8] * vz));
+    return true;
 }
 
 }  // namespace lrm

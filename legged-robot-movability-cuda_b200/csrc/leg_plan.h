@@ -98,6 +98,35 @@ struct LegPlan {
     float corner_y[kMaxCorners];
 };
 
+// ---- yaw sectors (fast path of the distance sweep) -------------------------------------------
+// Every yaw decision of finish_finding_closest (one_leg.cu:222-234: beyond limit +- pi/2, over /
+// under the limits, which limit plane the "coxa-limit plane is nearer" rule uses) depends on the
+// direction of the point around the coxa axis only.  The circle of directions is cut into
+// kYawBins bins of equal "diamond angle" (uy / (|ux| + |uy|), monotone in atan2); a bin whose five
+// yaw tests are constant for the direct AND the pi-flipped solution over the whole (padded) bin
+// carries a code = (flipped solution index << 4) | direct solution index into `sol`, or
+// kYawSkip for a solution that duplicates the other one (one_leg.cu:225-226); bins that contain a
+// decision boundary, the +-pi seam or the x axis (signed-zero rules) are kYawImpure and the point
+// takes the full evaluation.  The table never changes a result, it only replaces ~100
+// instructions of tests and selects by one shared-memory load.
+constexpr int kYawBins = 1024;
+constexpr int kYawSolutions = 14;
+constexpr int kYawSkip = 15;
+constexpr uint8_t kYawImpure = 0xFF;
+struct alignas(16) YawSol {
+    float k;           // plane direction (cs, ss) = k * (ux, uy) + (c_cs, c_ss):
+    float c_cs, c_ss;  //   k = +-1 for an unsaturated / mega-saturated yaw, 0 at a coxa limit
+    float nsat;        // 1 if the yaw is unsaturated (res = valid), else 0
+    float cl, sl;      // direction of the coxa limit used by one_leg.cu:258-274
+    float big;         // 0, or +inf when that rule is off (mega-saturated)
+    float pad;
+};
+struct FastTables {
+    YawSol sol[16];
+    uint8_t code[kYawBins + 16];  // bins 0 .. kYawBins used
+};
+void build_fast_tables(const LegPlan& plan, FastTables* out);
+
 // Host-side construction.  quat may be nullptr (identity).  Pure FP arithmetic, no CUDA.
 void build_leg_plan(const lrm_leg_t& leg, const float* quat, LegPlan* out);
 // Variant used by the positionability path (several_leg.cu:48-67,743-760): the tibia limits are

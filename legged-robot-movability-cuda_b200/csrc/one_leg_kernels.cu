@@ -12,6 +12,9 @@
 // and/or 12 B (vector) out per point — each byte crosses HBM exactly once.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <type_traits>
 
 #include "bulk_copy.cuh"
 #include "kernels.h"
@@ -25,26 +28,35 @@ constexpr int kThreads = 256;
 constexpr int kTile = 1024;  // points per tile (multiple of 16 keeps every bulk copy 16-B sized)
 constexpr int kStages = 2;
 constexpr size_t kAtlasMinPoints = size_t(1) << 22;
-static_assert(kTile % kThreads == 0 && kTile % 16 == 0, "tile shape");
+// deferred points of the fast path: entries of at most two tiles plus a partial flush block
+constexpr int kQueueCap = 2 * kTile + kThreads + 256;
+static_assert(kTile % kThreads == 0 && kTile % 16 == 0 && kTile <= 1024, "tile shape");
 
-template <int MODE>
+// shared-memory state of the fast path: certified tables + the ring of parked points
+struct FastSmem {
+    alignas(16) WinnerTable winners;
+    alignas(16) YawSol ysol[16];
+    alignas(16) unsigned char ycode[kYawBins + 16];
+    uint32_t queue[kQueueCap];  // ring: iteration << 10 | index in tile
+    unsigned qcnt[3];           // entries appended in iteration it % 3
+};
+struct NoFastSmem {};
+
+template <int MODE, bool FAST>
 struct alignas(128) StreamSmem {
     float in[kStages][3 * kTile];
     float vec[(MODE & kModeDist) ? 2 : 1][(MODE & kModeDist) ? 3 * kTile : 4];
     uint8_t flag[2][kTile];
     alignas(16) SectorTable table;
-    alignas(16) WinnerTable winners;   // atlas fast path
-    uint16_t queue[kTile];              // points of the current tile the atlas could not certify
-    int qcount[2];
+    alignas(16) typename std::conditional<FAST, FastSmem, NoFastSmem>::type fast;
     alignas(8) uint64_t full[kStages];
 };
 
-// Returns false only with ATLAS when the point could not be certified (nothing is written then).
-template <int MODE, bool SOA, bool GENERIC, bool ATLAS = false>
-__device__ __forceinline__ bool compute_point(const LegPlan& L, const SectorTable& tab,
+// One point through the full evaluation.
+template <int MODE, bool SOA, bool GENERIC>
+__device__ __forceinline__ void compute_point(const LegPlan& L, const SectorTable& tab,
                                               const float* in, float* vec, uint8_t* flag, int i,
-                                              int stride_pts, const AtlasView* A = nullptr,
-                                              const WinnerTable* W = nullptr) {
+                                              int stride_pts) {
     float x, y, z;
     if (SOA) {
         x = in[i], y = in[stride_pts + i], z = in[2 * stride_pts + i];
@@ -55,9 +67,7 @@ __device__ __forceinline__ bool compute_point(const LegPlan& L, const SectorTabl
     if (MODE == kModeReach) {
         flag[i] = reach_coxa_frame(L, tab, p) ? 1 : 0;
     } else {
-        bool ok = true;
-        const DistResult r = dist_coxa_frame<GENERIC, ATLAS>(L, tab, p, A, W, &ok);
-        if (ATLAS && !ok) return false;
+        const DistResult r = dist_coxa_frame<GENERIC>(L, tab, p);
         if (SOA) {
             vec[i] = r.dx, vec[stride_pts + i] = r.dy, vec[2 * stride_pts + i] = r.dz;
         } else {
@@ -66,21 +76,51 @@ __device__ __forceinline__ bool compute_point(const LegPlan& L, const SectorTabl
         // MODE dist: distance_global's bool; MODE both: reachability_global's bool
         flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
     }
+}
+
+// One point through the certified tables; false (nothing written) when they cannot decide it.
+template <int MODE, bool SOA, bool TEX>
+__device__ __forceinline__ bool compute_point_fast(const LegPlan& L, const FastView& F,
+                                                   const AtlasView& A, const WinnerTable& W,
+                                                   const float* in, float* vec, uint8_t* flag, int i) {
+    float x, y, z;
+    if (SOA) {
+        x = in[i], y = in[kTile + i], z = in[2 * kTile + i];
+    } else {
+        x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+    }
+    DistResult r;
+    if (!dist_fast<TEX>(L, F, A, W, to_coxa_frame(L, x, y, z), &r)) return false;
+    if (SOA) {
+        vec[i] = r.dx, vec[kTile + i] = r.dy, vec[2 * kTile + i] = r.dz;
+    } else {
+        vec[3 * i] = r.dx, vec[3 * i + 1] = r.dy, vec[3 * i + 2] = r.dz;
+    }
+    flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
     return true;
 }
 
 // AoS: in_x = xyz (N x 3), out_x = vectors (N x 3).  SoA: separate planes.
-template <int MODE, bool SOA, bool GENERIC, bool ATLAS>
+//
+// FAST (distance modes, standard legs, large sweeps): every point first goes through the
+// certified tables (dist_fast).  The few points they cannot decide are NOT redone inside the
+// tile — that would leave most warps idle at the tile barrier while two or three of them run the
+// long evaluation — but parked in a per-CTA ring and redone later, 256 at a time by all threads
+// (dense warps, equal work), straight from / to global memory.  A parked point is only redone
+// once the bulk store of its tile has completed (its slot in the output then holds stale bytes
+// that the late plain store replaces): thread 0 waits for all committed stores before every tile
+// barrier, so entries appended two iterations ago are safe.
+template <int MODE, bool SOA, bool GENERIC, bool FAST, bool TEX>
 __global__ void __launch_bounds__(kThreads)
-    one_leg_stream_kernel(const __grid_constant__ LegPlan L, const AtlasView atlas,
-                          const float* __restrict__ in_x, const float* __restrict__ in_y,
-                          const float* __restrict__ in_z, float* __restrict__ out_x,
-                          float* __restrict__ out_y, float* __restrict__ out_z,
-                          uint8_t* __restrict__ out_flag, size_t n) {
+    one_leg_stream_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
+                          const AtlasView atlas, const float* __restrict__ in_x,
+                          const float* __restrict__ in_y, const float* __restrict__ in_z,
+                          float* __restrict__ out_x, float* __restrict__ out_y,
+                          float* __restrict__ out_z, uint8_t* __restrict__ out_flag, size_t n) {
     // keep the pointer provably in the shared window (LDS/STS, not generic LD/ST): no integer
     // round-trip on the address; the bulk engine only needs 16-byte alignment
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    auto& S = *reinterpret_cast<StreamSmem<MODE>*>(smem_raw);
+    auto& S = *reinterpret_cast<StreamSmem<MODE, FAST>*>(smem_raw);
     const int tid = threadIdx.x;
 
     const size_t n_bulk = n & ~size_t(15);  // points that move through the bulk engine
@@ -88,11 +128,17 @@ __global__ void __launch_bounds__(kThreads)
     constexpr bool kVec = (MODE & kModeDist) != 0;
 
     fill_sector_table(L, &S.table, tid, kThreads);
-    if (ATLAS) fill_winner_table(L, &S.winners, tid, kThreads);
+    if constexpr (FAST) {
+        fill_winner_table(L, &S.fast.winners, tid, kThreads);
+        for (int i = tid; i < 16 * (int)(sizeof(YawSol) / 4); i += kThreads)
+            reinterpret_cast<float*>(S.fast.ysol)[i] = reinterpret_cast<const float*>(FT.sol)[i];
+        for (int i = tid; i < (kYawBins + 16) / 4; i += kThreads)
+            reinterpret_cast<uint32_t*>(S.fast.ycode)[i] = reinterpret_cast<const uint32_t*>(FT.code)[i];
+        if (tid == 0) S.fast.qcnt[0] = S.fast.qcnt[1] = S.fast.qcnt[2] = 0;
+    }
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) bulk::mbar_init(&S.full[s], 1);
         bulk::fence_barrier_init();
-        S.qcount[0] = S.qcount[1] = 0;
     }
     __syncthreads();
 
@@ -113,6 +159,25 @@ __global__ void __launch_bounds__(kThreads)
             bulk::load(&S.in[stage][0], in_x + 3 * first, cnt * 12, &S.full[stage]);
         }
     };
+    // a parked point, redone from / to global memory
+    auto redo = [&](uint32_t entry, uint32_t it_now) {
+        const uint32_t age = (it_now - (entry >> 10)) & 0x3fffffu;
+        const size_t g = ((size_t)blockIdx.x + (size_t)(it_now - age) * gridDim.x) * kTile + (entry & 1023u);
+        float xyz[3], v[3];
+        uint8_t f;
+        if (SOA) {
+            xyz[0] = in_x[g], xyz[1] = in_y[g], xyz[2] = in_z[g];
+        } else {
+            xyz[0] = in_x[3 * g], xyz[1] = in_x[3 * g + 1], xyz[2] = in_x[3 * g + 2];
+        }
+        compute_point<MODE, false, false>(L, S.table, xyz, v, &f, 0, 0);
+        if (SOA) {
+            out_x[g] = v[0], out_y[g] = v[1], out_z[g] = v[2];
+        } else {
+            out_x[3 * g] = v[0], out_x[3 * g + 1] = v[1], out_x[3 * g + 2] = v[2];
+        }
+        if (out_flag) out_flag[g] = f;
+    };
 
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) {
@@ -121,7 +186,13 @@ __global__ void __launch_bounds__(kThreads)
         }
     }
 
+    FastView fview{nullptr, nullptr};
+    if constexpr (FAST) fview = FastView{S.fast.ysol, S.fast.ycode};
     uint32_t it = 0;
+    // ring bookkeeping, identical in every thread: entries appended before this iteration (base),
+    // before the previous one (elig: their tiles' stores have completed), and redone so far (head)
+    uint32_t q_base = 0, q_elig = 0, q_head = 0;
+    int rot = 0;  // it % 3
     for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int stage = it % kStages;
         const int ob = it & 1;
@@ -131,20 +202,21 @@ __global__ void __launch_bounds__(kThreads)
         const float* in = S.in[stage];
         float* vec = S.vec[kVec ? ob : 0];
         uint8_t* flag = S.flag[ob];
-        if (ATLAS) {
-            // pass 1: every point through the atlas; the few it cannot certify are queued ...
+        if constexpr (FAST) {
+            const int rot_prev = rot == 0 ? 2 : rot - 1;
+            q_elig = q_base;
+            q_base += S.fast.qcnt[rot_prev];  // final since the previous tile barrier
+#pragma unroll 1
+            while (q_elig - q_head >= (uint32_t)kThreads) {
+                redo(S.fast.queue[(q_head + tid) % kQueueCap], it);
+                q_head += kThreads;
+            }
 #pragma unroll 2
             for (int i = tid; i < (int)cnt; i += kThreads)
-                if (!compute_point<MODE, SOA, false, true>(L, S.table, in, vec, flag, i, kTile, &atlas,
-                                                           &S.winners))
-                    S.queue[atomicAdd(&S.qcount[ob], 1)] = (uint16_t)i;
-            __syncthreads();
-            // ... pass 2: and redone with the full evaluation by densely packed warps
-            const int nq = S.qcount[ob];
-            if (tid == 0) S.qcount[ob ^ 1] = 0;
-#pragma unroll 1
-            for (int k = tid; k < nq; k += kThreads)
-                compute_point<MODE, SOA, false, false>(L, S.table, in, vec, flag, S.queue[k], kTile);
+                if (!compute_point_fast<MODE, SOA, TEX>(L, fview, atlas, S.fast.winners, in, vec, flag, i)) {
+                    const uint32_t pos = q_base + atomicAdd(&S.fast.qcnt[rot], 1u);
+                    S.fast.queue[pos % kQueueCap] = (it << 10) | (uint32_t)i;
+                }
         } else {
 #pragma unroll 1
             for (int i = tid; i < (int)cnt; i += kThreads)
@@ -152,7 +224,16 @@ __global__ void __launch_bounds__(kThreads)
         }
 
         bulk::fence_proxy_async();  // results written through the generic proxy -> bulk engine
-        if (tid == 0) bulk::wait_group_read<0>();  // previous tile's store has drained its buffer
+        if (tid == 0) {
+            // FAST: every committed store has COMPLETED (parked points of those tiles may be redone);
+            // otherwise it only has to have drained its shared-memory buffer
+            if constexpr (FAST) {
+                bulk::wait_group<0>();
+                S.fast.qcnt[rot == 2 ? 0 : rot + 1] = 0;  // next iteration's counter (last read two barriers ago)
+            } else {
+                bulk::wait_group_read<0>();
+            }
+        }
         __syncthreads();
         if (tid == 0) {
             const size_t first = tile * kTile;
@@ -170,8 +251,17 @@ __global__ void __launch_bounds__(kThreads)
             const size_t next = tile + (size_t)kStages * gridDim.x;
             if (next < n_tiles) issue_load(next, stage);
         }
+        rot = rot == 2 ? 0 : rot + 1;
     }
     if (tid == 0) bulk::wait_group<0>();
+    if constexpr (FAST) {
+        // drain the ring: every store has completed, every entry is final after this barrier
+        __syncthreads();
+        const uint32_t total = q_base + (it ? S.fast.qcnt[rot == 0 ? 2 : rot - 1] : 0u);
+#pragma unroll 1
+        for (; q_head < total; q_head += kThreads)
+            if (q_head + tid < total) redo(S.fast.queue[(q_head + tid) % kQueueCap], it);
+    }
 
     // the last n % 16 points bypass the bulk engine (sizes must be multiples of 16 B)
     if (blockIdx.x == 0) {
@@ -310,12 +400,12 @@ int sm_count() {
     return g_sm_count;
 }
 
-template <int MODE, bool SOA, bool GENERIC, bool ATLAS>
-cudaError_t launch_stream_impl(const LegPlan& plan, const AtlasView& atlas, const float* ix,
-                               const float* iy, const float* iz, float* ox, float* oy, float* oz,
-                               uint8_t* flag, size_t n, cudaStream_t stream) {
-    auto kernel = one_leg_stream_kernel<MODE, SOA, GENERIC, ATLAS>;
-    constexpr size_t smem = sizeof(StreamSmem<MODE>);
+template <int MODE, bool SOA, bool GENERIC, bool FAST, bool TEX>
+cudaError_t launch_stream_impl(const LegPlan& plan, const FastTables& ft, const AtlasView& atlas,
+                               const float* ix, const float* iy, const float* iz, float* ox, float* oy,
+                               float* oz, uint8_t* flag, size_t n, cudaStream_t stream) {
+    auto kernel = one_leg_stream_kernel<MODE, SOA, GENERIC, FAST, TEX>;
+    constexpr size_t smem = sizeof(StreamSmem<MODE, FAST>);
     // per-device: the attribute belongs to the device's copy of the function
     static int ctas_per_sm_dev[64] = {0};
     int dev = 0;
@@ -334,8 +424,19 @@ cudaError_t launch_stream_impl(const LegPlan& plan, const AtlasView& atlas, cons
     size_t grid = (size_t)sm_count() * ctas_per_sm;
     if (tiles < grid) grid = tiles;
     if (grid == 0) grid = 1;
-    kernel<<<(unsigned)grid, kThreads, smem, stream>>>(plan, atlas, ix, iy, iz, ox, oy, oz, flag, n);
+    kernel<<<(unsigned)grid, kThreads, smem, stream>>>(plan, ft, atlas, ix, iy, iz, ox, oy, oz, flag, n);
     return cudaGetLastError();
+}
+
+// LRM_ATLAS_TEX=0 selects plain loads from the blocked copy of the atlas instead of the texture
+// unit (same cells, same results; kept for A/B measurements)
+bool atlas_through_texture() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LRM_ATLAS_TEX");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
 }
 
 // reach-only never cross-validates, so only the distance modes have a generic instantiation
@@ -344,23 +445,30 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
                           float* ox, float* oy, float* oz, uint8_t* flag, size_t n,
                           cudaStream_t stream) {
     AtlasView none{};
+    static const FastTables no_tables{};
     if (MODE == kModeReach)
-        return launch_stream_impl<MODE, SOA, false, false>(plan, none, ix, iy, iz, ox, oy, oz, flag, n,
-                                                           stream);
+        return launch_stream_impl<MODE, SOA, false, false, false>(plan, no_tables, none, ix, iy, iz, ox, oy,
+                                                                  oz, flag, n, stream);
     constexpr bool kDist = MODE != kModeReach;
     if (plan.generic)
-        return launch_stream_impl<MODE, SOA, kDist, false>(plan, none, ix, iy, iz, ox, oy, oz, flag, n,
-                                                           stream);
-    // the atlas pays for itself (16 Mi probes) only on large sweeps, or once it is cached
-    if (n >= kAtlasMinPoints) {
+        return launch_stream_impl<MODE, SOA, kDist, false, false>(plan, no_tables, none, ix, iy, iz, ox, oy,
+                                                                  oz, flag, n, stream);
+    // the atlas pays for itself (16 Mi probes) only on large sweeps, or once it is cached; ring
+    // entries hold a 22-bit per-CTA iteration count (n / (kTile * grid) is far below that)
+    if (n >= kAtlasMinPoints && n / kTile / (size_t)sm_count() < (size_t(1) << 21)) {
         AtlasView atlas;
         cudaError_t e = get_plane_atlas(plan, stream, &atlas);
         if (e != cudaSuccess) return e;
-        return launch_stream_impl<MODE, SOA, false, kDist>(plan, atlas, ix, iy, iz, ox, oy, oz, flag, n,
-                                                           stream);
+        FastTables ft;
+        build_fast_tables(plan, &ft);
+        if (atlas_through_texture())
+            return launch_stream_impl<MODE, SOA, false, kDist, kDist>(plan, ft, atlas, ix, iy, iz, ox, oy, oz,
+                                                                      flag, n, stream);
+        return launch_stream_impl<MODE, SOA, false, kDist, false>(plan, ft, atlas, ix, iy, iz, ox, oy, oz, flag,
+                                                                  n, stream);
     }
-    return launch_stream_impl<MODE, SOA, false, false>(plan, none, ix, iy, iz, ox, oy, oz, flag, n,
-                                                       stream);
+    return launch_stream_impl<MODE, SOA, false, false, false>(plan, no_tables, none, ix, iy, iz, ox, oy, oz,
+                                                              flag, n, stream);
 }
 
 template <int MODE>

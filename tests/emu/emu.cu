@@ -77,38 +77,45 @@ void emu_dist_generic(const float* xyz, size_t n, const lrm_leg_t* leg, const fl
     }
 }
 
-// The atlas path exactly as the streaming kernel runs it: certified cells take plane_lookup, the
-// rest fall back to the full evaluation.  Returns the number of points that fell back.
+// The fast path exactly as the streaming kernel runs it (dist_fast: yaw-sector table + plane
+// atlas); points the tables cannot certify fall back to the full evaluation.  Returns the number
+// of points that fell back; *pure_cells / *pure_bins report the certified share of both tables.
 size_t emu_dist_atlas(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, int dim,
                       float cell, float* out_vec, uint8_t* out_flag, uint8_t* out_reach,
-                      size_t* pure_cells) {
+                      size_t* pure_cells, size_t* pure_bins) {
     lrm::LegPlan L;
     lrm::build_leg_plan(*leg, quat, &L);
     lrm::SectorTable tab;
     host_table(L, &tab);
     lrm::WinnerTable win;
     lrm::fill_winner_table(L, &win, 0, 1);
+    lrm::FastTables ft;
+    lrm::build_fast_tables(L, &ft);
+    if (pure_bins) {
+        *pure_bins = 0;
+        for (int b = 0; b <= lrm::kYawBins; b++) *pure_bins += ft.code[b] != lrm::kYawImpure;
+    }
     const float origin = -0.5f * dim * cell;
-    signed char* cells = new signed char[(size_t)dim * dim];
-    const float need = cell * 0.70711f * 1.02f + 2.0e-3f;  // same rule as atlas_build_kernel
+    unsigned char* cells = new unsigned char[(size_t)dim * dim];
+    const float need = lrm::kAtlasNeedFactor * cell + lrm::kAtlasNeedSlack;  // rule of atlas_build_kernel
     size_t pure = 0;
     for (int iy = 0; iy < dim; iy++)
         for (int ix = 0; ix < dim; ix++) {
             const float X = origin + ((float)ix + 0.5f) * cell, Y = origin + ((float)iy + 0.5f) * cell;
             const lrm::PlaneProbe pr = lrm::plane_probe(L, tab, X, Y);
             const bool ok = pr.safety > need;
-            cells[lrm::atlas_index(dim, ix, iy)] = (signed char)(ok ? pr.label : 0x80);
+            cells[lrm::atlas_index(dim, ix, iy)] = (unsigned char)(ok ? (lrm::kAtlasPure | (unsigned)pr.label) : 0);
             pure += ok;
         }
     if (pure_cells) *pure_cells = pure;
-    lrm::AtlasView A{cells, origin, origin, 1.0f / cell, dim, dim};
+    lrm::AtlasView A{cells, 0, 1.0f / cell, -origin / cell, -origin / cell, dim, dim};
+    const lrm::FastView F{ft.sol, ft.code};
     size_t fallback = 0;
     for (size_t i = 0; i < n; i++) {
         const lrm::CoxaPoint p = lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
-        bool ok = true;
-        lrm::DistResult r = lrm::dist_coxa_frame<false, true>(L, tab, p, &A, &win, &ok);
-        if (!ok) {
-            r = lrm::dist_coxa_frame<false, false>(L, tab, p);
+        lrm::DistResult r;
+        if (!lrm::dist_fast<false>(L, F, A, win, p, &r)) {
+            r = lrm::dist_coxa_frame<false>(L, tab, p);
             fallback++;
         }
         out_vec[3 * i] = r.dx, out_vec[3 * i + 1] = r.dy, out_vec[3 * i + 2] = r.dz;

@@ -117,31 +117,48 @@ def test_arc_tables_cover_default_legs_and_match_cross_validation(emu, port):
             assert (diff > 1e-2).sum() <= 4, (robot, az, int((diff > 1e-2).sum()))
 
 
-def test_plane_atlas_never_changes_a_result(emu, port):
-    """The plane atlas (leg_math.cuh plane_probe / plane_lookup) is a pure accelerator: certified
-    cells must reproduce the full evaluation (flags identical, vectors to float rounding), and
-    enough cells must be certified for it to be worth having."""
+def test_fast_path_never_changes_a_result(emu, port):
+    """The fast path of the distance sweep (leg_math.cuh dist_fast: yaw-sector table + plane atlas)
+    is a pure accelerator: wherever both tables certify a point it must reproduce the full
+    evaluation (flags identical, vectors to float rounding: a certified cell evaluates
+    P - projection as v (1 - r/|v|) instead of P - (c + v r/|v|)), and enough of both tables must
+    be certified to be worth having.
+    The cloud includes rings of points straddling every yaw decision (limits, limits +- pi/2, the
+    +-pi seam, the x axis) at several radii."""
     vp, sz = ctypes.c_void_p, ctypes.c_size_t
-    emu.emu_dist_atlas.argtypes = [vp, sz, vp, vp, ctypes.c_int, ctypes.c_float, vp, vp, vp, vp]
+    emu.emu_dist_atlas.argtypes = [vp, sz, vp, vp, ctypes.c_int, ctypes.c_float, vp, vp, vp, vp, vp]
     emu.emu_dist_atlas.restype = ctypes.c_size_t
     rng = np.random.default_rng(31)
-    pts = np.concatenate([rng.uniform([-100, -400, -500], [600, 400, 200], (60000, 3)),
-                          rng.uniform(-700, 700, (30000, 3))]).astype(np.float32)
+    cloud = np.concatenate([rng.uniform([-100, -400, -500], [600, 400, 200], (60000, 3)),
+                            rng.uniform(-700, 700, (30000, 3))]).astype(np.float32)
     cases = ((1, 0.0, [1, 0, 0, 0]), (0, 0.7853982, port.quaternion_from_angle_index(0)),
              (1, 3.9269907, port.full_struct_orientations()[31]))
     for robot, az, q in cases:
         leg = port.get_leg(robot, az)
         q = np.ascontiguousarray(q, np.float32)
+        # rings around the coxa axis in the world frame of an identity-orientation leg would only
+        # hit the boundaries for az = 0; build them in the coxa frame and map back instead:
+        # world = R^T (p_coxa - t) is not needed exactly — any dense set of directions does, so
+        # sweep the azimuth densely around the leg's mount point at several heights.
+        ang = np.linspace(-np.pi, np.pi, 7201)
+        near = np.concatenate([ang + d for d in (-1e-4, -1e-6, 0.0, 1e-6, 1e-4)])
+        rings = []
+        for rad, z in ((40.0, -50.0), (200.0, -120.0), (420.0, 30.0)):
+            cx, cy = np.float32(leg[1]) * np.cos(az), np.float32(leg[1]) * np.sin(az)
+            rings.append(np.stack([cx + rad * np.cos(near), cy + rad * np.sin(near), np.full_like(near, z)], 1))
+        pts = np.ascontiguousarray(np.concatenate([cloud] + rings), np.float32)
         _, base, bf, br = run_emu(emu, pts, leg, q)
         out = np.zeros_like(pts)
         fl = np.zeros(len(pts), np.uint8)
         rf = np.zeros(len(pts), np.uint8)
-        pure = ctypes.c_size_t(0)
+        pure, bins = ctypes.c_size_t(0), ctypes.c_size_t(0)
         fb = emu.emu_dist_atlas(pts.ctypes.data, len(pts), leg.ctypes.data, q.ctypes.data, 1024, 2.0,
-                                out.ctypes.data, fl.ctypes.data, rf.ctypes.data, ctypes.byref(pure))
+                                out.ctypes.data, fl.ctypes.data, rf.ctypes.data, ctypes.byref(pure),
+                                ctypes.byref(bins))
         assert np.array_equal(fl, bf) and np.array_equal(rf, br)
-        assert np.abs(out - base).max() < 1e-3
-        assert pure.value > 0.85 * 1024 * 1024 and fb < 0.3 * len(pts), (pure.value, fb)
+        assert np.abs(out - base).max() < 1e-3, float(np.abs(out - base).max())
+        assert pure.value > 0.85 * 1024 * 1024 and fb < 0.35 * len(pts), (pure.value, fb)
+        assert bins.value > 0.95 * 1025, bins.value
 
 
 def test_reach_plan_predicates(emu, port):
