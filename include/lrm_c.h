@@ -125,6 +125,9 @@ typedef struct lrm_posit_opts {
 
 /* Orientation set of robot_full_struct (several_leg.cu:811-857): writes 45 quaternions. */
 LRM_API int lrm_full_struct_orientations(float* out_quat4, int capacity);
+/* RPYtoQuat (octree_util.cu.h:164-172): roll, then pitch, then yaw, in the storage qtRotate
+ * expects — the way to build custom orientation sets (e.g. a yaw grid) for lrm_positionability. */
+LRM_API int lrm_rpy_to_quat(float roll, float pitch, float yaw, float out_quat4[4]);
 
 /* Replaces robot_full_struct's pipeline (several_leg.cu:326-877) with a per-pose result instead
  * of a compacted list: standable[b] = 1 + index of the first orientation in `quats` for which the

@@ -76,6 +76,7 @@ def lib():
         L.lrm_forward_kine.argtypes = [vp, sz, legp, vp, ci, vp, fp]
         L.lrm_make_lattice.argtypes = [vp, vp, vp, vp, sz, sz, vp]
         L.lrm_full_struct_orientations.argtypes = [vp, ci]
+        L.lrm_rpy_to_quat.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_float, vp]
         L.lrm_positionability.argtypes = [vp, sz, vp, sz, legp, ci, vp, ci,
                                           ctypes.POINTER(PositOpts), vp, ci, vp, fp]
         L.lrm_recurs.argtypes = [vp, sz, legp, vp, ci, vp, ci, vp, fp]
@@ -279,6 +280,21 @@ def full_struct_orientations():
     q = np.empty((45, 4), dtype=np.float32)
     _check(lib().lrm_full_struct_orientations(q.ctypes.data, 45))
     return q
+
+
+def rpy_to_quat(roll, pitch, yaw):
+    """RPYtoQuat (octree_util.cu.h:164-172) in the storage qtRotate expects, (4,) float32."""
+    q = np.empty(4, dtype=np.float32)
+    _check(lib().lrm_rpy_to_quat(float(roll), float(pitch), float(yaw), q.ctypes.data))
+    return q
+
+
+def yaw_orientations(n_yaw, yaw_min=0.0, yaw_max=2.0 * np.pi):
+    """n_yaw level orientations with uniformly spaced yaw in [yaw_min, yaw_max) (BASELINE configs[4]:
+    dense body-pose x yaw grid)."""
+    ys = np.float32(yaw_min) + (np.float32(yaw_max) - np.float32(yaw_min)) * (
+        np.arange(n_yaw, dtype=np.float32) / np.float32(n_yaw))
+    return np.stack([rpy_to_quat(0.0, 0.0, y) for y in ys]).astype(np.float32)
 
 
 def positionability(bodies, map_points, legs, quats=None, pre_cull=False, stream=None, timing=False):

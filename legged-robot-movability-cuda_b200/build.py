@@ -30,7 +30,10 @@ def _stale():
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    deps += [os.path.join(ROOT, "include", "lrm_c.h"), os.path.abspath(__file__)]
+    deps += [os.path.join(ROOT, "include", "lrm_c.h"), os.path.abspath(__file__),
+             os.path.join(HERE, "driver", "lrm_cuda.cpp")]
+    if not os.path.exists(os.path.join(HERE, "lrm_cuda")):
+        return True
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -44,7 +47,20 @@ def build(force=False, verbose=False):
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
+    build_driver()
     return LIB
+
+
+DRIVER = os.path.join(HERE, "lrm_cuda")
+
+
+def build_driver():
+    """The file-protocol driver (driver/lrm_cuda.cpp): plain C++ over the C ABI, rpath = its own dir."""
+    cxx = os.environ.get("CXX", "g++")
+    cmd = [cxx, "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-o", DRIVER,
+           os.path.join(HERE, "driver", "lrm_cuda.cpp"), "-L" + HERE, "-llrm_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return DRIVER
 
 
 if __name__ == "__main__":

@@ -15,8 +15,10 @@ enum : int { kModeReach = 1, kModeDist = 2, kModeBoth = 3 };
 // One-leg sweep over N x 3 AoS points already on the device.  mode: kModeReach -> flag only,
 // kModeDist -> vector (+ distance_global's bool if flag != nullptr), kModeBoth -> vector +
 // reachability flag.
+// n_call: size of the whole call this launch is a chunk of (0 = n); the certified tables of the
+// distance fast path are built / used when the call, not the chunk, is large enough to pay for them.
 cudaError_t launch_one_leg_aos(int mode, const LegPlan& plan, const float* xyz, float* out_vec,
-                               uint8_t* flag, size_t n, cudaStream_t stream);
+                               uint8_t* flag, size_t n, cudaStream_t stream, size_t n_call = 0);
 // SoA planes; dx == nullptr selects reach-only.
 cudaError_t launch_one_leg_soa(const LegPlan& plan, const float* x, const float* y, const float* z,
                                float* dx, float* dy, float* dz, uint8_t* flag, size_t n,
@@ -31,9 +33,11 @@ cudaError_t launch_lattice(float* out, const float lo[3], const float step[3],
                            const uint32_t dims[3], size_t first, size_t count,
                            cudaStream_t stream);
 
-// Plane atlas of a plan (plane_atlas.cu): built on first use, cached per device.
+// Certified tables of a plan's distance fast path (plane_atlas.cu): the plane atlas (device) and
+// the yaw-sector table (host, passed as a kernel parameter); built on first use, cached per device.
 struct AtlasView;
-cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView* view);
+cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView* view,
+                            FastTables* tables);
 
 // Multi-leg positionability (positionability.cu).  All pointers are device pointers.
 struct PositParams {

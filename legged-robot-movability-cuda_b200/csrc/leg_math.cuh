@@ -329,10 +329,19 @@ LRM_HD float angle_margin(const AngleTest& t, float X, float Y) {
     return fminf(fabsf(cr), fabsf(Y));               // ... or to the X axis, where `up` flips
 }
 
-// plane_clamp<false> instrumented: same arithmetic, plus the smallest decision margin.
+// plane_clamp<false> instrumented: same arithmetic, plus the distance within which every decision
+// THAT CAN CHANGE THE OUTCOME keeps its sign:
+//   * the sector tests that select the circle set (middle, and the saturation test of this side);
+//   * "P is valid": when valid, every circle's margin; when invalid, the margin of the most
+//     robustly violated circle is enough (the others may flip, the AND stays false);
+//   * the winner: its own arc membership, and its lead over every rival — a rival being any corner
+//     (when P is invalid) and any circle that is, or within the cell could become, a candidate
+//     (a circle that is robustly NOT a candidate needs no lead; one that is far behind needs no
+//     robust candidacy).  Every distance involved is 1-Lipschitz, hence the factor 1/2 on leads.
 LRM_HD PlaneProbe plane_probe(const LegPlan& L, const SectorTable& tab, float X, float Y) {
-    float safety = fminf(angle_margin(L.middle, X, Y),
-                         fminf(angle_margin(L.sat[0], X, Y), angle_margin(L.sat[1], X, Y)));
+    const float upf = up_flag(Y);
+    const bool upper = angle_gt(L.middle, X, Y, upf);
+    float safety = fminf(angle_margin(L.middle, X, Y), angle_margin(L.sat[upper ? 1 : 0], X, Y));
     const int s = find_sector(L, X, Y);
     float cx[4], cy[4], r[4], sg[4], ax[4], ay[4], ah[4];
     cx[0] = 0.f, cy[0] = 0.f, r[0] = L.inner.r, sg[0] = L.inner.sgn;
@@ -346,9 +355,10 @@ LRM_HD PlaneProbe plane_probe(const LegPlan& L, const SectorTable& tab, float X,
         if (j == 1) ay[0] = a.w;
         if (j == 2) ah[0] = a.w;
     }
-    float key[4];
+    float key[4], arc[4];
     bool cand[4];
     bool valid = true;
+    float valid_margin = 3.0e38f, invalid_margin = 0.f;
     auto arc_margin = [&](float g, float h) {  // g = dot - h*m ; |h| > 1 means constant outcome
         return fabsf(h) > 1.f ? 3.0e38f : 0.5f * fabsf(g);
     };
@@ -360,17 +370,24 @@ LRM_HD PlaneProbe plane_probe(const LegPlan& L, const SectorTable& tab, float X,
         key[j] = fabsf(d);
         const float v = sg[j] * d + kMarginF;
         valid = valid & (v > 0.f);
-        safety = fminf(safety, fabsf(v));
+        if (v > 0.f) valid_margin = fminf(valid_margin, v);
+        else invalid_margin = fmaxf(invalid_margin, -v);
         const float g = fmaf(vx, ax[j], vy * ay[j]) - ah[j] * m;
         cand[j] = g >= 0.f;
-        safety = fminf(safety, arc_margin(g, ah[j]));
+        arc[j] = arc_margin(g, ah[j]);
         if (j == 0) {
+            // two arcs: candidate if inside either; robust if robustly inside one or robustly outside both
             const float g2 = fmaf(vx, inner_b.x, vy * inner_b.y) - inner_b.z * m;
-            cand[0] = cand[0] | (g2 >= 0.f);
-            safety = fminf(safety, arc_margin(g2, inner_b.z));
+            const float arc2 = arc_margin(g2, inner_b.z);
+            const bool c2 = g2 >= 0.f;
+            if (cand[0] && c2) arc[0] = fmaxf(arc[0], arc2);
+            else if (c2) arc[0] = arc2;
+            else if (!cand[0]) arc[0] = fminf(arc[0], arc2);
+            cand[0] = cand[0] | c2;
         }
     }
-    // winner and its lead over every other eligible candidate (each distance is 1-Lipschitz)
+    safety = fminf(safety, valid ? valid_margin : invalid_margin);
+    // winner
     int win = kAtlasNone;
     float best = 3.0e38f;
     for (int j = 0; j < 4; j++)
@@ -382,8 +399,14 @@ LRM_HD PlaneProbe plane_probe(const LegPlan& L, const SectorTable& tab, float X,
             ckey[i] = sqrtf(fmaf(wx, wx, wy * wy));
             if (ckey[i] < best) best = ckey[i], win = 4 + i;
         }
-    for (int j = 0; j < 4; j++)
-        if (cand[j] && j != win) safety = fminf(safety, 0.5f * (key[j] - best));
+    for (int j = 0; j < 4; j++) {
+        if (j == win) {
+            safety = fminf(safety, arc[j]);
+            continue;
+        }
+        const float lead = 0.5f * (key[j] - best);
+        safety = fminf(safety, cand[j] ? lead : fmaxf(arc[j], lead));
+    }
     if (!valid)
         for (int i = 0; i < L.n_corners; i++)
             if (4 + i != win) safety = fminf(safety, 0.5f * (ckey[i] - best));

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -77,8 +78,21 @@ struct EventPair {
 
 
 // ---- pipelined staging for host-pointer calls --------------------------------------------------
-constexpr size_t kChunkPoints = size_t(1) << 23;  // 8 Mi points: 96 MiB up, 104 MiB down
-constexpr int kSlots = 3;
+// Chunk size: small enough that filling and draining the pipeline (one chunk up before the first
+// kernel, one chunk down after the last) is a small share of a call, large enough that each copy
+// runs at the link rate (>= 24 MiB on this box's PCIe 5 x16, tools/pcie_probe.py).
+// LRM_STAGING_CHUNK (points) overrides it for measurements.
+constexpr size_t kDefaultChunkPoints = size_t(1) << 21;  // 2 Mi points: 24 MiB up, 26 MiB down
+constexpr int kSlots = 4;
+size_t chunk_points() {
+    static size_t v = 0;
+    if (v == 0) {
+        const char* e = getenv("LRM_STAGING_CHUNK");
+        const long long want = e ? atoll(e) : 0;
+        v = want >= 4096 ? ((size_t)want & ~size_t(15)) : kDefaultChunkPoints;
+    }
+    return v;
+}
 
 struct Staging {
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
@@ -125,6 +139,7 @@ int staged_one_leg(int mode, const lrm::LegPlan& plan, const float* xyz, size_t 
                    uint8_t* flags, cudaStream_t user_stream, float* kernel_ms) {
     const bool want_vec = (mode & lrm::kModeDist) != 0;
     const bool want_flag = flags != nullptr;
+    const size_t kChunkPoints = chunk_points();
     const size_t chunk = n < kChunkPoints ? n : kChunkPoints;
     const size_t nchunks = (n + chunk - 1) / chunk;
     // Large sweeps reuse one set of streams / events / device buffers per device for the life of
@@ -180,7 +195,7 @@ int staged_one_leg(int mode, const lrm::LegPlan& plan, const float* xyz, size_t 
         cudaStreamWaitEvent(st.s_cmp, st.uploaded[slot], 0);
         cudaEventRecord(st.k0[slot], st.s_cmp);
         LRM_CUDA(lrm::launch_one_leg_aos(mode, plan, st.d_in[slot], st.d_vec[slot], st.d_flag[slot], cnt,
-                                         st.s_cmp),
+                                         st.s_cmp, n),
                  "one-leg kernel launch");
         cudaEventRecord(st.k1[slot], st.s_cmp);
         cudaEventRecord(st.computed[slot], st.s_cmp);
@@ -419,6 +434,19 @@ int lrm_full_struct_orientations(float* out, int capacity) {
             }
         }
     }
+    return LRM_OK;
+}
+
+int lrm_rpy_to_quat(float roll, float pitch, float yaw, float out[4]) {
+    if (!out) return fail(LRM_ERR_INVALID, "out is NULL");
+    const float ax[3] = {1, 0, 0}, ay[3] = {0, 1, 0}, az[3] = {0, 0, 1};
+    float q_roll[4], q_pitch[4], q_yaw[4], tmp[4];
+    lrm::quat_from_vect_angle(ax, roll, q_roll);
+    lrm::quat_from_vect_angle(ay, pitch, tmp);
+    lrm::quat_multiply(tmp, q_roll, q_pitch);
+    lrm::quat_from_vect_angle(az, yaw, tmp);
+    lrm::quat_multiply(tmp, q_pitch, q_yaw);
+    std::memcpy(out, q_yaw, sizeof q_yaw);
     return LRM_OK;
 }
 

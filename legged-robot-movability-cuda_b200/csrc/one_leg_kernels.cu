@@ -7,8 +7,8 @@
 // Here: a persistent grid (a few CTAs per SM) walks the point array in tiles.  Tiles are staged
 // global -> shared by the bulk-copy engine (cp.async.bulk, mbarrier completion, kStages deep),
 // threads read their points from shared memory with conflict-free strides, keep every
-// intermediate in registers, write results back to shared memory and one thread per CTA sends
-// the tile to global memory with a bulk store.  Algorithmic HBM traffic: 12 B in + 1 B (flag)
+// intermediate in registers, write results back to shared memory (in place) and one thread per
+// CTA sends the tile to global memory with a bulk store.  Algorithmic HBM traffic: 12 B in + 1 B (flag)
 // and/or 12 B (vector) out per point — each byte crosses HBM exactly once.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,7 +26,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kTile = 1024;  // points per tile (multiple of 16 keeps every bulk copy 16-B sized)
-constexpr int kStages = 2;
+constexpr int kPrefetch = 2;  // tiles in flight ahead of the compute
 constexpr size_t kAtlasMinPoints = size_t(1) << 22;
 // deferred points of the fast path: entries of at most two tiles plus a partial flush block
 constexpr int kQueueCap = 2 * kTile + kThreads + 256;
@@ -44,8 +44,11 @@ struct NoFastSmem {};
 
 template <int MODE, bool FAST>
 struct alignas(128) StreamSmem {
+    // Distance modes work IN PLACE: a thread overwrites its point with the point's vector (same 12
+    // bytes), and the tile goes back to global memory from the buffer it arrived in.  Three
+    // buffers rotate (being loaded / being computed / being stored); reach-only needs two.
+    static constexpr int kStages = (MODE & kModeDist) ? 3 : 2;
     float in[kStages][3 * kTile];
-    float vec[(MODE & kModeDist) ? 2 : 1][(MODE & kModeDist) ? 3 * kTile : 4];
     uint8_t flag[2][kTile];
     alignas(16) SectorTable table;
     alignas(16) typename std::conditional<FAST, FastSmem, NoFastSmem>::type fast;
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(kThreads)
             reinterpret_cast<uint32_t*>(S.fast.ycode)[i] = reinterpret_cast<const uint32_t*>(FT.code)[i];
         if (tid == 0) S.fast.qcnt[0] = S.fast.qcnt[1] = S.fast.qcnt[2] = 0;
     }
+    constexpr int kStages = StreamSmem<MODE, FAST>::kStages;
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) bulk::mbar_init(&S.full[s], 1);
         bulk::fence_barrier_init();
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(kThreads)
     };
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) {
+        for (int s = 0; s < kPrefetch; s++) {
             const size_t tile = (size_t)blockIdx.x + (size_t)s * gridDim.x;
             if (tile < n_tiles) issue_load(tile, s);
         }
@@ -199,8 +203,8 @@ __global__ void __launch_bounds__(kThreads)
         const uint32_t cnt = tile_count(tile);
         bulk::mbar_wait(&S.full[stage], (it / kStages) & 1);
 
-        const float* in = S.in[stage];
-        float* vec = S.vec[kVec ? ob : 0];
+        float* in = S.in[stage];
+        float* vec = in;  // in place (unused in reach-only mode)
         uint8_t* flag = S.flag[ob];
         if constexpr (FAST) {
             const int rot_prev = rot == 0 ? 2 : rot - 1;
@@ -248,8 +252,10 @@ __global__ void __launch_bounds__(kThreads)
             }
             if (out_flag) bulk::store(out_flag + first, flag, cnt);
             bulk::commit_group();
-            const size_t next = tile + (size_t)kStages * gridDim.x;
-            if (next < n_tiles) issue_load(next, stage);
+            // the buffer two tiles ahead is the one whose store (issued an iteration ago) thread 0
+            // has just waited for; with two buffers (reach-only) it is the one just consumed
+            const size_t next = tile + (size_t)kPrefetch * gridDim.x;
+            if (next < n_tiles) issue_load(next, (int)((it + kPrefetch) % kStages));
         }
         rot = rot == 2 ? 0 : rot + 1;
     }
@@ -443,7 +449,7 @@ bool atlas_through_texture() {
 template <int MODE, bool SOA>
 cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy, const float* iz,
                           float* ox, float* oy, float* oz, uint8_t* flag, size_t n,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, size_t n_call = 0) {
     AtlasView none{};
     static const FastTables no_tables{};
     if (MODE == kModeReach)
@@ -455,12 +461,11 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
                                                                   oz, flag, n, stream);
     // the atlas pays for itself (16 Mi probes) only on large sweeps, or once it is cached; ring
     // entries hold a 22-bit per-CTA iteration count (n / (kTile * grid) is far below that)
-    if (n >= kAtlasMinPoints && n / kTile / (size_t)sm_count() < (size_t(1) << 21)) {
+    if ((n_call > n ? n_call : n) >= kAtlasMinPoints && n / kTile / (size_t)sm_count() < (size_t(1) << 21)) {
         AtlasView atlas;
-        cudaError_t e = get_plane_atlas(plan, stream, &atlas);
-        if (e != cudaSuccess) return e;
         FastTables ft;
-        build_fast_tables(plan, &ft);
+        cudaError_t e = get_plane_atlas(plan, stream, &atlas, &ft);
+        if (e != cudaSuccess) return e;
         if (atlas_through_texture())
             return launch_stream_impl<MODE, SOA, false, kDist, kDist>(plan, ft, atlas, ix, iy, iz, ox, oy, oz,
                                                                       flag, n, stream);
@@ -492,7 +497,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 }  // namespace
 
 cudaError_t launch_one_leg_aos(int mode, const LegPlan& plan, const float* xyz, float* out_vec,
-                               uint8_t* flag, size_t n, cudaStream_t stream) {
+                               uint8_t* flag, size_t n, cudaStream_t stream, size_t n_call) {
     if (n == 0) return cudaSuccess;
     const bool bulk_ok = aligned16(xyz) && aligned16(out_vec) && aligned16(flag);
     switch (mode) {
@@ -502,11 +507,11 @@ cudaError_t launch_one_leg_aos(int mode, const LegPlan& plan, const float* xyz, 
                            : launch_plain<kModeReach>(plan, xyz, nullptr, flag, n, stream);
         case kModeDist:
             return bulk_ok ? launch_stream<kModeDist, false>(plan, xyz, nullptr, nullptr, out_vec,
-                                                             nullptr, nullptr, flag, n, stream)
+                                                             nullptr, nullptr, flag, n, stream, n_call)
                            : launch_plain<kModeDist>(plan, xyz, out_vec, flag, n, stream);
         case kModeBoth:
             return bulk_ok ? launch_stream<kModeBoth, false>(plan, xyz, nullptr, nullptr, out_vec,
-                                                             nullptr, nullptr, flag, n, stream)
+                                                             nullptr, nullptr, flag, n, stream, n_call)
                            : launch_plain<kModeBoth>(plan, xyz, out_vec, flag, n, stream);
     }
     return cudaErrorInvalidValue;

@@ -51,6 +51,7 @@ struct Entry {
     unsigned char* linear = nullptr;  // row-major staging copy for the texture upload
     cudaArray_t array = nullptr;
     cudaTextureObject_t tex = 0;
+    FastTables tables;  // yaw-sector table of the same plan (host-built, ~0.5 ms: cached with the atlas)
 };
 void release(Entry* c) {
     if (c->tex) cudaDestroyTextureObject(c->tex);
@@ -87,7 +88,7 @@ std::mutex g_mutex;
 
 }  // namespace
 
-cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView* view) {
+cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView* view, FastTables* tables) {
     std::lock_guard<std::mutex> lock(g_mutex);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -135,12 +136,14 @@ cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView*
         // other streams may use this entry next: make the build visible device-wide
         e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return e;
+        build_fast_tables(plan, &victim->tables);
         victim->used = true;
         victim->device = dev;
         std::memcpy(&victim->plan, &plan, sizeof(LegPlan));
         hit = victim;
     }
     hit->stamp = ++g_clock;
+    if (tables) *tables = hit->tables;
     view->cells = hit->cells;
     view->tex = hit->tex;
     view->inv_cell = 1.0f / kAtlasCell;

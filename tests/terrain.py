@@ -45,13 +45,15 @@ def fractal_noise_2d(shape, res, octaves=1, persistence=0.5, lacunarity=2):
 
 
 def perlin_terrain(n=1024, seed=42, x=(-2000.0, 2000.0), y=(-6000.0, 2000.0)):
-    """n x n lattice (n a multiple of 128) with the two fractal layers of maps.py:289-297."""
-    xs, ys = np.linspace(x[0], x[1], n), np.linspace(y[0], y[1], n)
+    """Lattice with the two fractal layers of maps.py:289-297.  n: points per side, or (ny, nx);
+    each a multiple of 128 (perlinnumpy2d.py:84-85)."""
+    ny, nx = (n, n) if np.isscalar(n) else (int(n[0]), int(n[1]))
+    xs, ys = np.linspace(x[0], x[1], nx), np.linspace(y[0], y[1], ny)
     X, Y, Z = np.meshgrid(xs, ys, 0)
     ground = np.concatenate([X.reshape(-1, 1), Y.reshape(-1, 1), Z.reshape(-1, 1)], axis=1).astype("float32")
     np.random.seed(seed=seed)
-    ground[:, 2] += (fractal_noise_2d((n, n), (8, 4), 5, 0.35, 2) * 300).reshape(-1)
-    ground[:, 2] += (fractal_noise_2d((n, n), (32, 16), 3, 0.2, 2) * 30).reshape(-1)
+    ground[:, 2] += (fractal_noise_2d((ny, nx), (8, 4), 5, 0.35, 2) * 300).reshape(-1).astype("float32")
+    ground[:, 2] += (fractal_noise_2d((ny, nx), (32, 16), 3, 0.2, 2) * 30).reshape(-1).astype("float32")
     return np.ascontiguousarray(ground, np.float32)
 
 

@@ -57,6 +57,17 @@ def test_full_struct_orientations_match_oracle(lrm, port, golden):
     assert np.allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-6)
 
 
+def test_rpy_to_quat_matches_oracle(lrm, port):
+    """RPYtoQuat (octree_util.cu.h:164-172), incl. the SURVEY appendix D known answers."""
+    for r, p, y in ((0, 0, 0), (-0.7853982, 0, 0), (-0.7853982, -0.3926991, -0.3926991), (0.1, -0.2, 2.5)):
+        assert np.array_equal(lrm.rpy_to_quat(r, p, y).view(np.uint32),
+                              np.asarray(port.rpy_to_quat(r, p, y), np.float32).view(np.uint32))
+    assert np.array_equal(lrm.rpy_to_quat(0, 0, 0), np.array([-1, 0, 0, 0], np.float32))
+    assert np.allclose(lrm.rpy_to_quat(-0.7853982, 0, 0), [-0.92388, -0.38268, 0, 0], atol=1e-5)
+    q = lrm.yaw_orientations(16)
+    assert q.shape == (16, 4) and np.allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-6)
+
+
 def test_argument_validation(lrm):
     L = lrm.lib()
     leg = lrm.get_M2_leg()

@@ -1,0 +1,18 @@
+"""A few launches of the fused reach+dist kernel on a resident lattice slab (profiling target)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import lrm_loader
+lrm = lrm_loader.load()
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+leg = lrm.get_M2_leg(0.0)
+lo, step, dims = lrm.lattice_spec((-100, -400, -500), (600, 400, 200), (max(1, n // 1_000_000), 1000, 1000))
+pts = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+lrm.make_lattice(pts, lo, step, dims, 0, n)
+flags = torch.empty(n, dtype=torch.uint8, device="cuda")
+vec = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+for _ in range(reps):
+    lrm.reach_dist(pts, leg, out_flags=flags, out_vec=vec)
+torch.cuda.synchronize()
+print("reachable", int(flags.sum().item()))
