@@ -618,7 +618,7 @@ LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, cons
 // plane-atlas cell of each solution's plane point.  Returns false — nothing is written — when
 // either table cannot certify the point; the caller then runs dist_coxa_frame.
 struct FastView {
-    const YawSol* sol;          // [16]
+    const YawPair* pair;        // [kYawPairs]
     const unsigned char* code;  // [kYawBins + 1]
 };
 
@@ -630,13 +630,12 @@ LRM_HD int yaw_bin(float ux, float uy) {
     return (int)fmaf(d, 0.25f * kYawBins, 0.5f * kYawBins);
 }
 
-LRM_HD BranchResult fast_branch(const CoxaPoint p, const YawSol& s, float cs, float ss,
-                                const PlaneResult pl) {
-    const float qx = pl.dx, qy = fmaf(p.y, cs, -p.x * ss), qz = pl.dy;  // in the plane's frame
+LRM_HD BranchResult fast_branch(const CoxaPoint p, const YawSol& s, float cs, float ss, float yr,
+                                float yl, const PlaneResult pl) {
+    const float qx = pl.dx, qy = yr, qz = pl.dy;  // in the plane's frame
     const float n2 = fmaf(qx, qx, fmaf(qy, qy, qz * qz));
     // in-plane region reached but the coxa-limit half-plane is nearer (one_leg.cu:258-274);
     // s.big = +inf switches the rule off for a mega-saturated yaw
-    const float yl = fmaf(p.y, s.cl, -p.x * s.sl);
     const float yl2 = fmaf(yl, yl, s.big);
     const bool to_plane = pl.valid & (n2 > yl2);
     BranchResult out;
@@ -659,10 +658,10 @@ LRM_HD bool dist_fast(const LegPlan& L, const FastView& F, const AtlasView& A, c
     if ((unsigned)bin > (unsigned)kYawBins) return false;
     const unsigned code = F.code[bin];
     if (code == kYawImpure) return false;
-    const unsigned ia = code & 15u, ib = code >> 4;
-    const bool has_a = ia != (unsigned)kYawSkip, has_b = ib != (unsigned)kYawSkip;
-    const YawSol& sa = F.sol[has_a ? ia : 0u];
-    const YawSol& sb = F.sol[has_b ? ib : 0u];
+    const YawPair& pr = F.pair[code];
+    const YawSol& sa = pr.a;
+    const YawSol& sb = pr.b;
+    const bool has_a = sa.present != 0.f, has_b = sb.present != 0.f;
     const float csa = fmaf(sa.k, ux, sa.c_cs), ssa = fmaf(sa.k, uy, sa.c_ss);
     const float csb = fmaf(sb.k, ux, sb.c_cs), ssb = fmaf(sb.k, uy, sb.c_ss);
     const float Xa = fmaf(p.x, csa, p.y * ssa) - L.coxa_length;
@@ -672,12 +671,18 @@ LRM_HD bool dist_fast(const LegPlan& L, const FastView& F, const AtlasView& A, c
     const unsigned la = has_a ? atlas_fetch<TEX>(A, fmaf(Xa, A.inv_cell, A.ox), fy) : kAtlasPure;
     const unsigned lb = has_b ? atlas_fetch<TEX>(A, fmaf(Xb, A.inv_cell, A.ox), fy) : kAtlasPure;
     if (((la & lb) & kAtlasPure) == 0u) return false;
+    // a solution that is absent can never be preferred: res = false, infinitely far
     BranchResult a, b;
-    a.res = b.res = false, a.vx = a.vy = a.vz = b.vx = b.vy = b.vz = 0.f, a.n2 = b.n2 = 0.f;
-    if (has_a) a = fast_branch(p, sa, csa, ssa, plane_from_label(W, la, Xa, p.z));
-    if (has_b) b = fast_branch(p, sb, csb, ssb, plane_from_label(W, lb, Xb, p.z));
-    if (!has_a) a = b, a.res = false;
-    if (!has_b) b = a, b.res = false;
+    a.res = b.res = false, a.vx = a.vy = a.vz = b.vx = b.vy = b.vz = 0.f, a.n2 = b.n2 = 3.0e38f;
+    const float yra = fmaf(p.y, csa, -p.x * ssa), yla = fmaf(p.y, sa.cl, -p.x * sa.sl);
+    const float yrb = fmaf(p.y, csb, -p.x * ssb), ylb = fmaf(p.y, sb.cl, -p.x * sb.sl);
+    if (has_a) a = fast_branch(p, sa, csa, ssa, yra, yla, plane_from_label(W, la, Xa, p.z));
+    // A saturated flipped solution reports res = false and a vector at least as long as its
+    // offset from its own plane (or from its limit plane): when the direct one is valid, or
+    // already nearer than that, the flipped one cannot be chosen and is not evaluated.
+    const float floor_b = fminf(yrb * yrb, fmaf(ylb, ylb, sb.big));
+    const bool need_b = has_b & !((sb.nsat == 0.f) & has_a & (a.res | (a.n2 < floor_b)));
+    if (need_b) b = fast_branch(p, sb, csb, ssb, yrb, ylb, plane_from_label(W, lb, Xb, p.z));
     const bool direct = (a.res == b.res) ? (a.n2 < b.n2) : a.res;
     const float vx = direct ? a.vx : b.vx, vy = direct ? a.vy : b.vy, vz = direct ? a.vz : b.vz;
     out->flag = a.res | b.res;

@@ -104,14 +104,12 @@ struct LegPlan {
 // direction of the point around the coxa axis only.  The circle of directions is cut into
 // kYawBins bins of equal "diamond angle" (uy / (|ux| + |uy|), monotone in atan2); a bin whose five
 // yaw tests are constant for the direct AND the pi-flipped solution over the whole (padded) bin
-// carries a code = (flipped solution index << 4) | direct solution index into `sol`, or
-// kYawSkip for a solution that duplicates the other one (one_leg.cu:225-226); bins that contain a
+// carries the index of its (direct, flipped) solution pair in `pair`; bins that contain a
 // decision boundary, the +-pi seam or the x axis (signed-zero rules) are kYawImpure and the point
 // takes the full evaluation.  The table never changes a result, it only replaces ~100
 // instructions of tests and selects by one shared-memory load.
 constexpr int kYawBins = 1024;
-constexpr int kYawSolutions = 14;
-constexpr int kYawSkip = 15;
+constexpr int kYawPairs = 16;         // distinct (direct, flipped) combinations a leg can have
 constexpr uint8_t kYawImpure = 0xFF;
 struct alignas(16) YawSol {
     float k;           // plane direction (cs, ss) = k * (ux, uy) + (c_cs, c_ss):
@@ -119,11 +117,14 @@ struct alignas(16) YawSol {
     float nsat;        // 1 if the yaw is unsaturated (res = valid), else 0
     float cl, sl;      // direction of the coxa limit used by one_leg.cu:258-274
     float big;         // 0, or +inf when that rule is off (mega-saturated)
-    float pad;
+    float present;     // 0 for a solution that duplicates the other one (one_leg.cu:225-226)
+};
+struct YawPair {
+    YawSol a, b;  // direct and pi-flipped solution of one yaw sector
 };
 struct FastTables {
-    YawSol sol[16];
-    uint8_t code[kYawBins + 16];  // bins 0 .. kYawBins used
+    YawPair pair[kYawPairs];
+    uint8_t code[kYawBins + 16];  // bins 0 .. kYawBins: index into pair, or kYawImpure
 };
 void build_fast_tables(const LegPlan& plan, FastTables* out);
 

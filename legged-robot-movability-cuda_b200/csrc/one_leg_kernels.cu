@@ -35,7 +35,7 @@ static_assert(kTile % kThreads == 0 && kTile % 16 == 0 && kTile <= 1024, "tile s
 // shared-memory state of the fast path: certified tables + the ring of parked points
 struct FastSmem {
     alignas(16) WinnerTable winners;
-    alignas(16) YawSol ysol[16];
+    alignas(16) YawPair ypair[kYawPairs];
     alignas(16) unsigned char ycode[kYawBins + 16];
     uint32_t queue[kQueueCap];  // ring: iteration << 10 | index in tile
     unsigned qcnt[3];           // entries appended in iteration it % 3
@@ -103,6 +103,31 @@ __device__ __forceinline__ bool compute_point_fast(const LegPlan& L, const FastV
     return true;
 }
 
+// The full evaluation of one point straight from / to global memory.  Deliberately NOT inlined
+// into the streaming loop: inlined, the compiler hoists this path's ~60 plan constants into
+// uniform registers at the top of every tile whether or not anything is redone.
+template <int MODE, bool SOA>
+__device__ __noinline__ void redo_point(const LegPlan& L, const SectorTable& tab,
+                                        const float* __restrict__ in_x, const float* __restrict__ in_y,
+                                        const float* __restrict__ in_z, float* __restrict__ out_x,
+                                        float* __restrict__ out_y, float* __restrict__ out_z,
+                                        uint8_t* __restrict__ out_flag, size_t g) {
+    float xyz[3], v[3];
+    uint8_t f;
+    if (SOA) {
+        xyz[0] = in_x[g], xyz[1] = in_y[g], xyz[2] = in_z[g];
+    } else {
+        xyz[0] = in_x[3 * g], xyz[1] = in_x[3 * g + 1], xyz[2] = in_x[3 * g + 2];
+    }
+    compute_point<MODE, false, false>(L, tab, xyz, v, &f, 0, 0);
+    if (SOA) {
+        out_x[g] = v[0], out_y[g] = v[1], out_z[g] = v[2];
+    } else {
+        out_x[3 * g] = v[0], out_x[3 * g + 1] = v[1], out_x[3 * g + 2] = v[2];
+    }
+    if (out_flag) out_flag[g] = f;
+}
+
 // AoS: in_x = xyz (N x 3), out_x = vectors (N x 3).  SoA: separate planes.
 //
 // FAST (distance modes, standard legs, large sweeps): every point first goes through the
@@ -133,8 +158,8 @@ __global__ void __launch_bounds__(kThreads)
     fill_sector_table(L, &S.table, tid, kThreads);
     if constexpr (FAST) {
         fill_winner_table(L, &S.fast.winners, tid, kThreads);
-        for (int i = tid; i < 16 * (int)(sizeof(YawSol) / 4); i += kThreads)
-            reinterpret_cast<float*>(S.fast.ysol)[i] = reinterpret_cast<const float*>(FT.sol)[i];
+        for (int i = tid; i < kYawPairs * (int)(sizeof(YawPair) / 4); i += kThreads)
+            reinterpret_cast<float*>(S.fast.ypair)[i] = reinterpret_cast<const float*>(FT.pair)[i];
         for (int i = tid; i < (kYawBins + 16) / 4; i += kThreads)
             reinterpret_cast<uint32_t*>(S.fast.ycode)[i] = reinterpret_cast<const uint32_t*>(FT.code)[i];
         if (tid == 0) S.fast.qcnt[0] = S.fast.qcnt[1] = S.fast.qcnt[2] = 0;
@@ -167,20 +192,7 @@ __global__ void __launch_bounds__(kThreads)
     auto redo = [&](uint32_t entry, uint32_t it_now) {
         const uint32_t age = (it_now - (entry >> 10)) & 0x3fffffu;
         const size_t g = ((size_t)blockIdx.x + (size_t)(it_now - age) * gridDim.x) * kTile + (entry & 1023u);
-        float xyz[3], v[3];
-        uint8_t f;
-        if (SOA) {
-            xyz[0] = in_x[g], xyz[1] = in_y[g], xyz[2] = in_z[g];
-        } else {
-            xyz[0] = in_x[3 * g], xyz[1] = in_x[3 * g + 1], xyz[2] = in_x[3 * g + 2];
-        }
-        compute_point<MODE, false, false>(L, S.table, xyz, v, &f, 0, 0);
-        if (SOA) {
-            out_x[g] = v[0], out_y[g] = v[1], out_z[g] = v[2];
-        } else {
-            out_x[3 * g] = v[0], out_x[3 * g + 1] = v[1], out_x[3 * g + 2] = v[2];
-        }
-        if (out_flag) out_flag[g] = f;
+        redo_point<MODE, SOA>(L, S.table, in_x, in_y, in_z, out_x, out_y, out_z, out_flag, g);
     };
 
     if (tid == 0) {
@@ -191,7 +203,7 @@ __global__ void __launch_bounds__(kThreads)
     }
 
     FastView fview{nullptr, nullptr};
-    if constexpr (FAST) fview = FastView{S.fast.ysol, S.fast.ycode};
+    if constexpr (FAST) fview = FastView{S.fast.ypair, S.fast.ycode};
     uint32_t it = 0;
     // ring bookkeeping, identical in every thread: entries appended before this iteration (base),
     // before the previous one (elig: their tiles' stores have completed), and redone so far (head)

@@ -109,7 +109,7 @@ size_t emu_dist_atlas(const float* xyz, size_t n, const lrm_leg_t* leg, const fl
         }
     if (pure_cells) *pure_cells = pure;
     lrm::AtlasView A{cells, 0, 1.0f / cell, -origin / cell, -origin / cell, dim, dim};
-    const lrm::FastView F{ft.sol, ft.code};
+    const lrm::FastView F{ft.pair, ft.code};
     size_t fallback = 0;
     for (size_t i = 0; i < n; i++) {
         const lrm::CoxaPoint p = lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);

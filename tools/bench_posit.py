@@ -1,12 +1,15 @@
-"""Positionability benchmark (BASELINE configs[2] shape): Perlin terrain map, pose lattice, M2
-legs, the 45 orientations of robot_full_struct.  Prints one JSON line (body poses/s).
+"""Positionability benchmarks (BASELINE configs[2..4]).  Prints one JSON line per run.
 
-    python tools/bench_posit.py [--map 1024] [--poses 64 128 32] [--check 3000] [--pre-cull]
+    python tools/bench_posit.py --config c3            # 4 legs, 1 Mi-point Perlin map, 256^3 poses, 45 RPY
+    python tools/bench_posit.py --config c4            # 50 M-point map: lrm_oct + pose search on it
+    python tools/bench_posit.py --config c5            # 6 legs at k*pi/3, pose lattice x 16 yaws
+    python tools/bench_posit.py [--map 1024] [--poses 64 128 32] [--legs 4] [--yaws 0] [--check 3000]
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_posit.py ...
 
 Multi-GPU: rank 0 builds the map and broadcasts it once over NCCL (NVLink /
 NVSwitch); every rank then owns a contiguous slab of poses — no collective in the search itself;
 the per-slab standable counts are gathered at the end and the time is the max over ranks.
+The CPU check runs the oracle (all host threads) on a random sample of poses of rank 0's slab.
 """
 import argparse, json, os, sys, time
 import numpy as np
@@ -16,14 +19,31 @@ import torch.distributed as dist
 import lrm_loader
 from tests import terrain
 
+PRESETS = {
+    # BASELINE configs[2]: 4-leg positionability, 1 Mi-point Perlin map, 256^3 body poses
+    "c3": dict(map=[1024, 1024], poses=[256, 256, 256], legs=4, yaws=0, oct_depth=-1),
+    # configs[3]: 50 M-point terrain (7168 x 7040 lattice), map replicated per GPU; the body-space
+    # octree (apply_oct semantics) over all footholds + the pose search on the same map
+    "c4": dict(map=[7168, 7040], poses=[128, 128, 64], legs=4, yaws=0, oct_depth=6),
+    # configs[4]: hexapod, mounts k*pi/3, dense pose lattice x yaw grid
+    "c5": dict(map=[1024, 1024], poses=[256, 256, 64], legs=6, yaws=16, oct_depth=-1),
+}
+
 ap = argparse.ArgumentParser()
-ap.add_argument("--map", type=int, default=1024)
+ap.add_argument("--config", choices=sorted(PRESETS), default=None)
+ap.add_argument("--map", type=int, nargs="+", default=[1024], help="points per side, or ny nx")
 ap.add_argument("--poses", type=int, nargs=3, default=[64, 128, 32])
-ap.add_argument("--check", type=int, default=3000, help="poses to verify against the CPU oracle")
+ap.add_argument("--check", type=int, default=2000, help="poses to verify against the CPU oracle")
 ap.add_argument("--pre-cull", action="store_true")
 ap.add_argument("--legs", type=int, default=4)
-ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--yaws", type=int, default=0, help="0: the 45 RPY orientations of robot_full_struct; N: N level yaws")
+ap.add_argument("--oct-depth", type=int, default=-1, help=">= 0: also time lrm_oct on the map at this depth")
+ap.add_argument("--reps", type=int, default=2)
 args = ap.parse_args()
+if args.config:
+    for k, v in PRESETS[args.config].items():
+        setattr(args, k, v)
+map_shape = (args.map[0], args.map[0]) if len(args.map) == 1 else (args.map[0], args.map[1])
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -37,10 +57,13 @@ lrm = lrm_loader.load()
 from importlib import import_module
 slabs = import_module("lrm_b200.slabs")
 
-n_map = args.map * args.map
+n_map = map_shape[0] * map_shape[1]
 d_terr = torch.empty((n_map, 3), dtype=torch.float32, device=dev)
+gen_s = 0.0
 if rank == 0:
-    terr = terrain.perlin_terrain(args.map)
+    t0 = time.perf_counter()
+    terr = terrain.perlin_terrain(map_shape)
+    gen_s = time.perf_counter() - t0
     d_terr.copy_(torch.from_numpy(terr))
 bcast_ms = 0.0
 if world > 1:
@@ -49,12 +72,12 @@ if world > 1:
     dist.broadcast(d_terr, src=0)          # the map is replicated once
     torch.cuda.synchronize()
     bcast_ms = (time.perf_counter() - t0) * 1e3
-terr = d_terr.cpu().numpy()
+    terr = d_terr.cpu().numpy()
 bodies_all = terrain.body_lattice(terr, *args.poses)
 first, count = slabs.slab_range(len(bodies_all), rank, world)
 bodies = bodies_all[first:first + count]
 legs = [lrm.get_M2_leg(float(np.float32(k) * np.float32(2 * np.pi) / np.float32(args.legs))) for k in range(args.legs)]
-quats = lrm.full_struct_orientations()
+quats = lrm.yaw_orientations(args.yaws) if args.yaws > 0 else lrm.full_struct_orientations()
 d_bod = torch.from_numpy(bodies).to(dev)
 out, ms = lrm.positionability(d_bod, d_terr, legs, quats, pre_cull=args.pre_cull, timing=True)  # warm-up
 times = []
@@ -75,22 +98,47 @@ standable = torch.tensor([int((got != 0).sum())], dtype=torch.int64, device=dev)
 if world > 1:
     dist.all_reduce(standable)
 if rank == 0:
-    line = {"metric": "body poses/s (4-leg map positionability)", "value": len(bodies_all) / wall, "unit": "poses/s",
+    line = {"metric": f"body poses/s ({args.legs}-leg map positionability)", "value": len(bodies_all) / wall,
+            "unit": "poses/s", "config": args.config or "custom",
             "n_gpus": world, "poses": len(bodies_all), "map_points": n_map, "orientations": len(quats),
             "legs": args.legs, "wall_ms": wall * 1e3, "kernel_ms_max": kms, "standable": int(standable.item()),
-            "pre_cull": args.pre_cull, "map_broadcast_ms": bcast_ms}
+            "pre_cull": args.pre_cull, "map_broadcast_ms": bcast_ms, "map_generation_s": round(gen_s, 1)}
     if args.check and not args.pre_cull:
         from oracle.oracle import PortOracle
+        from tests import parity
         port = PortOracle()
         rng = np.random.default_rng(0)
         idx = rng.choice(len(bodies), size=min(args.check, len(bodies)), replace=False)
+        la = [l.as_array() for l in legs]
+        threads = os.cpu_count() or 1
         t0 = time.perf_counter()
-        want = port.standability(bodies[idx], terr, [l.as_array() for l in legs], quats, pre_cull=False,
-                                 threads=os.cpu_count() or 1)
+        want = port.standability(bodies[idx], terr, la, quats, pre_cull=False, threads=threads)
         cpu_s = time.perf_counter() - t0
-        line["check"] = {"poses": len(idx), "flag_diff": int(((got[idx] != 0) != (want != 0)).sum()),
-                         "standable_oracle": int((want != 0).sum()), "cpu_poses_per_s": len(idx) / cpu_s,
-                         "cpu_threads": os.cpu_count()}
-    print(json.dumps(line))
+        rep = parity.pose_report(bodies[idx], got[idx], want,
+                                 lambda p: port.standability(p, terr, la, quats, pre_cull=False, threads=threads))
+        bad = np.flatnonzero(got[idx] != want)
+        line["check"] = {"poses": len(idx), "parity": rep, "standable_oracle": int((want != 0).sum()),
+                         "cpu_poses_per_s": len(idx) / cpu_s, "cpu_threads": threads,
+                         "mismatches": [{"pose": [float(v) for v in bodies[idx[k]]], "b200": int(got[idx[k]]),
+                                         "oracle": int(want[k])} for k in bad[:8]]}
+    print(json.dumps(line), flush=True)
+    if args.oct_depth >= 0:
+        # apply_oct semantics on the whole map as footholds: shipped leg (no box can be valid, see
+        # DESIGN.md) and a wide-coxa leg (valid boxes appear once boxes are small)
+        for name, leg in (("M2_as_shipped", lrm.get_M2_leg(0.0)), ("wide_coxa", None)):
+            if leg is None:
+                a = lrm.get_M2_leg(0.0).as_array()
+                a[8], a[9] = 3.0, -3.0
+                leg = lrm.LegDimensions.from_array(a)
+            res, oms = lrm.apply_oct(d_terr, leg, max_depth=args.oct_depth, cap=1 << 20, timing=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res, oms = lrm.apply_oct(d_terr, leg, max_depth=args.oct_depth, cap=1 << 20, timing=True)
+            torch.cuda.synchronize()
+            owall = time.perf_counter() - t0
+            print(json.dumps({"metric": "apply_oct (body-space octree) wall ms", "config": args.config or "custom",
+                              "leg": name, "footholds": n_map, "max_depth": args.oct_depth,
+                              "valid_boxes": int(len(res)), "wall_ms": owall * 1e3, "kernel_ms": oms,
+                              "footholds_per_s": n_map / owall}), flush=True)
 if world > 1:
     dist.destroy_process_group()
