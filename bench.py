@@ -166,6 +166,8 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path); use --impl reference")
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's banner / debug lines go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n = args.points

@@ -218,10 +218,11 @@ struct alignas(16) ReachPlan {
     float inner_sgn, inner_thr_s;
     float r_min, r_max;      // inner / outer circle radii   (cell-level pruning)
     float yaw_min, yaw_max;  // coxa yaw limits, radians     (cell-level pruning)
-    float pad[2];
+    float az_cos, az_sin;    // sincosf(-body_angle) as the reference evaluates it (knife-edge recheck)
 };
 
-LRM_HD void make_reach_plan(const LegPlan& L, float yaw_min, float yaw_max, ReachPlan* R) {
+LRM_HD void make_reach_plan(const LegPlan& L, float yaw_min, float yaw_max, float az_cos, float az_sin,
+                            ReachPlan* R) {
     for (int s = 0; s < 4; s++)
         for (int j = 0; j < 3; j++) {
             const float* o = L.sector[s].slot[j];
@@ -234,15 +235,83 @@ LRM_HD void make_reach_plan(const LegPlan& L, float yaw_min, float yaw_max, Reac
     R->inner_sgn = L.inner.sgn, R->inner_thr_s = L.inner.thr_s;
     R->r_min = L.inner.r, R->r_max = L.outer.r;
     R->yaw_min = yaw_min, R->yaw_max = yaw_max;
-    R->pad[0] = R->pad[1] = 0.f;
+    R->az_cos = az_cos, R->az_sin = az_sin;
+}
+
+// ---- the gravity-side test on its knife edge -----------------------------------------------------
+// reachable_rotate_leg rejects a foothold when x < 0 for
+//     x = Rz(-body_angle) * qtRotate(qtInvert(q), qtRotate(q, t) - qtRotate(q, b))
+// (several_leg.cu:48-62, rotateData :401-411), i.e. for the WORLD offset t - b up to the rounding
+// of three rotations.  When the pose lattice coincides with the map lattice whole columns of
+// footholds have t.x - b.x = 0 exactly and the reference's decision is that rounding.  The search
+// evaluates the test with one fused dot product; within kGravBand of zero it re-evaluates it
+// with the reference's own sequence of individually rounded operations, so that even those
+// decisions are the reference's.
+struct GravExact {
+    float rq[9];   // coefficient sums of qtRotate(q, .), unified_math_cuda.cu.h:13-27, in its order
+    float rqi[9];  // the same for qtInvert(q)
+};
+LRM_HD float nf_mul(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);  // never contracted into an FMA
+#else
+    return a * b;            // host emulation is built with -ffp-contract=off
+#endif
+}
+LRM_HD float nf_add(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+// 2.0f * ((c0*v.x + c1*v.y) + c2*v.z) + w
+LRM_HD float ref_rot_row(const float* c, float x, float y, float z, float w) {
+    return nf_add(nf_mul(2.0f, nf_add(nf_add(nf_mul(c[0], x), nf_mul(c[1], y)), nf_mul(c[2], z))), w);
+}
+LRM_HD void make_grav_exact(const float q[4], GravExact* G) {
+    auto fill = [](float x, float y, float z, float w, float* c) {
+        const float t2 = x * y, t3 = x * z, t4 = x * w, t5 = -y * y, t6 = y * z, t7 = y * w, t8 = -z * z,
+                    t9 = z * w, t10 = -w * w;
+        c[0] = t8 + t10, c[1] = t6 - t4, c[2] = t3 + t7;
+        c[3] = t4 + t6, c[4] = t5 + t10, c[5] = t9 - t2;
+        c[6] = t7 - t3, c[7] = t2 + t9, c[8] = t5 + t8;
+    };
+    fill(q[0], q[1], q[2], q[3], G->rq);
+    const float n = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];  // qtInvert, :29-34
+    fill(q[0] / n, -q[1] / n, -q[2] / n, -q[3] / n, G->rqi);
+}
+struct GravCtx {
+    const GravExact* G;
+    float bx, by, bz;  // body position, world frame
+    float tx, ty, tz;  // foothold, world frame
+};
+constexpr float kGravBand = 0.02f, kGravBandRel = 4.0e-6f;
+LRM_HD bool grav_rejects_exact(const ReachPlan& L, const GravCtx& c) {
+    const float* q = c.G->rq;
+    const float Bx = ref_rot_row(q, c.bx, c.by, c.bz, c.bx), By = ref_rot_row(q + 3, c.bx, c.by, c.bz, c.by),
+                Bz = ref_rot_row(q + 6, c.bx, c.by, c.bz, c.bz);
+    const float Tx = ref_rot_row(q, c.tx, c.ty, c.tz, c.tx), Ty = ref_rot_row(q + 3, c.tx, c.ty, c.tz, c.ty),
+                Tz = ref_rot_row(q + 6, c.tx, c.ty, c.tz, c.tz);
+    const float vx = nf_add(Tx, -Bx), vy = nf_add(Ty, -By), vz = nf_add(Tz, -Bz);
+    const float* qi = c.G->rqi;
+    const float gx = ref_rot_row(qi, vx, vy, vz, vx), gy = ref_rot_row(qi + 3, vx, vy, vz, vy);
+    // rotateInPlace(gravity_down, -body_angle): x * cos - y * sin
+    return nf_add(nf_mul(gx, L.az_cos), -nf_mul(gy, L.az_sin)) < 0.f;
 }
 
 // reachable_rotate_leg for a foothold offset (vx, vy, vz) in the orientation frame:
 // gravity-side test, leg frame, reachability_circles.  Same arithmetic as
 // to_coxa_frame + reach_coxa_frame on the full plan.
-LRM_HD bool reach_offset(const ReachPlan& L, float vx, float vy, float vz) {
+LRM_HD bool reach_offset(const ReachPlan& L, float vx, float vy, float vz, const GravCtx* ctx = nullptr) {
     const float g = fmaf(L.grav[0], vx, fmaf(L.grav[1], vy, L.grav[2] * vz));
-    if (g < 0.f) return false;
+    if (ctx != nullptr &&
+        fabsf(g) < fmaf(kGravBandRel, fabsf(ctx->bx) + fabsf(ctx->by) + fabsf(ctx->bz) + fabsf(ctx->tx) +
+                                          fabsf(ctx->ty) + fabsf(ctx->tz), kGravBand)) {
+        if (grav_rejects_exact(L, *ctx)) return false;
+    } else if (g < 0.f) {
+        return false;
+    }
     const float px = fmaf(L.M[0], vx, fmaf(L.M[1], vy, fmaf(L.M[2], vz, L.t[0])));
     const float py = fmaf(L.M[3], vx, fmaf(L.M[4], vy, fmaf(L.M[5], vz, L.t[1])));
     const float pz = fmaf(L.M[6], vx, fmaf(L.M[7], vy, fmaf(L.M[8], vz, L.t[2])));
@@ -318,9 +387,17 @@ constexpr float kAtlasNeedFactor = 0.70711f * 1.02f + 0.012f;
 constexpr float kAtlasNeedSlack = 2.0e-3f;
 
 struct PlaneProbe {
-    int label;     // bits 0-6 as above (never has bit 7)
-    float safety;  // every decision keeps its sign within this distance of the probed point
+    int label;           // bits 0-6 as above (never has bit 7)
+    float safety;        // every decision keeps its sign within this distance of the probed point
+    float valid_safety;  // the same for "P is valid" alone (sector tests + circle margins)
 };
+// cell byte for a cell that is impure for the distance but whose validity is certified: 1 + valid
+constexpr unsigned kAtlasValidOnly = 1u;
+LRM_HD unsigned atlas_cell_byte(const PlaneProbe& pr, float need) {
+    if (pr.safety > need) return kAtlasPure | (unsigned)pr.label;
+    if (pr.valid_safety > need) return kAtlasValidOnly + ((pr.label & 0x40) ? 1u : 0u);
+    return 0u;
+}
 
 // signed distance of (X, Y) to the decision boundary of an AngleTest, conservatively
 LRM_HD float angle_margin(const AngleTest& t, float X, float Y) {
@@ -387,6 +464,7 @@ LRM_HD PlaneProbe plane_probe(const LegPlan& L, const SectorTable& tab, float X,
         }
     }
     safety = fminf(safety, valid ? valid_margin : invalid_margin);
+    const float valid_safety = safety;  // sector tests, circle centres, validity: all reach needs
     // winner
     int win = kAtlasNone;
     float best = 3.0e38f;
@@ -415,6 +493,7 @@ LRM_HD PlaneProbe plane_probe(const LegPlan& L, const SectorTable& tab, float X,
     PlaneProbe out;
     out.label = (valid ? 0x40 : 0) | (s << 4) | win;
     out.safety = safety;
+    out.valid_safety = valid_safety;
     return out;
 }
 
@@ -489,6 +568,26 @@ LRM_HD bool reach_coxa_frame(const LegPlan& L, const SectorTable& tab, const Cox
     const float rho2 = fmaf(p.x, p.x, p.y * p.y);
     const float rho = rho2 > 0.f ? rho2 * fast_rsqrt(rho2) : 0.f;
     const float X = (flip ? -rho : rho) - L.coxa_length;
+    return plane_reach(L, tab, X, p.z);
+}
+
+// reachability_circles through the plane atlas: the coxa yaw tests are evaluated as always, the
+// four circle tests of eval_plane_circles<REACH> come from the certified valid bit of the cell
+// holding the plane point; cells certified neither for the distance nor for validity alone
+// (a band around the reachability edge and the sector lines) take the explicit tests.
+template <bool TEX>
+LRM_HD bool reach_coxa_frame_atlas(const LegPlan& L, const SectorTable& tab, const AtlasView& A,
+                                   const CoxaPoint p) {
+    const bool flip = f2i(p.x) < 0;  // signbit: mirrored through the coxa axis
+    const float xf = flip ? -p.x : p.x;
+    const float yf = flip ? -p.y : p.y;
+    if (angle_gt(L.over, xf, yf) | angle_gt(L.under, xf, -yf)) return false;  // outside the yaw limits
+    const float rho2 = fmaf(p.x, p.x, p.y * p.y);
+    const float rho = rho2 > 0.f ? rho2 * fast_rsqrt(rho2) : 0.f;
+    const float X = (flip ? -rho : rho) - L.coxa_length;
+    const unsigned cell = atlas_fetch<TEX>(A, fmaf(X, A.inv_cell, A.ox), fmaf(p.z, A.inv_cell, A.oy));
+    if (cell & kAtlasPure) return (cell & 0x40u) != 0;
+    if (cell != 0u) return cell != kAtlasValidOnly;
     return plane_reach(L, tab, X, p.z);
 }
 

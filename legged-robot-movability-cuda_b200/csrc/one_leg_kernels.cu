@@ -51,7 +51,7 @@ struct alignas(128) StreamSmem {
     float in[kStages][3 * kTile];
     uint8_t flag[2][kTile];
     alignas(16) SectorTable table;
-    alignas(16) typename std::conditional<FAST, FastSmem, NoFastSmem>::type fast;
+    alignas(16) typename std::conditional<(FAST && (MODE & kModeDist) != 0), FastSmem, NoFastSmem>::type fast;
     alignas(8) uint64_t full[kStages];
 };
 
@@ -154,9 +154,11 @@ __global__ void __launch_bounds__(kThreads)
     const size_t n_bulk = n & ~size_t(15);  // points that move through the bulk engine
     const size_t n_tiles = (n_bulk + kTile - 1) / kTile;
     constexpr bool kVec = (MODE & kModeDist) != 0;
+    constexpr bool kRedo = FAST && kVec;       // distance fast path: certified tables + deferred redo
+    constexpr bool kReachAtlas = FAST && !kVec;  // reach-only: valid bit of the atlas cell
 
     fill_sector_table(L, &S.table, tid, kThreads);
-    if constexpr (FAST) {
+    if constexpr (kRedo) {
         fill_winner_table(L, &S.fast.winners, tid, kThreads);
         for (int i = tid; i < kYawPairs * (int)(sizeof(YawPair) / 4); i += kThreads)
             reinterpret_cast<float*>(S.fast.ypair)[i] = reinterpret_cast<const float*>(FT.pair)[i];
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(kThreads)
     }
 
     FastView fview{nullptr, nullptr};
-    if constexpr (FAST) fview = FastView{S.fast.ypair, S.fast.ycode};
+    if constexpr (kRedo) fview = FastView{S.fast.ypair, S.fast.ycode};
     uint32_t it = 0;
     // ring bookkeeping, identical in every thread: entries appended before this iteration (base),
     // before the previous one (elig: their tiles' stores have completed), and redone so far (head)
@@ -218,7 +220,18 @@ __global__ void __launch_bounds__(kThreads)
         float* in = S.in[stage];
         float* vec = in;  // in place (unused in reach-only mode)
         uint8_t* flag = S.flag[ob];
-        if constexpr (FAST) {
+        if constexpr (kReachAtlas) {
+#pragma unroll 2
+            for (int i = tid; i < (int)cnt; i += kThreads) {
+                float x, y, z;
+                if (SOA) {
+                    x = in[i], y = in[kTile + i], z = in[2 * kTile + i];
+                } else {
+                    x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+                }
+                flag[i] = reach_coxa_frame_atlas<TEX>(L, S.table, atlas, to_coxa_frame(L, x, y, z)) ? 1 : 0;
+            }
+        } else if constexpr (kRedo) {
             const int rot_prev = rot == 0 ? 2 : rot - 1;
             q_elig = q_base;
             q_base += S.fast.qcnt[rot_prev];  // final since the previous tile barrier
@@ -243,7 +256,7 @@ __global__ void __launch_bounds__(kThreads)
         if (tid == 0) {
             // FAST: every committed store has COMPLETED (parked points of those tiles may be redone);
             // otherwise it only has to have drained its shared-memory buffer
-            if constexpr (FAST) {
+            if constexpr (kRedo) {
                 bulk::wait_group<0>();
                 S.fast.qcnt[rot == 2 ? 0 : rot + 1] = 0;  // next iteration's counter (last read two barriers ago)
             } else {
@@ -272,7 +285,7 @@ __global__ void __launch_bounds__(kThreads)
         rot = rot == 2 ? 0 : rot + 1;
     }
     if (tid == 0) bulk::wait_group<0>();
-    if constexpr (FAST) {
+    if constexpr (kRedo) {
         // drain the ring: every store has completed, every entry is final after this barrier
         __syncthreads();
         const uint32_t total = q_base + (it ? S.fast.qcnt[rot == 0 ? 2 : rot - 1] : 0u);
@@ -464,16 +477,29 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
                           cudaStream_t stream, size_t n_call = 0) {
     AtlasView none{};
     static const FastTables no_tables{};
-    if (MODE == kModeReach)
+    const bool big = (n_call > n ? n_call : n) >= kAtlasMinPoints;
+    if (MODE == kModeReach) {
+        // large reach-only sweeps read the valid bit of the plane atlas instead of testing circles
+        if (big && !plan.generic) {
+            AtlasView atlas;
+            cudaError_t e = get_plane_atlas(plan, stream, &atlas, nullptr);
+            if (e != cudaSuccess) return e;
+            if (atlas_through_texture())
+                return launch_stream_impl<MODE, SOA, false, MODE == kModeReach, true>(
+                    plan, no_tables, atlas, ix, iy, iz, ox, oy, oz, flag, n, stream);
+            return launch_stream_impl<MODE, SOA, false, MODE == kModeReach, false>(
+                plan, no_tables, atlas, ix, iy, iz, ox, oy, oz, flag, n, stream);
+        }
         return launch_stream_impl<MODE, SOA, false, false, false>(plan, no_tables, none, ix, iy, iz, ox, oy,
                                                                   oz, flag, n, stream);
+    }
     constexpr bool kDist = MODE != kModeReach;
     if (plan.generic)
         return launch_stream_impl<MODE, SOA, kDist, false, false>(plan, no_tables, none, ix, iy, iz, ox, oy,
                                                                   oz, flag, n, stream);
     // the atlas pays for itself (16 Mi probes) only on large sweeps, or once it is cached; ring
     // entries hold a 22-bit per-CTA iteration count (n / (kTile * grid) is far below that)
-    if ((n_call > n ? n_call : n) >= kAtlasMinPoints && n / kTile / (size_t)sm_count() < (size_t(1) << 21)) {
+    if (big && n / kTile / (size_t)sm_count() < (size_t(1) << 21)) {
         AtlasView atlas;
         FastTables ft;
         cudaError_t e = get_plane_atlas(plan, stream, &atlas, &ft);
@@ -515,7 +541,7 @@ cudaError_t launch_one_leg_aos(int mode, const LegPlan& plan, const float* xyz, 
     switch (mode) {
         case kModeReach:
             return bulk_ok ? launch_stream<kModeReach, false>(plan, xyz, nullptr, nullptr, nullptr,
-                                                              nullptr, nullptr, flag, n, stream)
+                                                              nullptr, nullptr, flag, n, stream, n_call)
                            : launch_plain<kModeReach>(plan, xyz, nullptr, flag, n, stream);
         case kModeDist:
             return bulk_ok ? launch_stream<kModeDist, false>(plan, xyz, nullptr, nullptr, out_vec,

@@ -36,7 +36,7 @@ __global__ void atlas_build_kernel(const __grid_constant__ LegPlan L, unsigned c
         const int ix = (int)(i % dim), iy = (int)(i / dim);
         const float X = origin + ((float)ix + 0.5f) * cell, Y = origin + ((float)iy + 0.5f) * cell;
         const PlaneProbe pr = plane_probe(L, table, X, Y);
-        const unsigned char v = pr.safety > need ? (unsigned char)(kAtlasPure | (unsigned)pr.label) : 0;
+        const unsigned char v = (unsigned char)atlas_cell_byte(pr, need);
         blocked[atlas_index(dim, ix, iy)] = v;
         linear[i] = v;
     }

@@ -99,6 +99,7 @@ struct OrientConsts {
     float radius_in, plus_in, minus_in, radius_out;  // cull cylinders (:505-520)
     float r_near, r_hit;  // world-frame search radii of the two cylinders
     float pad;
+    GravExact grav;       // the reference's own rotation sequence, for gravity-plane knife edges
 };
 
 struct SearchParams {
@@ -242,7 +243,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
                             // reachable_rotate_leg (several_leg.cu:48-67): offset in the
                             // orientation frame, gravity-side test, leg frame, reachability_circles
                             const float3 T = rotate(O.R, t.x, t.y, t.z);
-                            const bool r = ok && t.w != 0.f && reach_offset(L, T.x - B.x, T.y - B.y, T.z - B.z);
+                            const GravCtx gc{&O.grav, bx, by, bz, t.x, t.y, t.z};
+                            const bool r = ok && t.w != 0.f && reach_offset(L, T.x - B.x, T.y - B.y, T.z - B.z, &gc);
                             return __any_sync(0xffffffffu, r) != 0;
                         });
                 }
@@ -282,7 +284,9 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
         for (int l = 0; l < p.nlegs; l++) {
             LegPlan full;
             build_leg_plan_rotated_limits(p.legs[l], q, &full);
-            make_reach_plan(full, p.legs[l].min_angle_coxa, p.legs[l].max_angle_coxa,
+            float az_s, az_c;
+            sincosf(-p.legs[l].body_angle, &az_s, &az_c);  // rotateInPlace, several_leg.cu:26-32
+            make_reach_plan(full, p.legs[l].min_angle_coxa, p.legs[l].max_angle_coxa, az_c, az_s,
                             &plans[(size_t)o * p.nlegs + l]);
             const lrm_leg_t& d = p.legs[l];
             r_leg = std::fmax(r_leg, std::fabs(d.body) + std::fabs(d.coxa_length) +
@@ -304,6 +308,7 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
         O.r_near = std::sqrt(O.radius_in * O.radius_in + zin * zin) + 1.f;
         O.r_hit = std::sqrt(O.radius_out * O.radius_out + 250.f * 250.f) + 1.f;
         O.pad = 0.f;
+        make_grav_exact(q, &O.grav);
     }
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -82,7 +82,7 @@ void emu_dist_generic(const float* xyz, size_t n, const lrm_leg_t* leg, const fl
 // of points that fell back; *pure_cells / *pure_bins report the certified share of both tables.
 size_t emu_dist_atlas(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, int dim,
                       float cell, float* out_vec, uint8_t* out_flag, uint8_t* out_reach,
-                      size_t* pure_cells, size_t* pure_bins) {
+                      size_t* pure_cells, size_t* pure_bins, uint8_t* out_reach_atlas) {
     lrm::LegPlan L;
     lrm::build_leg_plan(*leg, quat, &L);
     lrm::SectorTable tab;
@@ -104,7 +104,7 @@ size_t emu_dist_atlas(const float* xyz, size_t n, const lrm_leg_t* leg, const fl
             const float X = origin + ((float)ix + 0.5f) * cell, Y = origin + ((float)iy + 0.5f) * cell;
             const lrm::PlaneProbe pr = lrm::plane_probe(L, tab, X, Y);
             const bool ok = pr.safety > need;
-            cells[lrm::atlas_index(dim, ix, iy)] = (unsigned char)(ok ? (lrm::kAtlasPure | (unsigned)pr.label) : 0);
+            cells[lrm::atlas_index(dim, ix, iy)] = (unsigned char)lrm::atlas_cell_byte(pr, need);
             pure += ok;
         }
     if (pure_cells) *pure_cells = pure;
@@ -113,6 +113,7 @@ size_t emu_dist_atlas(const float* xyz, size_t n, const lrm_leg_t* leg, const fl
     size_t fallback = 0;
     for (size_t i = 0; i < n; i++) {
         const lrm::CoxaPoint p = lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        if (out_reach_atlas) out_reach_atlas[i] = lrm::reach_coxa_frame_atlas<false>(L, tab, A, p) ? 1 : 0;
         lrm::DistResult r;
         if (!lrm::dist_fast<false>(L, F, A, win, p, &r)) {
             r = lrm::dist_coxa_frame<false>(L, tab, p);
@@ -132,7 +133,7 @@ void emu_standability(const float* bodies, size_t nb, const float* map, size_t n
                       const lrm_leg_t* legs, int nlegs, const float* quats, int nq, uint8_t* out) {
     const float pi = 3.14159265358979323846264338327950288419716939937510582097f;
     std::vector<lrm::ReachPlan> plans((size_t)nq * nlegs);
-    struct OC { float R[9], radius_in, plus_in, minus_in, radius_out; };
+    struct OC { float R[9], radius_in, plus_in, minus_in, radius_out; lrm::GravExact grav; };
     std::vector<OC> oc(nq);
     for (int o = 0; o < nq; o++) {
         const float* q = quats + 4 * o;
@@ -143,9 +144,12 @@ void emu_standability(const float* bodies, size_t nb, const float* map, size_t n
         for (int l = 0; l < nlegs; l++) {
             lrm::LegPlan full;
             lrm::build_leg_plan_rotated_limits(legs[l], q, &full);
-            lrm::make_reach_plan(full, legs[l].min_angle_coxa, legs[l].max_angle_coxa,
+            float az_s, az_c;
+            sincosf(-legs[l].body_angle, &az_s, &az_c);
+            lrm::make_reach_plan(full, legs[l].min_angle_coxa, legs[l].max_angle_coxa, az_c, az_s,
                                  &plans[(size_t)o * nlegs + l]);
         }
+        lrm::make_grav_exact(q, &oc[o].grav);
         lrm_leg_t d = legs[0];
         const float pitch = lrm::quat_pitch_for_leg(q, d.body_angle);
         d.tibia_absolute_pos -= pitch, d.tibia_absolute_neg -= pitch;
@@ -186,7 +190,9 @@ void emu_standability(const float* bodies, size_t nb, const float* map, size_t n
                 for (size_t t = 0; t < nt && !found; t++) {
                     const float vx = T[3 * t] - B[0], vy = T[3 * t + 1] - B[1], vz = T[3 * t + 2] - B[2];
                     if (fabsf(vx) > 520.f || fabsf(vy) > 520.f) continue;
-                    if (lrm::reach_offset(L, vx, vy, vz)) found = true;
+                    const lrm::GravCtx gc{&oc[o].grav, bodies[3 * b], bodies[3 * b + 1], bodies[3 * b + 2],
+                                          map[3 * t], map[3 * t + 1], map[3 * t + 2]};
+                    if (lrm::reach_offset(L, vx, vy, vz, &gc)) found = true;
                 }
                 all = found;
             }
@@ -202,7 +208,9 @@ void emu_reach_offset(const float* offsets, size_t n, const lrm_leg_t* leg, cons
     lrm::LegPlan full;
     lrm::build_leg_plan_rotated_limits(*leg, quat, &full);
     lrm::ReachPlan L;
-    lrm::make_reach_plan(full, leg->min_angle_coxa, leg->max_angle_coxa, &L);
+    float az_s, az_c;
+    sincosf(-leg->body_angle, &az_s, &az_c);
+    lrm::make_reach_plan(full, leg->min_angle_coxa, leg->max_angle_coxa, az_c, az_s, &L);
     for (size_t i = 0; i < n; i++) {
         const float vx = offsets[3 * i], vy = offsets[3 * i + 1], vz = offsets[3 * i + 2];
         out_reach[i] = lrm::reach_offset(L, vx, vy, vz) ? 1 : 0;

@@ -126,7 +126,7 @@ def test_fast_path_never_changes_a_result(emu, port):
     The cloud includes rings of points straddling every yaw decision (limits, limits +- pi/2, the
     +-pi seam, the x axis) at several radii."""
     vp, sz = ctypes.c_void_p, ctypes.c_size_t
-    emu.emu_dist_atlas.argtypes = [vp, sz, vp, vp, ctypes.c_int, ctypes.c_float, vp, vp, vp, vp, vp]
+    emu.emu_dist_atlas.argtypes = [vp, sz, vp, vp, ctypes.c_int, ctypes.c_float, vp, vp, vp, vp, vp, vp]
     emu.emu_dist_atlas.restype = ctypes.c_size_t
     rng = np.random.default_rng(31)
     cloud = np.concatenate([rng.uniform([-100, -400, -500], [600, 400, 200], (60000, 3)),
@@ -147,15 +147,17 @@ def test_fast_path_never_changes_a_result(emu, port):
             cx, cy = np.float32(leg[1]) * np.cos(az), np.float32(leg[1]) * np.sin(az)
             rings.append(np.stack([cx + rad * np.cos(near), cy + rad * np.sin(near), np.full_like(near, z)], 1))
         pts = np.ascontiguousarray(np.concatenate([cloud] + rings), np.float32)
-        _, base, bf, br = run_emu(emu, pts, leg, q)
+        r0, base, bf, br = run_emu(emu, pts, leg, q)
         out = np.zeros_like(pts)
         fl = np.zeros(len(pts), np.uint8)
         rf = np.zeros(len(pts), np.uint8)
+        ra = np.zeros(len(pts), np.uint8)
         pure, bins = ctypes.c_size_t(0), ctypes.c_size_t(0)
         fb = emu.emu_dist_atlas(pts.ctypes.data, len(pts), leg.ctypes.data, q.ctypes.data, 1024, 2.0,
                                 out.ctypes.data, fl.ctypes.data, rf.ctypes.data, ctypes.byref(pure),
-                                ctypes.byref(bins))
+                                ctypes.byref(bins), ra.ctypes.data)
         assert np.array_equal(fl, bf) and np.array_equal(rf, br)
+        assert np.array_equal(ra, r0)   # reach-only sweep through the atlas' valid bit
         assert np.abs(out - base).max() < 1e-3, float(np.abs(out - base).max())
         assert pure.value > 0.85 * 1024 * 1024 and fb < 0.35 * len(pts), (pure.value, fb)
         assert bins.value > 0.95 * 1025, bins.value

@@ -217,3 +217,69 @@ def test_kernel_ms_is_reported(lrm):
     pts = torch.rand((1 << 20, 3), device="cuda") * 600
     out, ms = lrm.reachability(pts, lrm.get_M2_leg(), timing=True)
     assert 0 < ms < 50
+
+
+# ---- the fast path (certified tables + deferred redo) only runs on sweeps of >= 4 Mi points -------
+def _sample_check(lrm, oracle, dev_pts, leg, q, label, n_sample=250_000, seed=0):
+    """Fused + stand-alone distance on the whole device array, oracle on a random sample."""
+    n = dev_pts.shape[0]
+    la = leg.as_array()
+    fr, vec = lrm.reach_dist(dev_pts, leg, q)
+    d, f = lrm.distance(dev_pts, leg, q)
+    assert torch.equal(vec, d), label                       # fused == separate, bit for bit
+    r = lrm.reachability(dev_pts, leg, q)
+    assert int((fr != r).sum().item()) <= n // 1_000_000 + 2, label
+    idx = torch.from_numpy(np.random.default_rng(seed).choice(n, size=min(n_sample, n), replace=False)).cuda()
+    pts = dev_pts[idx].cpu().numpy()
+    qq = np.array([1, 0, 0, 0], np.float32) if q is None else np.asarray(q, np.float32)
+    want_r = oracle.reach(pts, la, qq, threads=8)
+    want_d, want_f = oracle.dist(pts, la, qq, threads=8)
+    rep = parity.flag_report(pts, fr[idx].cpu().numpy(), want_r, lambda p: oracle.reach(p, la, qq, threads=8))
+    assert rep["unexplained"] == 0 and rep["mismatch"] <= max(3, len(pts) // 20000), (label, rep)
+    rep = parity.flag_report(pts, f[idx].cpu().numpy(), want_f, lambda p: oracle.dist(p, la, qq, threads=8)[1])
+    assert rep["unexplained"] == 0, (label, rep)
+    slack = abs(float((qq.astype(np.float64) ** 2).sum()) - 1.0)
+    rep = parity.dist_report(pts, vec[idx].cpu().numpy(), want_d, lambda p: oracle.dist(p, la, qq, threads=8)[0],
+                             frame_slack=slack)
+    assert rep["unexplained"] == 0 and rep["over_tol"] <= max(3, len(pts) // 2000), (label, rep)
+    return vec, fr
+
+
+def test_fast_path_parity_on_large_sweeps(lrm, oracle):
+    """6 Mi-point clouds (bench box + far field), both robots, identity and tilted orientations."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 6 * (1 << 20) + 37
+    lo = torch.tensor([-100.0, -400.0, -500.0], device="cuda")
+    ext = torch.tensor([700.0, 800.0, 700.0], device="cuda")
+    pts = torch.rand((n, 3), device="cuda", generator=g) * ext + lo
+    pts[: n // 4] = torch.rand((n // 4, 3), device="cuda", generator=g) * 1800.0 - 900.0
+    for robot, az, q in ((1, 0.0, None), (0, 2.0, oracle_quat(9)), (1, 5.5, oracle_quat(4))):
+        _sample_check(lrm, oracle, pts, lrm.get_leg(robot, az), q, f"fast robot{robot} az{az}")
+
+
+def test_fast_path_with_every_point_parked(lrm, oracle):
+    """Points on / next to the coxa axis and on the yaw seam cannot be certified: the whole sweep
+    goes through the deferred redo (ring wrap-around, partial last block, drain at the end)."""
+    leg = lrm.get_M2_leg(0.0)
+    n = 5 * (1 << 20) + 5
+    g = torch.Generator(device="cuda").manual_seed(9)
+    t = torch.rand(n, device="cuda", generator=g) * 900.0 - 450.0
+    # the coxa axis in the world frame (x' = 0 after place_over_coxa, one_leg.cu:9-24):
+    # through (body, 0, 0) along (-sin pitch, 0, cos pitch)
+    c, s = float(np.cos(leg.coxa_pitch)), float(np.sin(leg.coxa_pitch))
+    pts = torch.stack([leg.body - t * s, torch.zeros_like(t), t * c], 1).contiguous()
+    pts[n // 2:, 1] = 0.0
+    pts[n // 2:, 0] -= torch.rand(n - n // 2, device="cuda", generator=g) * 300.0   # y = +0, behind: the +-pi seam
+    vec, fr = _sample_check(lrm, oracle, pts, leg, None, "all parked", n_sample=100_000)
+    assert bool(torch.isfinite(vec).all())
+
+
+def test_fast_path_soa_matches_aos_at_scale(lrm):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    n = 5 * (1 << 20)
+    pts = torch.rand((n, 3), device="cuda", generator=g) * 900.0 - 300.0
+    leg = lrm.get_M2_leg(0.3)
+    fr, vec = lrm.reach_dist(pts, leg)
+    planes = [pts[:, k].contiguous() for k in range(3)]
+    f2, dx, dy, dz = lrm.reach_dist_soa(*planes, leg)
+    assert torch.equal(f2, fr) and torch.equal(torch.stack([dx, dy, dz], 1), vec)

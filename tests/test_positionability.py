@@ -87,31 +87,59 @@ def test_gpu_matches_oracle_perlin_terrain(lrm, port):
     assert rep["flag_mismatch"] <= 3 and rep["orientation_mismatch"] <= 6, rep
 
 
+def _aligned_scene():
+    """before.py:24-35 starts the pose lattice on the map's own first column, so whole columns of
+    footholds have an offset with x == 0 (or y == 0) exactly: they lie ON the gravity-side plane of
+    a leg (several_leg.cu:58-62, `gravity_down.x < 0`), where the reference's outcome is the
+    rounding of its rotate / subtract / un-rotate sequence."""
+    terr = terrain.sine_terrain(128, 2400.0, 100.0)
+    bodies = terrain.body_lattice(terr, 24, 24, 12)
+    lo, hi = terr.min(0), terr.max(0)
+    edge = (np.abs(bodies[:, 0] - lo[0]) < 1) | (np.abs(bodies[:, 0] - hi[0]) < 1) | \
+           (np.abs(bodies[:, 1] - lo[1]) < 1) | (np.abs(bodies[:, 1] - hi[1]) < 1)
+    return terr, bodies, edge
+
+
+def test_gravity_plane_knife_edge_is_the_references_own_rounding(port):
+    """CPU: the search's per-pose logic (tests/emu, same header as the kernel) re-evaluates the
+    gravity-side test with the reference's own operation sequence when it is within a hair of
+    zero (leg_math.cuh grav_rejects_exact); on lattice-aligned edge poses — where a fused dot
+    product alone disagreed with the oracle on ~10 % of the poses — it must now agree exactly."""
+    import ctypes
+    from tests.emu.build_emu import build
+    E = ctypes.CDLL(build())
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    E.emu_standability.argtypes = [vp, sz, vp, sz, vp, ctypes.c_int, vp, ctypes.c_int, vp]
+    terr, bodies, edge = _aligned_scene()
+    B = np.ascontiguousarray(np.concatenate([bodies[edge][::3], bodies[~edge][::29]]))
+    legs = np.stack(m2_legs(port, 4)).astype(np.float32)
+    quats = np.ascontiguousarray(port.full_struct_orientations(), np.float32)
+    got = np.zeros(len(B), np.uint8)
+    E.emu_standability(B.ctypes.data, len(B), terr.ctypes.data, len(terr), legs.ctypes.data, 4,
+                       quats.ctypes.data, len(quats), got.ctypes.data)
+    want = port.standability(B, terr, [l for l in legs], quats, pre_cull=False, threads=8)
+    assert (want != 0).sum() > 50
+    assert np.array_equal(got, want), int((got != want).sum())
+
+
 @pytest.mark.gpu
-def test_lattice_aligned_poses_are_the_only_degenerate_ones(lrm, port):
-    """before.py:24-35 starts the pose lattice on the map's own first column, so a whole column of
-    footholds has an offset with x == 0 exactly: it lies ON the gravity-side plane of the legs at
-    azimuth 0 and pi (several_leg.cu:58-62, `gravity_down.x < 0`), where the reference's own
-    outcome is decided by the rounding of a rotate / un-rotate round trip.  Every mismatching pose
-    must be of that kind (or explained by a 1e-3 mm displacement), and they must stay rare."""
-    terr = terrain.perlin_terrain(128)
-    bodies = terrain.body_lattice(terr, 24, 48, 20)
+def test_lattice_aligned_poses_match_exactly(lrm, port):
+    """GPU: the same scene through lrm_positionability, with and without the constructor culls
+    (the shape tools/vs_refgpu.py runs against the reference's own robot_full_struct)."""
+    terr, bodies, edge = _aligned_scene()
     legs_o = m2_legs(port, 4)
     legs = [lrm.LegDimensions.from_array(l) for l in legs_o]
     quats = lrm.full_struct_orientations()
-    want = port.standability(bodies, terr, legs_o, quats, threads=8)
-    got = lrm.positionability(torch.from_numpy(bodies).cuda(), torch.from_numpy(terr).cuda(), legs, quats)
-    got = got.cpu().numpy()
-    bad = np.nonzero(got != want)[0]
-    assert len(bad) <= len(bodies) // 50
-    map_x, map_y = np.unique(terr[:, 0]), np.unique(terr[:, 1])
-    on_col = np.abs(bodies[bad, 0][:, None] - map_x[None, :]).min(axis=1) < 1e-3
-    on_row = np.abs(bodies[bad, 1][:, None] - map_y[None, :]).min(axis=1) < 1e-3
-    rest = bad[~(on_col | on_row)]
-    if len(rest):
-        rep = parity.pose_report(bodies[rest], got[rest], want[rest],
-                                 lambda p: port.standability(p, terr, legs_o, quats, threads=8))
-        assert rep["unexplained"] == 0, rep
+    for pre_cull in (False, True):
+        want = port.standability(bodies, terr, legs_o, quats, pre_cull=pre_cull, threads=8)
+        got = lrm.positionability(torch.from_numpy(bodies).cuda(), torch.from_numpy(terr).cuda(), legs, quats,
+                                  pre_cull=pre_cull).cpu().numpy()
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) <= 2, (pre_cull, len(bad), int(edge[bad].sum()))
+        if len(bad) and not pre_cull:
+            rep = parity.pose_report(bodies[bad], got[bad], want[bad],
+                                     lambda p: port.standability(p, terr, legs_o, quats, threads=8))
+            assert rep["unexplained"] == 0, rep
 
 
 @pytest.mark.gpu

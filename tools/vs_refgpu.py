@@ -4,7 +4,9 @@ the same B200 next to this repo's kernels.
 
     python tools/vs_refgpu.py [--points 20000000] [--json gpurun_out/vs_refgpu.json]
 
-Sections (each guarded: a failing section is reported, not fatal):
+Sections (each guarded: a Python-level failure is reported, not fatal; robot_full_struct runs first, in
+a context no other allocator has touched — with torch's caching allocator active before it, the
+reference's pipeline died with an illegal address inside thrust::partition):
   one_leg   apply_kernel(reachability_global_kernel / distance_global_kernel)   vs lrm_reach / lrm_dist
   full      robot_full_struct (several_leg.cu:796-877)                          vs lrm_positionability(pre_cull)
             and vs the CPU restatement (oracle_port.c op_standability) -> pins the pipeline logic
@@ -73,62 +75,6 @@ def bench_points(n):
                      lo[2] + iz.astype(np.float32) * step[2]], 1).astype(np.float32)
 
 
-@section("one_leg")
-def _one_leg():
-    g = load_ref()
-    from oracle.oracle import best
-    cpu = best()
-    res = {}
-    n = args.points
-    pts = bench_points(n)
-    for robot, name in ((1, "M2"), (0, "moonbot")):
-        leg = lrm.get_leg(robot, 0.0)
-        la = leg.as_array()
-        r_ref = np.empty(n, np.uint8)
-        d_ref = np.empty((n, 3), np.float32)
-        ms_r = min(g.refgpu_reach(pts.ctypes.data, n, la.ctypes.data, r_ref.ctypes.data) for _ in range(3))
-        ms_d = min(g.refgpu_dist(pts.ctypes.data, n, la.ctypes.data, d_ref.ctypes.data) for _ in range(3))
-        # device-resident, one launch, kernel-only time: what apply_kernel's return value measures
-        import torch
-        d_pts = torch.from_numpy(pts).cuda()
-        r_us, t_r = None, 1e30
-        for _ in range(4):
-            r_us, t = lrm.reachability(d_pts, leg, timing=True)
-            t_r = min(t_r, t)
-        d_us, t_d = None, 1e30
-        for _ in range(4):
-            d_us, _f, t = lrm.distance(d_pts, leg, timing=True)
-            t_d = min(t_d, t)
-        r_us, d_us = r_us.cpu().numpy(), d_us.cpu().numpy()
-        del d_pts
-        flag_diff = np.flatnonzero(r_ref != r_us)
-        err = np.abs(d_ref - d_us).max(axis=1)
-        bad = np.flatnonzero(err > 1e-2)
-        # judge every disagreement against the reference's own CPU path (the parity oracle)
-        sub = np.unique(np.concatenate([flag_diff[:20000], bad[:20000]]))
-        cpu_r = cpu.reach(pts[sub], la, threads=8) if len(sub) else np.zeros(0, np.uint8)
-        cpu_d = cpu.dist(pts[sub], la, threads=8)[0] if len(sub) else np.zeros((0, 3), np.float32)
-        pos = {int(k): j for j, k in enumerate(sub)}
-        fd = [pos[int(k)] for k in flag_diff[:20000]]
-        bd = [pos[int(k)] for k in bad[:20000]]
-        res[name] = {
-            "points": n,
-            "ref_gpu_reach_ms": ms_r, "ref_gpu_dist_ms": ms_d, "b200_reach_ms": t_r, "b200_dist_ms": t_d,
-            "ref_gpu_reach_gpts": n / ms_r / 1e6, "ref_gpu_dist_gpts": n / ms_d / 1e6,
-            "b200_reach_gpts": n / t_r / 1e6, "b200_dist_gpts": n / t_d / 1e6,
-            "speedup_reach": ms_r / t_r, "speedup_dist": ms_d / t_d,
-            "flags_differ_vs_ref_gpu": int(len(flag_diff)),
-            "of_those_b200_equals_ref_cpu": int((cpu_r[fd] == r_us[flag_diff[:20000]]).sum()) if len(fd) else 0,
-            "of_those_ref_gpu_equals_ref_cpu": int((cpu_r[fd] == r_ref[flag_diff[:20000]]).sum()) if len(fd) else 0,
-            "vectors_differ_gt_1e-2mm_vs_ref_gpu": int(len(bad)),
-            "of_those_b200_within_1e-2_of_ref_cpu": int((np.abs(cpu_d[bd] - d_us[bad[:20000]]).max(axis=1) <= 1e-2).sum()) if len(bd) else 0,
-            "of_those_ref_gpu_within_1e-2_of_ref_cpu": int((np.abs(cpu_d[bd] - d_ref[bad[:20000]]).max(axis=1) <= 1e-2).sum()) if len(bd) else 0,
-            "max_abs_vector_diff_mm": float(err.max()), "median_abs_vector_diff_mm": float(np.median(err)),
-            "reachable_ref_gpu": int(r_ref.sum()), "reachable_b200": int(r_us.sum()),
-        }
-    return res
-
-
 def _full_struct_call(libname, bodies, terr, la):
     s = ctypes.CDLL(os.path.join(REF, libname))
     s.refgpu_full_struct.restype = ctypes.c_double
@@ -193,6 +139,62 @@ def _full():
         dump[name + "_oracle_codes"] = want
     if args.json:
         np.savez_compressed(os.path.splitext(args.json)[0] + "_full_dump.npz", columns=np.array(names), **dump)
+    return res
+
+
+@section("one_leg")
+def _one_leg():
+    g = load_ref()
+    from oracle.oracle import best
+    cpu = best()
+    res = {}
+    n = args.points
+    pts = bench_points(n)
+    for robot, name in ((1, "M2"), (0, "moonbot")):
+        leg = lrm.get_leg(robot, 0.0)
+        la = leg.as_array()
+        r_ref = np.empty(n, np.uint8)
+        d_ref = np.empty((n, 3), np.float32)
+        ms_r = min(g.refgpu_reach(pts.ctypes.data, n, la.ctypes.data, r_ref.ctypes.data) for _ in range(3))
+        ms_d = min(g.refgpu_dist(pts.ctypes.data, n, la.ctypes.data, d_ref.ctypes.data) for _ in range(3))
+        # device-resident, one launch, kernel-only time: what apply_kernel's return value measures
+        import torch
+        d_pts = torch.from_numpy(pts).cuda()
+        r_us, t_r = None, 1e30
+        for _ in range(4):
+            r_us, t = lrm.reachability(d_pts, leg, timing=True)
+            t_r = min(t_r, t)
+        d_us, t_d = None, 1e30
+        for _ in range(4):
+            d_us, _f, t = lrm.distance(d_pts, leg, timing=True)
+            t_d = min(t_d, t)
+        r_us, d_us = r_us.cpu().numpy(), d_us.cpu().numpy()
+        del d_pts
+        flag_diff = np.flatnonzero(r_ref != r_us)
+        err = np.abs(d_ref - d_us).max(axis=1)
+        bad = np.flatnonzero(err > 1e-2)
+        # judge every disagreement against the reference's own CPU path (the parity oracle)
+        sub = np.unique(np.concatenate([flag_diff[:20000], bad[:20000]]))
+        cpu_r = cpu.reach(pts[sub], la, threads=8) if len(sub) else np.zeros(0, np.uint8)
+        cpu_d = cpu.dist(pts[sub], la, threads=8)[0] if len(sub) else np.zeros((0, 3), np.float32)
+        pos = {int(k): j for j, k in enumerate(sub)}
+        fd = [pos[int(k)] for k in flag_diff[:20000]]
+        bd = [pos[int(k)] for k in bad[:20000]]
+        res[name] = {
+            "points": n,
+            "ref_gpu_reach_ms": ms_r, "ref_gpu_dist_ms": ms_d, "b200_reach_ms": t_r, "b200_dist_ms": t_d,
+            "ref_gpu_reach_gpts": n / ms_r / 1e6, "ref_gpu_dist_gpts": n / ms_d / 1e6,
+            "b200_reach_gpts": n / t_r / 1e6, "b200_dist_gpts": n / t_d / 1e6,
+            "speedup_reach": ms_r / t_r, "speedup_dist": ms_d / t_d,
+            "flags_differ_vs_ref_gpu": int(len(flag_diff)),
+            "of_those_b200_equals_ref_cpu": int((cpu_r[fd] == r_us[flag_diff[:20000]]).sum()) if len(fd) else 0,
+            "of_those_ref_gpu_equals_ref_cpu": int((cpu_r[fd] == r_ref[flag_diff[:20000]]).sum()) if len(fd) else 0,
+            "vectors_differ_gt_1e-2mm_vs_ref_gpu": int(len(bad)),
+            "of_those_b200_within_1e-2_of_ref_cpu": int((np.abs(cpu_d[bd] - d_us[bad[:20000]]).max(axis=1) <= 1e-2).sum()) if len(bd) else 0,
+            "of_those_ref_gpu_within_1e-2_of_ref_cpu": int((np.abs(cpu_d[bd] - d_ref[bad[:20000]]).max(axis=1) <= 1e-2).sum()) if len(bd) else 0,
+            "max_abs_vector_diff_mm": float(err.max()), "median_abs_vector_diff_mm": float(np.median(err)),
+            "reachable_ref_gpu": int(r_ref.sum()), "reachable_b200": int(r_us.sum()),
+        }
     return res
 
 
