@@ -746,17 +746,22 @@ LRM_HD BranchResult fast_branch(const CoxaPoint p, const YawSol& s, float cs, fl
     return out;
 }
 
-template <bool TEX>
+// Straight-line on purpose (one exit, no early returns): a thread's two consecutive points can
+// then be interleaved by the compiler, so that their texture fetches overlap.  A point the tables
+// cannot certify runs to the end on harmless values and reports false.
+template <bool TEX, bool SKIP_B = true>
 LRM_HD bool dist_fast(const LegPlan& L, const FastView& F, const AtlasView& A, const WinnerTable& W,
                       const CoxaPoint p, DistResult* out) {
     const float rho2 = fmaf(p.x, p.x, p.y * p.y);
-    if (!(rho2 > 1.0e-12f)) return false;  // on the coxa axis (or NaN): full evaluation
-    const float inv_rho = fast_rsqrt(rho2);
+    bool ok = rho2 > 1.0e-12f;  // on the coxa axis (or NaN): full evaluation
+    const float inv_rho = fast_rsqrt(ok ? rho2 : 1.f);
     const float ux = p.x * inv_rho, uy = p.y * inv_rho;
-    const int bin = yaw_bin(ux, uy);
-    if ((unsigned)bin > (unsigned)kYawBins) return false;
-    const unsigned code = F.code[bin];
-    if (code == kYawImpure) return false;
+    int bin = yaw_bin(ux, uy);
+    ok = ok & ((unsigned)bin <= (unsigned)kYawBins);
+    bin = ok ? bin : 0;
+    unsigned code = F.code[bin];
+    ok = ok & (code != kYawImpure);
+    code = ok ? code : 0u;
     const YawPair& pr = F.pair[code];
     const YawSol& sa = pr.a;
     const YawSol& sb = pr.b;
@@ -765,23 +770,32 @@ LRM_HD bool dist_fast(const LegPlan& L, const FastView& F, const AtlasView& A, c
     const float csb = fmaf(sb.k, ux, sb.c_cs), ssb = fmaf(sb.k, uy, sb.c_ss);
     const float Xa = fmaf(p.x, csa, p.y * ssa) - L.coxa_length;
     const float Xb = fmaf(p.x, csb, p.y * ssb) - L.coxa_length;
-    // both cells are requested before either is consumed
+    // both cells are requested before either is consumed; an absent solution reads its cell too
+    // (its plane point is a valid one) and is neutralised below
     const float fy = fmaf(p.z, A.inv_cell, A.oy);
-    const unsigned la = has_a ? atlas_fetch<TEX>(A, fmaf(Xa, A.inv_cell, A.ox), fy) : kAtlasPure;
-    const unsigned lb = has_b ? atlas_fetch<TEX>(A, fmaf(Xb, A.inv_cell, A.ox), fy) : kAtlasPure;
-    if (((la & lb) & kAtlasPure) == 0u) return false;
-    // a solution that is absent can never be preferred: res = false, infinitely far
-    BranchResult a, b;
-    a.res = b.res = false, a.vx = a.vy = a.vz = b.vx = b.vy = b.vz = 0.f, a.n2 = b.n2 = 3.0e38f;
+    const unsigned la = atlas_fetch<TEX>(A, fmaf(Xa, A.inv_cell, A.ox), fy);
+    const unsigned lb = atlas_fetch<TEX>(A, fmaf(Xb, A.inv_cell, A.ox), fy);
+    ok = ok & ((((has_a ? la : kAtlasPure) & (has_b ? lb : kAtlasPure)) & kAtlasPure) != 0u);
     const float yra = fmaf(p.y, csa, -p.x * ssa), yla = fmaf(p.y, sa.cl, -p.x * sa.sl);
     const float yrb = fmaf(p.y, csb, -p.x * ssb), ylb = fmaf(p.y, sb.cl, -p.x * sb.sl);
-    if (has_a) a = fast_branch(p, sa, csa, ssa, yra, yla, plane_from_label(W, la, Xa, p.z));
-    // A saturated flipped solution reports res = false and a vector at least as long as its
-    // offset from its own plane (or from its limit plane): when the direct one is valid, or
-    // already nearer than that, the flipped one cannot be chosen and is not evaluated.
-    const float floor_b = fminf(yrb * yrb, fmaf(ylb, ylb, sb.big));
-    const bool need_b = has_b & !((sb.nsat == 0.f) & has_a & (a.res | (a.n2 < floor_b)));
-    if (need_b) b = fast_branch(p, sb, csb, ssb, yrb, ylb, plane_from_label(W, lb, Xb, p.z));
+    // a solution that is absent can never be preferred: res = false, infinitely far
+    BranchResult a = fast_branch(p, sa, csa, ssa, yra, yla, plane_from_label(W, la, Xa, p.z));
+    a.res = a.res & has_a;
+    a.n2 = has_a ? a.n2 : 3.0e38f;
+    BranchResult b;
+    b.res = false, b.vx = b.vy = b.vz = 0.f, b.n2 = 3.0e38f;
+    if (SKIP_B) {
+        // A saturated flipped solution reports res = false and a vector at least as long as its
+        // offset from its own plane (or from its limit plane): when the direct one is valid, or
+        // already nearer than that, the flipped one cannot be chosen and is not evaluated.
+        const float floor_b = fminf(yrb * yrb, fmaf(ylb, ylb, sb.big));
+        const bool need_b = has_b & !((sb.nsat == 0.f) & has_a & (a.res | (a.n2 < floor_b)));
+        if (need_b) b = fast_branch(p, sb, csb, ssb, yrb, ylb, plane_from_label(W, lb, Xb, p.z));
+    } else {
+        b = fast_branch(p, sb, csb, ssb, yrb, ylb, plane_from_label(W, lb, Xb, p.z));
+        b.res = b.res & has_b;
+        b.n2 = has_b ? b.n2 : 3.0e38f;
+    }
     const bool direct = (a.res == b.res) ? (a.n2 < b.n2) : a.res;
     const float vx = direct ? a.vx : b.vx, vy = direct ? a.vy : b.vy, vz = direct ? a.vz : b.vz;
     out->flag = a.res | b.res;
@@ -789,7 +803,7 @@ LRM_HD bool dist_fast(const LegPlan& L, const FastView& F, const AtlasView& A, c
     out->dx = fmaf(L.Mo[0], vx, fmaf(L.Mo[1], vy, L.Mo[2] * vz));
     out->dy = fmaf(L.Mo[3], vx, fmaf(L.Mo[4], vy, L.Mo[5] * vz));
     out->dz = fmaf(L.Mo[6], vx, fmaf(L.Mo[7], vy, L.Mo[8] * vz));
-    return true;
+    return ok;
 }
 
 }  // namespace lrm

@@ -27,6 +27,11 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kTile = 1024;  // points per tile (multiple of 16 keeps every bulk copy 16-B sized)
 constexpr int kPrefetch = 2;  // tiles in flight ahead of the compute
+#ifndef LRM_SKIP_B
+#define LRM_SKIP_B 0
+#endif
+constexpr bool kSkipB = LRM_SKIP_B != 0;  // skip the flipped solution by its lower bound: a branch that
+// keeps the two points of a trip from interleaving (measured: 104 vs 111 Gpoints/s) -> off
 constexpr size_t kAtlasMinPoints = size_t(1) << 22;
 // deferred points of the fast path: entries of at most two tiles plus a partial flush block
 constexpr int kQueueCap = 2 * kTile + kThreads + 256;
@@ -93,14 +98,18 @@ __device__ __forceinline__ bool compute_point_fast(const LegPlan& L, const FastV
         x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
     }
     DistResult r;
-    if (!dist_fast<TEX>(L, F, A, W, to_coxa_frame(L, x, y, z), &r)) return false;
-    if (SOA) {
-        vec[i] = r.dx, vec[kTile + i] = r.dy, vec[2 * kTile + i] = r.dz;
-    } else {
-        vec[3 * i] = r.dx, vec[3 * i + 1] = r.dy, vec[3 * i + 2] = r.dz;
+    const bool ok = dist_fast<TEX, kSkipB>(L, F, A, W, to_coxa_frame(L, x, y, z), &r);
+    // an uncertified point leaves its input in place (values are garbage then; the redo rewrites
+    // the slot in global memory after the tile's store)
+    if (ok) {
+        if (SOA) {
+            vec[i] = r.dx, vec[kTile + i] = r.dy, vec[2 * kTile + i] = r.dz;
+        } else {
+            vec[3 * i] = r.dx, vec[3 * i + 1] = r.dy, vec[3 * i + 2] = r.dz;
+        }
+        flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
     }
-    flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
-    return true;
+    return ok;
 }
 
 // The full evaluation of one point straight from / to global memory.  Deliberately NOT inlined
@@ -240,12 +249,44 @@ __global__ void __launch_bounds__(kThreads)
                 redo(S.fast.queue[(q_head + tid) % kQueueCap], it);
                 q_head += kThreads;
             }
-#pragma unroll 2
-            for (int i = tid; i < (int)cnt; i += kThreads)
-                if (!compute_point_fast<MODE, SOA, TEX>(L, fview, atlas, S.fast.winners, in, vec, flag, i)) {
-                    const uint32_t pos = q_base + atomicAdd(&S.fast.qcnt[rot], 1u);
-                    S.fast.queue[pos % kQueueCap] = (it << 10) | (uint32_t)i;
+            // two points per trip, both computed before either is parked: the fast path is
+            // straight-line code, so the two evaluations (and their texture fetches) interleave
+            auto park = [&](int i) {
+                const uint32_t pos = q_base + atomicAdd(&S.fast.qcnt[rot], 1u);
+                S.fast.queue[pos % kQueueCap] = (it << 10) | (uint32_t)i;
+            };
+            auto load_pt = [&](int i, float& x, float& y, float& z) {
+                if (SOA) {
+                    x = in[i], y = in[kTile + i], z = in[2 * kTile + i];
+                } else {
+                    x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
                 }
+            };
+            // an uncertified point leaves its slot alone (the redo rewrites it in global memory
+            // after the tile's store)
+            auto store_pt = [&](int i, const DistResult& r) {
+                if (SOA) {
+                    vec[i] = r.dx, vec[kTile + i] = r.dy, vec[2 * kTile + i] = r.dz;
+                } else {
+                    vec[3 * i] = r.dx, vec[3 * i + 1] = r.dy, vec[3 * i + 2] = r.dz;
+                }
+                flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
+            };
+#pragma unroll 1
+            for (int i = tid; i < (int)cnt; i += 2 * kThreads) {
+                const bool has_j = i + kThreads < (int)cnt;
+                const int j = has_j ? i + kThreads : i;
+                float xi, yi, zi, xj, yj, zj;
+                load_pt(i, xi, yi, zi);
+                load_pt(j, xj, yj, zj);  // both loads before any store: the tile is updated in place
+                DistResult ri, rj;
+                const bool ok_i = dist_fast<TEX, kSkipB>(L, fview, atlas, S.fast.winners, to_coxa_frame(L, xi, yi, zi), &ri);
+                const bool ok_j = dist_fast<TEX, kSkipB>(L, fview, atlas, S.fast.winners, to_coxa_frame(L, xj, yj, zj), &rj);
+                if (ok_i) store_pt(i, ri);
+                if (ok_j & has_j) store_pt(j, rj);
+                if (!ok_i) park(i);
+                if (!ok_j & has_j) park(j);
+            }
         } else {
 #pragma unroll 1
             for (int i = tid; i < (int)cnt; i += kThreads)
