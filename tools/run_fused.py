@@ -1,4 +1,5 @@
-"""A few launches of the fused reach+dist kernel on a resident lattice slab (profiling target)."""
+"""A few launches of one one-leg kernel on a resident lattice slab (profiling target).
+    python tools/run_fused.py [points] [reps] [reach|dist|both]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,7 +13,13 @@ pts = torch.empty((n, 3), dtype=torch.float32, device="cuda")
 lrm.make_lattice(pts, lo, step, dims, 0, n)
 flags = torch.empty(n, dtype=torch.uint8, device="cuda")
 vec = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+mode = sys.argv[3] if len(sys.argv) > 3 else "both"
 for _ in range(reps):
-    lrm.reach_dist(pts, leg, out_flags=flags, out_vec=vec)
+    if mode == "reach":
+        lrm.reachability(pts, leg, out=flags)
+    elif mode == "dist":
+        lrm.distance(pts, leg, out=vec, flags=False)
+    else:
+        lrm.reach_dist(pts, leg, out_flags=flags, out_vec=vec)
 torch.cuda.synchronize()
 print("reachable", int(flags.sum().item()))
