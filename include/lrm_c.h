@@ -68,6 +68,10 @@ typedef struct lrm_leg {
 /* ---- library / device ------------------------------------------------------------------- */
 LRM_API int lrm_abi_version(void);
 LRM_API const char* lrm_last_error(void);
+/* Tuning knob: one-leg sweeps of at least n points go through the certified tables (plane atlas,
+ * yaw sectors; same results).  Default 4 Mi points — building the 16 MiB atlas of
+ * a new (leg, orientation) costs about 0.3 ms.  Returns the previous value. */
+LRM_API size_t lrm_set_fast_path_min_points(size_t n);
 LRM_API int lrm_device_count(void);
 LRM_API int lrm_set_device(int device);
 

@@ -67,6 +67,8 @@ def lib():
         L.lrm_abi_version.restype = ci
         L.lrm_last_error.restype = ctypes.c_char_p
         L.lrm_device_count.restype = ci
+        L.lrm_set_fast_path_min_points.restype = sz
+        L.lrm_set_fast_path_min_points.argtypes = [sz]
         L.lrm_set_device.argtypes = [ci]
         L.lrm_default_leg.argtypes = [ci, ctypes.c_float, legp]
         L.lrm_reach.argtypes = [vp, sz, legp, vp, vp, ci, vp, fp]
@@ -88,6 +90,11 @@ def lib():
 def _check(rc):
     if rc != LRM_OK:
         raise LrmError(f"lrm error {rc}: {lib().lrm_last_error().decode()}")
+
+
+def set_fast_path_min_points(n):
+    """One-leg sweeps of >= n points use the certified tables (default 4 Mi); returns the old value."""
+    return int(lib().lrm_set_fast_path_min_points(int(n)))
 
 
 def get_leg(robot, azimuth=0.0):

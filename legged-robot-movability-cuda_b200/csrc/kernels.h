@@ -19,6 +19,9 @@ enum : int { kModeReach = 1, kModeDist = 2, kModeBoth = 3 };
 // distance fast path are built / used when the call, not the chunk, is large enough to pay for them.
 cudaError_t launch_one_leg_aos(int mode, const LegPlan& plan, const float* xyz, float* out_vec,
                                uint8_t* flag, size_t n, cudaStream_t stream, size_t n_call = 0);
+// Sweeps (calls) of at least this many points use the certified tables (default 4 Mi: building the
+// atlas costs ~0.3 ms per new plan); returns the previous value.
+size_t set_fast_path_min_points(size_t n);
 // SoA planes; dx == nullptr selects reach-only.
 cudaError_t launch_one_leg_soa(const LegPlan& plan, const float* x, const float* y, const float* z,
                                float* dx, float* dy, float* dz, uint8_t* flag, size_t n,

@@ -268,6 +268,8 @@ extern "C" {
 int lrm_abi_version(void) { return LRM_ABI_VERSION; }
 const char* lrm_last_error(void) { return g_error.c_str(); }
 
+size_t lrm_set_fast_path_min_points(size_t n) { return lrm::set_fast_path_min_points(n); }
+
 int lrm_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {

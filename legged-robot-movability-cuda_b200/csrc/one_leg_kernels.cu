@@ -14,6 +14,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <type_traits>
 
 #include "bulk_copy.cuh"
@@ -33,6 +34,7 @@ constexpr int kPrefetch = 2;  // tiles in flight ahead of the compute
 constexpr bool kSkipB = LRM_SKIP_B != 0;  // skip the flipped solution by its lower bound: a branch that
 // keeps the two points of a trip from interleaving (measured: 104 vs 111 Gpoints/s) -> off
 constexpr size_t kAtlasMinPoints = size_t(1) << 22;
+std::atomic<size_t> g_fast_min_points{kAtlasMinPoints};
 // deferred points of the fast path: entries of at most two tiles plus a partial flush block
 constexpr int kQueueCap = 2 * kTile + kThreads + 256;
 static_assert(kTile % kThreads == 0 && kTile % 16 == 0 && kTile <= 1024, "tile shape");
@@ -518,7 +520,7 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
                           cudaStream_t stream, size_t n_call = 0) {
     AtlasView none{};
     static const FastTables no_tables{};
-    const bool big = (n_call > n ? n_call : n) >= kAtlasMinPoints;
+    const bool big = (n_call > n ? n_call : n) >= g_fast_min_points.load(std::memory_order_relaxed);
     if (MODE == kModeReach) {
         // large reach-only sweeps read the valid bit of the plane atlas instead of testing circles
         if (big && !plan.generic) {
@@ -574,6 +576,8 @@ cudaError_t launch_plain(const LegPlan& plan, const float* xyz, float* out_vec, 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
+
+size_t set_fast_path_min_points(size_t n) { return g_fast_min_points.exchange(n); }
 
 cudaError_t launch_one_leg_aos(int mode, const LegPlan& plan, const float* xyz, float* out_vec,
                                uint8_t* flag, size_t n, cudaStream_t stream, size_t n_call) {

@@ -283,3 +283,24 @@ def test_fast_path_soa_matches_aos_at_scale(lrm):
     planes = [pts[:, k].contiguous() for k in range(3)]
     f2, dx, dy, dz = lrm.reach_dist_soa(*planes, leg)
     assert torch.equal(f2, fr) and torch.equal(torch.stack([dx, dy, dz], 1), vec)
+
+
+def test_golden_vectors_through_the_fast_path(lrm, oracle, golden):
+    """The committed golden vectors (lattices, the bench slice, random clouds, 2 robots x 2 azimuths
+    x 4 orientations) with the certified tables forced on for every size: the fast path and its
+    deferred redo must meet the same bars as the plain kernels on the reference's own outputs."""
+    old = lrm.set_fast_path_min_points(1)
+    try:
+        for key, rname, az, qname, pname in _cases(golden):
+            _check(lrm, oracle, golden[f"pts_{pname}"], golden[f"leg_{rname}_{az}"], golden[f"quat_{qname}"],
+                   golden[f"reach_{key}"], golden[f"dist_{key}"], golden[f"dflag_{key}"], "fast " + key)
+        # ragged tiny sizes through the ring / drain logic
+        rng = np.random.default_rng(4)
+        leg = lrm.get_M2_leg(0.0)
+        la = leg.as_array()
+        for n in (1, 15, 16, 17, 1023, 1025, 4099):
+            pts = rng.uniform([-100, -400, -500], [600, 400, 200], (n, 3)).astype(np.float32)
+            _check(lrm, oracle, pts, la, None, oracle.reach(pts, la, threads=2), *oracle.dist(pts, la, threads=2),
+                   f"fast ragged {n}")
+    finally:
+        lrm.set_fast_path_min_points(old)
