@@ -112,6 +112,10 @@ struct SearchParams {
     int nq, nlegs;
     int plans_in_smem;
     float r_leg;
+    // orientation-independent bounds of the two cull cylinders (rotations keep 3-D distances):
+    // a map point nearer than r_collide_all is inside the body cylinder under EVERY orientation, and
+    // without a map point within r_near_any the reach cylinder is empty under every orientation
+    float r_collide_all, r_near_any;
     uint8_t* standable;
     unsigned long long* next;   // dynamic work counter
 };
@@ -191,7 +195,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
         uint8_t result = 0;
         if (P.alive == nullptr || P.alive[b]) {
             const float bx = P.bodies[3 * b], by = P.bodies[3 * b + 1], bz = P.bodies[3 * b + 2];
-            for (int o = 0; o < P.nq && result == 0; o++) {
+            // One orientation-independent scan settles most poses of a dense pose lattice (far above
+            // the map, or inside it) before the per-orientation scans: exact, because both bounds
+            // are conservative for every rotation.
+            const bool collide_all = walk_filtered(
+                P.map, bx, by, P.r_collide_all, lane,
+                [&](float x, float y, float z, float rc) {
+                    return norm3df(x - bx, y - by, z - bz) < P.r_collide_all + rc;
+                },
+                [&](float4 t, bool ok) {
+                    const float d = norm3df(t.x - bx, t.y - by, t.z - bz);
+                    return __any_sync(0xffffffffu, ok && t.w != 0.f && d < P.r_collide_all) != 0;
+                });
+            const bool near_any = !collide_all && walk_filtered(
+                P.map, bx, by, P.r_near_any, lane,
+                [&](float x, float y, float z, float rc) {
+                    return norm3df(x - bx, y - by, z - bz) < P.r_near_any + rc;
+                },
+                [&](float4 t, bool ok) {
+                    const float d = norm3df(t.x - bx, t.y - by, t.z - bz);
+                    return __any_sync(0xffffffffu, ok && t.w != 0.f && d < P.r_near_any) != 0;
+                });
+            const int nq = (collide_all || !near_any) ? 0 : P.nq;
+            for (int o = 0; o < nq && result == 0; o++) {
                 const OrientConsts& O = P.orient[o];
                 const float3 B = rotate(O.R, bx, by, bz);
                 // eliminateFarAndColliding (several_leg.cu:504-559): no map point inside the body
@@ -364,6 +390,17 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
     S.map = map_grid, S.bodies = p.bodies, S.alive = alive, S.nb = p.nb;
     S.orient = d_orient, S.plans = d_plans, S.nq = p.nq, S.nlegs = p.nlegs;
     S.r_leg = r_leg;
+    {
+        // body cylinder (r = radius_out, z in (-110, 250)): the ball of radius min(r, 110) around the
+        // body centre lies inside it; reach cylinder: contained in the ball of radius r_near.
+        float r_in = 1.0e30f, r_far = 0.f;
+        for (const OrientConsts& O : orient) {
+            r_in = std::fmin(r_in, std::fmin(O.radius_out, 110.f));
+            r_far = std::fmax(r_far, O.r_near);
+        }
+        S.r_collide_all = std::fmax(0.f, r_in - 1.f);  // 1 mm of slack for the rounding of the rotations
+        S.r_near_any = r_far + 1.f;
+    }
     S.standable = p.standable, S.next = d_next;
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
