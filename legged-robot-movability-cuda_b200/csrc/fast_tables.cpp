@@ -25,31 +25,12 @@ void diamond_dir(double d, double* x, double* y) {
     }
 }
 
-// solution kind: [free lo, free hi, min lo, min hi, max lo, max hi, mega]; "hi" = upper_lim
-int sol_kind(const YawFlags& f) {
-    if (f.mega) return 6;
-    if (f.under) return 2 + (f.upper_lim ? 1 : 0);
-    if (f.over) return 4 + (f.upper_lim ? 1 : 0);
-    return f.upper_lim ? 1 : 0;
-}
-constexpr int kSkipped = 7;
-
-// (direct kind, flipped kind) of a direction, packed; kSkipped for a duplicate solution
-int combo_of(const LegPlan& L, float x, float y) {
-    YawFlags fa, fb;
-    yaw_tests_both(L, x, y, fa, fb);
-    // same rule as dist_coxa_frame: a mega-saturated solution next to an unsaturated one is skipped
-    const bool skip_a = fa.mega & !(fb.mega | fb.over | fb.under);
-    const bool skip_b = fb.mega & !(fa.mega | fa.over | fa.under);
-    return ((skip_b ? kSkipped : sol_kind(fb)) << 3) | (skip_a ? kSkipped : sol_kind(fa));
-}
-
 YawSol make_sol(const LegPlan& L, int kind, bool flipped) {
     const float inf = std::numeric_limits<float>::infinity();
     const float sigma = flipped ? -1.f : 1.f;
     YawSol s;
     std::memset(&s, 0, sizeof s);
-    if (kind == kSkipped) {
+    if (kind == kYawSkipped) {
         // never evaluated; harmless finite values
         s.k = sigma, s.cl = L.cos_min, s.sl = L.sin_min, s.big = inf, s.present = 0.f;
         return s;
@@ -90,7 +71,7 @@ void build_fast_tables(const LegPlan& L, FastTables* out) {
             diamond_dir(lo + (hi - lo) * s / samples, &x, &y);
             for (int scale = 0; ok && scale < 2; scale++) {  // the tests are scale-free; check two radii
                 const float r = scale ? 700.f : 3.f;
-                const int c = combo_of(L, (float)(x * r), (float)(y * r));
+                const int c = yaw_combo(L, (float)(x * r), (float)(y * r));
                 if (combo < 0) combo = c;
                 ok = ok && c == combo;
             }
@@ -107,6 +88,13 @@ void build_fast_tables(const LegPlan& L, FastTables* out) {
             }
         }
         out->code[b] = id >= 0 ? (uint8_t)id : kYawImpure;  // table full (exotic leg): full evaluation
+    }
+    out->ncombo = ncombo;
+    for (int i = 0; i < ncombo; i++) {
+        out->combo[i] = combos[i];
+        if (out->pair[i].a.present != 0.f && out->pair[i].b.present != 0.f && out->pair[i].a.nsat != 0.f &&
+            out->pair[i].b.nsat != 0.f)
+            out->both_unsat = 1;
     }
 }
 

@@ -42,6 +42,11 @@ struct AtlasView;
 cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView* view,
                             FastTables* tables);
 
+// Choice volume of a plan whose atlas is cached (get_plane_atlas first): 3-D texture of the winning
+// coxa solution per cube, built on first request (plane_atlas.cu).
+struct VolumeView;
+cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeView* view);
+
 // Multi-leg positionability (positionability.cu).  All pointers are device pointers.
 struct PositParams {
     const float* bodies;   // nb x 3

@@ -534,16 +534,17 @@ LRM_HD unsigned atlas_fetch(const AtlasView& A, float fx, float fy) {
     return A.cells[atlas_index(A.w, ix, iy)];
 #endif
 }
-// Plane evaluation of a certified cell: P - (c + r v/|v|) = v (1 - r/|v|); a corner is a circle
-// of radius 0.
+// Plane evaluation of a certified cell: P - (c + r v/|v|), the very operations plane_clamp applies
+// to its winner, so that a point gets the same bits whichever tier decides it (a corner is a
+// circle of radius 0: c + 0 v = c exactly; certified cells stay off circle centres and corners).
 LRM_HD PlaneResult plane_from_label(const WinnerTable& W, unsigned label, float X, float Y) {
     const float4 e = W.e[label & 63];
     const float vx = X - e.x, vy = Y - e.y;
-    const float k = 1.f - e.z * fast_rsqrt(fmaf(vx, vx, vy * vy));
+    const float k = e.z * fast_rsqrt(fmaf(vx, vx, vy * vy));
     PlaneResult out;
     out.valid = (label & 0x40u) != 0;
-    out.dx = vx * k;
-    out.dy = vy * k;
+    out.dx = X - fmaf(vx, k, e.x);
+    out.dy = Y - fmaf(vy, k, e.y);
     return out;
 }
 
@@ -620,6 +621,25 @@ LRM_HD void yaw_tests_both(const LegPlan& L, float x, float y, YawFlags& a, YawF
     yaw_pair(L.over, fmaf(L.over.c, y, L.over.ns * x), up_d, up_f, a.over, b.over);
     yaw_pair(L.under, fmaf(L.under.c, -y, L.under.ns * x), up_dn, up_fn, a.under, b.under);
     yaw_pair(L.mid, fmaf(L.mid.c, y, L.mid.ns * x), up_d, up_f, a.upper_lim, b.upper_lim);
+}
+
+// The yaw decisions of both solutions of a direction as one small integer: solution kind
+// [free lo, free hi, min lo, min hi, max lo, max hi, mega] ("hi" = upper_lim), kYawSkipped for a
+// solution that duplicates the other one (same rule as dist_coxa_frame); direct kind in bits 0-2,
+// flipped kind in bits 3-5.
+constexpr int kYawSkipped = 7;
+LRM_HD int yaw_sol_kind(const YawFlags& f) {
+    if (f.mega) return 6;
+    if (f.under) return 2 + (f.upper_lim ? 1 : 0);
+    if (f.over) return 4 + (f.upper_lim ? 1 : 0);
+    return f.upper_lim ? 1 : 0;
+}
+LRM_HD int yaw_combo(const LegPlan& L, float x, float y) {
+    YawFlags fa, fb;
+    yaw_tests_both(L, x, y, fa, fb);
+    const bool skip_a = fa.mega & !(fb.mega | fb.over | fb.under);
+    const bool skip_b = fb.mega & !(fa.mega | fa.over | fa.under);
+    return ((skip_b ? kYawSkipped : yaw_sol_kind(fb)) << 3) | (skip_a ? kYawSkipped : yaw_sol_kind(fa));
 }
 
 struct BranchResult {
@@ -804,6 +824,136 @@ LRM_HD bool dist_fast(const LegPlan& L, const FastView& F, const AtlasView& A, c
     out->dy = fmaf(L.Mo[3], vx, fmaf(L.Mo[4], vy, L.Mo[5] * vz));
     out->dz = fmaf(L.Mo[6], vx, fmaf(L.Mo[7], vy, L.Mo[8] * vz));
     return ok;
+}
+
+
+// ---- choice volume: which coxa solution wins, certified per 3-D cell ----------------------------
+// dist_fast still evaluates BOTH coxa solutions and needs BOTH plane cells certified.  Which of
+// the two wins (one_leg.cu:334), and every yaw decision behind them, varies slowly in space: a
+// regular grid of cubes over the coxa frame holds, per cube, the winning solution — index of its
+// YawSol in the pair table — wherever that can be PROVEN constant over the cube:
+//   * the yaw decisions: same yaw_combo at the four corners of the cube's (padded) xy footprint,
+//     footprint clear of the y = 0 plane (signed-zero rules of atan2f, the +-pi seam).  The
+//     decision boundaries are rays from the coxa axis, the footprint is convex, so a boundary
+//     crossing it separates two of its corners;
+//   * the choice: the length of each solution's vector is 1-Lipschitz in the point (distance to
+//     a closed set in an isometric frame), so |n_other - n_chosen| / 2 bounds the radius within
+//     which the comparison keeps its sign; a solution with an unsaturated yaw additionally
+//     flips `res` where its plane point crosses the reachability edge, bounded by the plane
+//     probe's valid_safety.  Checked at the cube centre against the cube's half diagonal, and
+//     if that fails on 4^3 sub-cubes against theirs.
+// A point in a certified cube evaluates ONE solution: one plane-atlas fetch, one projection.  The
+// limit-plane rule (one_leg.cu:258-274) is still evaluated per point.  Uncertified cubes (and
+// everything off the volume) take dist_fast, uncertified plane cells the full evaluation.
+//
+// cube byte: 0 = uncertified; else bit 7 | pair index << 1 | side (0 direct, 1 flipped) — bits 0-4
+// index the pair table viewed as YawSol[2 * kYawPairs].
+constexpr unsigned kVolPure = 0x80u;
+struct VolumeView {
+    cudaTextureObject_t tex;  // 3-D texture of cube bytes (point sampling, border = 0)
+    float inv_cell, o;        // cube coordinates = p * inv_cell + o on every axis
+    int dim;
+};
+
+// Both solutions of one point through the full evaluation, with what the certification needs.
+struct ChoiceProbe {
+    bool direct;   // the full evaluation's choice at this point
+    float margin;  // the choice (and the flags that follow from it) cannot change within this distance
+};
+LRM_HD ChoiceProbe choice_probe(const LegPlan& L, const SectorTable& tab, const CoxaPoint p) {
+    const float rho2 = fmaf(p.x, p.x, p.y * p.y);
+    const float inv_rho = rho2 > 0.f ? fast_rsqrt(rho2) : 0.f;
+    const float ux = rho2 > 0.f ? p.x * inv_rho : 1.f;
+    const float uy = rho2 > 0.f ? p.y * inv_rho : 0.f;
+    YawFlags fa, fb;
+    yaw_tests_both(L, p.x, p.y, fa, fb);
+    const BranchPrep pa = branch_prep(L, p, fa, ux, uy);
+    const BranchPrep pb = branch_prep(L, p, fb, -ux, -uy);
+    const PlaneResult pla = plane_clamp<false>(L, tab, pa.X, p.z);
+    const PlaneResult plb = plane_clamp<false>(L, tab, pb.X, p.z);
+    const BranchResult a = branch_finish(L, p, fa, pa, pla);
+    const BranchResult b = branch_finish(L, p, fb, pb, plb);
+    ChoiceProbe out;
+    out.direct = (a.res == b.res) ? (a.n2 < b.n2) : a.res;
+    const float nc = sqrtf(out.direct ? a.n2 : b.n2), no = sqrtf(out.direct ? b.n2 : a.n2);
+    const bool c_sat = out.direct ? pa.saturated : pb.saturated, o_sat = out.direct ? pb.saturated : pa.saturated;
+    const bool c_valid = out.direct ? pla.valid : plb.valid, o_valid = out.direct ? plb.valid : pla.valid;
+    const float Xc = out.direct ? pa.X : pb.X, Xo = out.direct ? pb.X : pa.X;
+    // the chosen one stays strictly nearer ...  (0.05 mm: float rounding of both lengths)
+    float m = 0.5f * (no - nc) - 0.05f;
+    // ... or stays valid with an unsaturated yaw: res = true decides for it whatever the lengths
+    if (!c_sat && c_valid) m = fmaxf(m, plane_probe(L, tab, Xc, p.z).valid_safety - 0.01f);
+    // the other one must not turn res = true anywhere nearby
+    if (!o_sat) m = o_valid ? -1.f : fminf(m, plane_probe(L, tab, Xo, p.z).valid_safety - 0.01f);
+    out.margin = m;
+    return out;
+}
+
+// Cube byte of the cube [x0, x0+h] x [y0, y0+h] x [z0, z0+h] of the coxa frame.
+LRM_HD unsigned choice_cell_byte(const LegPlan& L, const SectorTable& tab, const FastTables& FT, float x0,
+                                 float y0, float z0, float h) {
+    // the texture unit resolves cube coordinates to 1/256 of a cube; float rounding of the
+    // coordinate itself is far below 0.01 mm
+    const float pad = h * (1.f / 64.f) + 0.01f;
+    const float xa = x0 - pad, xb = x0 + h + pad, ya = y0 - pad, yb = y0 + h + pad;
+    if (ya <= 0.f && yb >= 0.f) return 0u;
+    const int combo = yaw_combo(L, xa, ya);
+    if (yaw_combo(L, xb, ya) != combo || yaw_combo(L, xa, yb) != combo || yaw_combo(L, xb, yb) != combo)
+        return 0u;
+    int id = -1;
+    for (int i = 0; i < FT.ncombo; i++)
+        if (FT.combo[i] == combo) id = i;
+    if (id < 0 || FT.both_unsat) return 0u;
+    const bool has_a = (combo & 7) != kYawSkipped, has_b = (combo >> 3) != kYawSkipped;
+    if (!has_b) return kVolPure | ((unsigned)id << 1);
+    if (!has_a) return kVolPure | ((unsigned)id << 1) | 1u;
+    const float side = h + 2.f * pad;
+    const float r0 = 0.8660255f * side;
+    CoxaPoint c;
+    c.x = xa + 0.5f * side, c.y = ya + 0.5f * side, c.z = z0 - pad + 0.5f * side;
+    const ChoiceProbe pc = choice_probe(L, tab, c);
+    bool ok = pc.margin > r0;
+    if (!ok && pc.margin > -0.5f * r0) {  // hopeless cubes are not refined
+        constexpr int S = 4;
+        const float sub = side * (1.f / S), r1 = 0.8660255f * sub;
+        ok = true;
+        for (int k = 0; k < S * S * S && ok; k++) {
+            CoxaPoint q;
+            q.x = xa + ((float)(k % S) + 0.5f) * sub;
+            q.y = ya + ((float)((k / S) % S) + 0.5f) * sub;
+            q.z = z0 - pad + ((float)(k / (S * S)) + 0.5f) * sub;
+            const ChoiceProbe ps = choice_probe(L, tab, q);
+            ok = ps.direct == pc.direct && ps.margin > r1;
+        }
+    }
+    if (!ok) return 0u;
+    return kVolPure | ((unsigned)id << 1) | (pc.direct ? 0u : 1u);
+}
+
+// One point of a certified cube: the chosen solution only.  Same arithmetic as dist_fast for that
+// solution.  Straight-line; returns 0 = done, 1 = cube uncertified (dist_fast can still decide the
+// point), 2 = the chosen solution's plane cell is uncertified (full evaluation).
+template <bool TEX>
+LRM_HD int dist_choice(const LegPlan& L, const YawSol* sols, unsigned cube, const AtlasView& A,
+                       const WinnerTable& W, const CoxaPoint p, DistResult* out) {
+    const YawSol& s = sols[cube & 31u];
+    const float rho2 = fmaf(p.x, p.x, p.y * p.y);
+    const float inv_rho = fast_rsqrt(rho2 > 1.0e-12f ? rho2 : 1.f);  // certified cubes stay clear of the axis
+    const float ux = p.x * inv_rho, uy = p.y * inv_rho;
+    const float cs = fmaf(s.k, ux, s.c_cs), ss = fmaf(s.k, uy, s.c_ss);
+    const float X = fmaf(p.x, cs, p.y * ss) - L.coxa_length;
+    const unsigned la = atlas_fetch<TEX>(A, fmaf(X, A.inv_cell, A.ox), fmaf(p.z, A.inv_cell, A.oy));
+    const float yr = fmaf(p.y, cs, -p.x * ss), yl = fmaf(p.y, s.cl, -p.x * s.sl);
+    const BranchResult b = fast_branch(p, s, cs, ss, yr, yl, plane_from_label(W, la, X, p.z));
+    // no pair has two unsaturated solutions (FastTables::both_unsat): res of the other one is
+    // false wherever this one is chosen, so res || res_other = res, and reachability_circles'
+    // flag is res of the solution on the point's own side of the coxa axis
+    out->flag = b.res;
+    out->reach = b.res & (((cube & 1u) != 0u) == (f2i(p.x) < 0));
+    out->dx = fmaf(L.Mo[0], b.vx, fmaf(L.Mo[1], b.vy, L.Mo[2] * b.vz));
+    out->dy = fmaf(L.Mo[3], b.vx, fmaf(L.Mo[4], b.vy, L.Mo[5] * b.vz));
+    out->dz = fmaf(L.Mo[6], b.vx, fmaf(L.Mo[7], b.vy, L.Mo[8] * b.vz));
+    return (cube & kVolPure) ? ((la & kAtlasPure) ? 0 : 2) : 1;
 }
 
 }  // namespace lrm

@@ -125,6 +125,11 @@ struct YawPair {
 struct FastTables {
     YawPair pair[kYawPairs];
     uint8_t code[kYawBins + 16];  // bins 0 .. kYawBins: index into pair, or kYawImpure
+    // the (direct kind, flipped kind) combination each pair stands for (see yaw_combo), so that
+    // the choice volume can map a direction's yaw decisions to its pair without going through bins
+    int32_t ncombo;
+    int32_t combo[kYawPairs];
+    int32_t both_unsat;  // some pair has two unsaturated solutions (yaw range >= pi): no choice volume
 };
 void build_fast_tables(const LegPlan& plan, FastTables* out);
 

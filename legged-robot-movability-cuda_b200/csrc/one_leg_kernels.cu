@@ -361,6 +361,329 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// ---- three-tier distance sweep ------------------------------------------------------------------
+// Tier 1 (every point): the choice volume names the winning coxa solution of the point's cube;
+// that ONE solution is evaluated through the plane atlas (dist_choice).  Tier 2: points of
+// uncertified cubes are parked in ring 2 and redone with dist_fast (both solutions through the
+// tables).  Tier 3: points whose plane cell is uncertified — straight from tier 1, or failing
+// tier 2 — are parked in ring 3 and redone with the full evaluation.  Both rings are drained
+// 256 entries at a time by all threads (dense warps), from / to global memory, and only after the
+// bulk store of the entry's tile has completed (see one_leg_stream_kernel).  A ring that is full
+// refuses the push; the point is then evaluated on the spot (correct, just divergent).
+constexpr int kRingCap = 1024;  // entries per ring (power of two)
+static_assert((kRingCap & (kRingCap - 1)) == 0 && kRingCap >= 2 * kThreads, "ring shape");
+
+struct alignas(128) TierSmem {
+    float in[3][3 * kTile];  // in-place tiles: being loaded / computed / stored
+    uint8_t flag[2][kTile];
+    alignas(16) SectorTable table;
+    alignas(16) WinnerTable winners;
+    alignas(16) YawPair ypair[kYawPairs];
+    alignas(16) unsigned char ycode[kYawBins + 16];
+    uint32_t ring2[kRingCap];  // iteration << 10 | index in tile
+    uint32_t ring3[kRingCap];
+    unsigned cnt2[3], cnt3[3];  // pushes attempted in iteration it % 3
+    alignas(8) uint64_t full[3];
+};
+
+// dist_fast for one parked point, global -> global; false (nothing written) if the tables cannot
+// decide it.  Not inlined: see redo_point.
+template <int MODE, bool SOA>
+__device__ __noinline__ bool redo_point_fast(const LegPlan& L, const FastView F, const AtlasView& A,
+                                             const WinnerTable& W, const float* __restrict__ in_x,
+                                             const float* __restrict__ in_y, const float* __restrict__ in_z,
+                                             float* __restrict__ out_x, float* __restrict__ out_y,
+                                             float* __restrict__ out_z, uint8_t* __restrict__ out_flag,
+                                             size_t g) {
+    float x, y, z;
+    if (SOA) {
+        x = in_x[g], y = in_y[g], z = in_z[g];
+    } else {
+        x = in_x[3 * g], y = in_x[3 * g + 1], z = in_x[3 * g + 2];
+    }
+    DistResult r;
+    if (!dist_fast<true, false>(L, F, A, W, to_coxa_frame(L, x, y, z), &r)) return false;
+    if (SOA) {
+        out_x[g] = r.dx, out_y[g] = r.dy, out_z[g] = r.dz;
+    } else {
+        out_x[3 * g] = r.dx, out_x[3 * g + 1] = r.dy, out_x[3 * g + 2] = r.dz;
+    }
+    if (out_flag) out_flag[g] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
+    return true;
+}
+
+// full evaluation of one point of the tile in shared memory, in place (ring overflow only); the
+// slot already holds the point in the coxa frame
+template <int MODE, bool SOA>
+__device__ __noinline__ void tile_point_full(const LegPlan& L, const SectorTable& tab, float* tile,
+                                             uint8_t* flag, int i) {
+    CoxaPoint p;
+    if (SOA) {
+        p.x = tile[i], p.y = tile[kTile + i], p.z = tile[2 * kTile + i];
+    } else {
+        p.x = tile[3 * i], p.y = tile[3 * i + 1], p.z = tile[3 * i + 2];
+    }
+    const DistResult r = dist_coxa_frame<false>(L, tab, p);
+    if (SOA) {
+        tile[i] = r.dx, tile[kTile + i] = r.dy, tile[2 * kTile + i] = r.dz;
+    } else {
+        tile[3 * i] = r.dx, tile[3 * i + 1] = r.dy, tile[3 * i + 2] = r.dz;
+    }
+    flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
+}
+
+#ifndef LRM_TIER_CTAS
+#define LRM_TIER_CTAS 4
+#endif
+template <int MODE, bool SOA>
+__global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
+    one_leg_tier_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
+                        const AtlasView atlas, const VolumeView vol, const float* __restrict__ in_x,
+                        const float* __restrict__ in_y, const float* __restrict__ in_z,
+                        float* __restrict__ out_x, float* __restrict__ out_y, float* __restrict__ out_z,
+                        uint8_t* __restrict__ out_flag, size_t n, int kshift) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    auto& S = *reinterpret_cast<TierSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const size_t n_bulk = n & ~size_t(15);
+    const size_t n_tiles = (n_bulk + kTile - 1) / kTile;
+    constexpr int kStages = 3;
+
+    fill_sector_table(L, &S.table, tid, kThreads);
+    fill_winner_table(L, &S.winners, tid, kThreads);
+    for (int i = tid; i < kYawPairs * (int)(sizeof(YawPair) / 4); i += kThreads)
+        reinterpret_cast<float*>(S.ypair)[i] = reinterpret_cast<const float*>(FT.pair)[i];
+    for (int i = tid; i < (kYawBins + 16) / 4; i += kThreads)
+        reinterpret_cast<uint32_t*>(S.ycode)[i] = reinterpret_cast<const uint32_t*>(FT.code)[i];
+    if (tid == 0) {
+        for (int k = 0; k < 3; k++) S.cnt2[k] = S.cnt3[k] = 0;
+        for (int s = 0; s < kStages; s++) bulk::mbar_init(&S.full[s], 1);
+        bulk::fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto tile_count = [&](size_t tile) -> uint32_t {
+        const size_t first = tile * kTile;
+        return (uint32_t)((n_bulk - first < (size_t)kTile) ? (n_bulk - first) : kTile);
+    };
+    auto issue_load = [&](size_t tile, int stage) {
+        const uint32_t cnt = tile_count(tile);
+        const size_t first = tile * kTile;
+        if (SOA) {
+            bulk::mbar_expect_tx(&S.full[stage], 3 * cnt * 4);
+            bulk::load(&S.in[stage][0], in_x + first, cnt * 4, &S.full[stage]);
+            bulk::load(&S.in[stage][kTile], in_y + first, cnt * 4, &S.full[stage]);
+            bulk::load(&S.in[stage][2 * kTile], in_z + first, cnt * 4, &S.full[stage]);
+        } else {
+            bulk::mbar_expect_tx(&S.full[stage], cnt * 12);
+            bulk::load(&S.in[stage][0], in_x + 3 * first, cnt * 12, &S.full[stage]);
+        }
+    };
+    // Tiles are dealt to the CTAs in chunks of 2^kshift consecutive tiles: neighbouring tiles of a
+    // lattice sweep are neighbouring columns, whose points fall into the same cubes and plane
+    // cells, so a CTA's texture fetches keep hitting lines it has just brought in.
+    auto tile_of = [&](uint32_t iter) -> size_t {
+        return ((((size_t)(iter >> kshift) * gridDim.x + blockIdx.x)) << kshift) + (iter & ((1u << kshift) - 1u));
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kPrefetch; s++) {
+            const size_t tile = tile_of((uint32_t)s);
+            if (tile < n_tiles) issue_load(tile, s);
+        }
+    }
+
+    const FastView fview{S.ypair, S.ycode};
+    const YawSol* sols = reinterpret_cast<const YawSol*>(S.ypair);
+    uint32_t it = 0;
+    // ring bookkeeping, identical in every thread: accepted entries before this iteration (base),
+    // before the previous one (elig: their tiles' stores have completed), redone so far (head),
+    // and the room the ring had when this iteration's pushes began (room)
+    uint32_t base2 = 0, elig2 = 0, head2 = 0, room2 = kRingCap;
+    uint32_t base3 = 0, elig3 = 0, head3 = 0, room3 = kRingCap;
+    int rot = 0;  // it % 3
+
+    auto global_index = [&](uint32_t entry, uint32_t it_now) -> size_t {
+        const uint32_t age = (it_now - (entry >> 10)) & 0x3fffffu;
+        return tile_of(it_now - age) * kTile + (entry & 1023u);
+    };
+    auto push2 = [&](uint32_t entry) -> bool {
+        const uint32_t k = atomicAdd(&S.cnt2[rot], 1u);
+        if (k >= room2) return false;
+        S.ring2[(base2 + k) & (kRingCap - 1)] = entry;
+        return true;
+    };
+    auto push3 = [&](uint32_t entry) -> bool {
+        const uint32_t k = atomicAdd(&S.cnt3[rot], 1u);
+        if (k >= room3) return false;
+        S.ring3[(base3 + k) & (kRingCap - 1)] = entry;
+        return true;
+    };
+    auto redo3 = [&](uint32_t entry) {
+        redo_point<MODE, SOA>(L, S.table, in_x, in_y, in_z, out_x, out_y, out_z, out_flag, global_index(entry, it));
+    };
+    auto redo2 = [&](uint32_t entry) {
+        if (!redo_point_fast<MODE, SOA>(L, fview, atlas, S.winners, in_x, in_y, in_z, out_x, out_y, out_z,
+                                        out_flag, global_index(entry, it)))
+            if (!push3(entry)) redo3(entry);
+    };
+    auto min_u = [](uint32_t a, uint32_t b) { return a < b ? a : b; };
+
+    for (size_t tile = tile_of(0); tile < n_tiles; tile = tile_of(++it)) {
+        const int stage = it % kStages;
+        const uint32_t cnt = tile_count(tile);
+        bulk::mbar_wait(&S.full[stage], (it / kStages) & 1);
+        float* in = S.in[stage];
+        uint8_t* flag = S.flag[it & 1];
+
+        // counters of the previous iteration are final since its tile barrier
+        const int rot_prev = rot == 0 ? 2 : rot - 1;
+        elig2 = base2, elig3 = base3;
+        base2 += min_u(S.cnt2[rot_prev], room2);
+        base3 += min_u(S.cnt3[rot_prev], room3);
+        // room BEFORE this iteration's redo: slots freed now are still being read by slower warps
+        // (there is no barrier between the redo loops and the pushes of faster warps)
+        room2 = kRingCap - (base2 - head2);
+        room3 = kRingCap - (base3 - head3);
+#pragma unroll 1
+        while (elig3 - head3 >= (uint32_t)kThreads) {
+            redo3(S.ring3[(head3 + tid) & (kRingCap - 1)]);
+            head3 += kThreads;
+        }
+#pragma unroll 1
+        while (elig2 - head2 >= (uint32_t)kThreads) {
+            redo2(S.ring2[(head2 + tid) & (kRingCap - 1)]);
+            head2 += kThreads;
+        }
+
+        auto load_pt = [&](int i, float& x, float& y, float& z) {
+            if (SOA) {
+                x = in[i], y = in[kTile + i], z = in[2 * kTile + i];
+            } else {
+                x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+            }
+        };
+        auto store3 = [&](int i, float x, float y, float z) {
+            if (SOA) {
+                in[i] = x, in[kTile + i] = y, in[2 * kTile + i] = z;
+            } else {
+                in[3 * i] = x, in[3 * i + 1] = y, in[3 * i + 2] = z;
+            }
+        };
+        // Phase 1: every point of the thread goes to the coxa frame (kept in the point's own slot)
+        // and its cube byte is requested; the bytes are parked in the flag slots.  All of a
+        // thread's volume fetches are in flight together, off the critical path of phase 2.
+        {
+            constexpr int kPer = kTile / kThreads;
+            unsigned cube[kPer];
+            if (cnt == (uint32_t)kTile) {
+#pragma unroll
+                for (int k = 0; k < kPer; k++) {
+                    const int i = tid + k * kThreads;
+                    float x, y, z;
+                    load_pt(i, x, y, z);
+                    const CoxaPoint p = to_coxa_frame(L, x, y, z);
+                    cube[k] = tex3D<unsigned char>(vol.tex, fmaf(p.x, vol.inv_cell, vol.o),
+                                                   fmaf(p.y, vol.inv_cell, vol.o), fmaf(p.z, vol.inv_cell, vol.o));
+                    store3(i, p.x, p.y, p.z);
+                }
+#pragma unroll
+                for (int k = 0; k < kPer; k++) flag[tid + k * kThreads] = (uint8_t)cube[k];
+            } else {
+#pragma unroll 1
+                for (int i = tid; i < (int)cnt; i += kThreads) {
+                    float x, y, z;
+                    load_pt(i, x, y, z);
+                    const CoxaPoint p = to_coxa_frame(L, x, y, z);
+                    flag[i] = (uint8_t)tex3D<unsigned char>(vol.tex, fmaf(p.x, vol.inv_cell, vol.o),
+                                                            fmaf(p.y, vol.inv_cell, vol.o), fmaf(p.z, vol.inv_cell, vol.o));
+                    store3(i, p.x, p.y, p.z);
+                }
+            }
+        }
+        // Phase 2: the chosen solution of each point, two points per trip (their plane-atlas
+        // fetches overlap).  A parked point leaves its slot alone: the redo rewrites it in global
+        // memory after the tile's store.
+        auto store_pt = [&](int i, const DistResult& r) {
+            store3(i, r.dx, r.dy, r.dz);
+            flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
+        };
+        auto park = [&](int i, int why) {
+            const uint32_t entry = (it << 10) | (uint32_t)i;
+            if (why == 1 && push2(entry)) return;
+            if (push3(entry)) return;
+            tile_point_full<MODE, SOA>(L, S.table, in, flag, i);
+        };
+#pragma unroll 1
+        for (int i = tid; i < (int)cnt; i += 2 * kThreads) {
+            const bool has_j = i + kThreads < (int)cnt;
+            const int j = has_j ? i + kThreads : i;
+            CoxaPoint pi, pj;
+            load_pt(i, pi.x, pi.y, pi.z);
+            load_pt(j, pj.x, pj.y, pj.z);  // both loads before any store: the tile is updated in place
+            const unsigned ci = flag[i], cj = flag[j];
+            DistResult ri, rj;
+            const int si = dist_choice<true>(L, sols, ci, atlas, S.winners, pi, &ri);
+            const int sj = dist_choice<true>(L, sols, cj, atlas, S.winners, pj, &rj);
+            if (si == 0) store_pt(i, ri);
+            if ((sj == 0) & has_j) store_pt(j, rj);
+            if (si != 0) park(i, si);
+            if ((sj != 0) & has_j) park(j, sj);
+        }
+
+        bulk::fence_proxy_async();
+        if (tid == 0) {
+            bulk::wait_group<0>();  // every committed store has COMPLETED: parked points of those tiles may be redone
+            const int rot_next = rot == 2 ? 0 : rot + 1;
+            S.cnt2[rot_next] = 0, S.cnt3[rot_next] = 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const size_t first = tile * kTile;
+            if (SOA) {
+                bulk::store(out_x + first, in, cnt * 4);
+                bulk::store(out_y + first, in + kTile, cnt * 4);
+                bulk::store(out_z + first, in + 2 * kTile, cnt * 4);
+            } else {
+                bulk::store(out_x + 3 * first, in, cnt * 12);
+            }
+            if (out_flag) bulk::store(out_flag + first, flag, cnt);
+            bulk::commit_group();
+            const size_t next = tile_of(it + kPrefetch);
+            if (next < n_tiles) issue_load(next, (int)((it + kPrefetch) % kStages));
+        }
+        rot = rot == 2 ? 0 : rot + 1;
+    }
+    if (tid == 0) bulk::wait_group<0>();
+    __syncthreads();  // every store has completed, every counter is final
+    {
+        const int rot_prev = rot == 0 ? 2 : rot - 1;
+        if (it) {
+            base2 += min_u(S.cnt2[rot_prev], room2);
+            base3 += min_u(S.cnt3[rot_prev], room3);
+        }
+#pragma unroll 1
+        for (; head3 < base3; head3 += kThreads)
+            if (head3 + tid < base3) redo3(S.ring3[(head3 + tid) & (kRingCap - 1)]);
+        head3 = base3;
+        room3 = kRingCap;  // ring 3 is empty; tier-2 failures of the drain go to cnt3[rot] (zero so far)
+        __syncthreads();
+#pragma unroll 1
+        for (; head2 < base2; head2 += kThreads)
+            if (head2 + tid < base2) redo2(S.ring2[(head2 + tid) & (kRingCap - 1)]);
+        __syncthreads();
+        base3 += min_u(S.cnt3[rot], room3);
+#pragma unroll 1
+        for (; head3 < base3; head3 += kThreads)
+            if (head3 + tid < base3) redo3(S.ring3[(head3 + tid) & (kRingCap - 1)]);
+    }
+
+    // the last n % 16 points bypass the bulk engine
+    if (blockIdx.x == 0) {
+        const size_t i = n_bulk + tid;
+        if (i < n) redo_point<MODE, SOA>(L, S.table, in_x, in_y, in_z, out_x, out_y, out_z, out_flag, i);
+    }
+}
+
 // Same math with plain per-thread global accesses: used when a caller's buffers are not 16-byte
 // aligned (the bulk engine's requirement) — still the GPU path, just without staging.
 template <int MODE, bool GENERIC>
@@ -502,6 +825,48 @@ cudaError_t launch_stream_impl(const LegPlan& plan, const FastTables& ft, const 
     return cudaGetLastError();
 }
 
+// LRM_TIER_CHUNK (log2 of the tiles per chunk, default 3): measurement knob
+int tier_chunk_shift_max() {
+    const char* e = getenv("LRM_TIER_CHUNK");
+    const int v = e ? atoi(e) : 3;
+    return v < 0 ? 0 : (v > 8 ? 8 : v);
+}
+
+template <int MODE, bool SOA>
+cudaError_t launch_tier_impl(const LegPlan& plan, const FastTables& ft, const AtlasView& atlas,
+                             const VolumeView& vol, const float* ix, const float* iy, const float* iz,
+                             float* ox, float* oy, float* oz, uint8_t* flag, size_t n, cudaStream_t stream) {
+    auto kernel = one_leg_tier_kernel<MODE, SOA>;
+    constexpr size_t smem = sizeof(TierSmem);
+    static int ctas_per_sm_dev[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& ctas_per_sm = ctas_per_sm_dev[dev & 63];
+    if (ctas_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = occ < 1 ? 1 : occ;
+    }
+    const size_t tiles = ((n & ~size_t(15)) + kTile - 1) / kTile;
+    size_t grid = (size_t)sm_count() * ctas_per_sm;
+    if (tiles < grid) grid = tiles;
+    if (grid == 0) grid = 1;
+    // chunks of up to 8 consecutive tiles per CTA, fewer on small sweeps (keep >= 16 chunks per CTA)
+    int kshift = 0;
+    while (kshift < tier_chunk_shift_max() && (tiles >> (kshift + 1)) >= grid * 16) kshift++;
+    kernel<<<(unsigned)grid, kThreads, smem, stream>>>(plan, ft, atlas, vol, ix, iy, iz, ox, oy, oz, flag, n, kshift);
+    return cudaGetLastError();
+}
+
+// LRM_CHOICE_VOLUME=0 keeps the two-tier sweep (dist_fast + full evaluation) for A/B measurements
+bool choice_volume_enabled() {
+    const char* e = getenv("LRM_CHOICE_VOLUME");  // read per launch: tools switch it inside one process
+    return !(e && e[0] == '0');
+}
+
 // LRM_ATLAS_TEX=0 selects plain loads from the blocked copy of the atlas instead of the texture
 // unit (same cells, same results; kept for A/B measurements)
 bool atlas_through_texture() {
@@ -547,6 +912,15 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
         FastTables ft;
         cudaError_t e = get_plane_atlas(plan, stream, &atlas, &ft);
         if (e != cudaSuccess) return e;
+        if constexpr (kDist) {
+            if (atlas_through_texture() && choice_volume_enabled() && ft.both_unsat == 0) {
+                VolumeView vol;
+                e = get_choice_volume(plan, stream, &vol);
+                if (e == cudaSuccess)
+                    return launch_tier_impl<MODE, SOA>(plan, ft, atlas, vol, ix, iy, iz, ox, oy, oz, flag, n, stream);
+                (void)cudaGetLastError();  // no memory for the volume: the two-tier sweep still works
+            }
+        }
         if (atlas_through_texture())
             return launch_stream_impl<MODE, SOA, false, kDist, kDist>(plan, ft, atlas, ix, iy, iz, ox, oy, oz,
                                                                       flag, n, stream);

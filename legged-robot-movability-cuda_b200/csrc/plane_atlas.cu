@@ -8,6 +8,7 @@
 // cannot certify.  16 MiB per (leg, orientation); a small per-device LRU keeps the last few.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -42,6 +43,23 @@ __global__ void atlas_build_kernel(const __grid_constant__ LegPlan L, unsigned c
     }
 }
 
+// One thread per cube of the choice volume (leg_math.cuh): x fastest, like the 3-D array upload.
+__global__ void __launch_bounds__(128)
+    volume_build_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
+                        unsigned char* __restrict__ linear, int dim, float cell) {
+    __shared__ SectorTable table;
+    fill_sector_table(L, &table, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const size_t total = (size_t)dim * dim * dim;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const float half = 0.5f * (float)dim;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int ix = (int)(i % dim), iy = (int)((i / dim) % dim), iz = (int)(i / ((size_t)dim * dim));
+        linear[i] = (unsigned char)choice_cell_byte(L, table, FT, ((float)ix - half) * cell,
+                                                    ((float)iy - half) * cell, ((float)iz - half) * cell, cell);
+    }
+}
+
 struct Entry {
     bool used = false;
     int device = -1;
@@ -52,8 +70,20 @@ struct Entry {
     cudaArray_t array = nullptr;
     cudaTextureObject_t tex = 0;
     FastTables tables;  // yaw-sector table of the same plan (host-built, ~0.5 ms: cached with the atlas)
+    // choice volume (built on first request, see get_choice_volume)
+    cudaArray_t vol_array = nullptr;
+    cudaTextureObject_t vol_tex = 0;
+    int vol_dim = 0;
+    float vol_cell = 0.f;
+    bool vol_ready = false;
 };
+void release_volume(Entry* c) {
+    if (c->vol_tex) cudaDestroyTextureObject(c->vol_tex);
+    if (c->vol_array) cudaFreeArray(c->vol_array);
+    c->vol_tex = 0, c->vol_array = nullptr, c->vol_ready = false, c->vol_dim = 0;
+}
 void release(Entry* c) {
+    release_volume(c);
     if (c->tex) cudaDestroyTextureObject(c->tex);
     if (c->array) cudaFreeArray(c->array);
     if (c->cells) cudaFree(c->cells);
@@ -117,6 +147,7 @@ cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView*
             if (e != cudaSuccess) return e;
         }
         victim->used = false;
+        victim->vol_ready = false;  // the volume belongs to the evicted plan: rebuilt on request
         if (!victim->cells) {
             e = allocate(victim);
             if (e != cudaSuccess) {
@@ -149,6 +180,89 @@ cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView*
     view->inv_cell = 1.0f / kAtlasCell;
     view->ox = view->oy = -kAtlasOrigin / kAtlasCell;
     view->w = kAtlasDim, view->h = kAtlasDim;
+    return cudaSuccess;
+}
+
+// LRM_VOL_CELL (mm, default 4) / LRM_VOL_DIM (cubes per side, default 384): measurement knobs
+void volume_shape(int* dim, float* cell) {
+    static int d = 0;
+    static float c = 0.f;
+    if (d == 0) {
+        const char* ec = getenv("LRM_VOL_CELL");
+        const char* ed = getenv("LRM_VOL_DIM");
+        c = ec ? (float)atof(ec) : 4.0f;
+        if (!(c >= 0.5f && c <= 64.f)) c = 4.0f;
+        d = ed ? atoi(ed) : 384;
+        if (d < 16 || d > 1024) d = 384;
+    }
+    *dim = d, *cell = c;
+}
+
+cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeView* view) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    Entry* hit = nullptr;
+    for (Entry& c : g_cache)
+        if (c.used && c.device == dev && std::memcmp(&c.plan, &plan, sizeof(LegPlan)) == 0) hit = &c;
+    if (!hit) return cudaErrorInvalidValue;  // get_plane_atlas first
+    int dim;
+    float cell;
+    volume_shape(&dim, &cell);
+    if (!hit->vol_ready) {
+        if (hit->vol_array && hit->vol_dim != dim) release_volume(hit);
+        if (!hit->vol_array) {
+            const cudaChannelFormatDesc fmt = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+            e = cudaMalloc3DArray(&hit->vol_array, &fmt, make_cudaExtent(dim, dim, dim));
+            if (e != cudaSuccess) return e;
+            cudaResourceDesc res;
+            std::memset(&res, 0, sizeof res);
+            res.resType = cudaResourceTypeArray;
+            res.res.array.array = hit->vol_array;
+            cudaTextureDesc td;
+            std::memset(&td, 0, sizeof td);
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;  // off the volume -> 0
+            td.filterMode = cudaFilterModePoint;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            e = cudaCreateTextureObject(&hit->vol_tex, &res, &td, nullptr);
+            if (e != cudaSuccess) {
+                release_volume(hit);
+                return e;
+            }
+            hit->vol_dim = dim;
+        }
+        // earlier sweeps on other streams may still read a volume being rebuilt for a new plan
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return e;
+        const size_t bytes = (size_t)dim * dim * dim;
+        unsigned char* linear = nullptr;
+        e = cudaMalloc((void**)&linear, bytes);
+        if (e != cudaSuccess) return e;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        volume_build_kernel<<<sms * 16, 128, 0, stream>>>(plan, hit->tables, linear, dim, cell);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) {
+            cudaMemcpy3DParms cp;
+            std::memset(&cp, 0, sizeof cp);
+            cp.srcPtr = make_cudaPitchedPtr(linear, (size_t)dim, (size_t)dim, (size_t)dim);
+            cp.dstArray = hit->vol_array;
+            cp.extent = make_cudaExtent(dim, dim, dim);
+            cp.kind = cudaMemcpyDeviceToDevice;
+            e = cudaMemcpy3DAsync(&cp, stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        cudaFree(linear);
+        if (e != cudaSuccess) return e;
+        hit->vol_cell = cell;
+        hit->vol_ready = true;
+    }
+    view->tex = hit->vol_tex;
+    view->inv_cell = 1.0f / hit->vol_cell;
+    view->o = 0.5f * (float)hit->vol_dim;
+    view->dim = hit->vol_dim;
     return cudaSuccess;
 }
 

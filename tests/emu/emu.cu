@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <unordered_map>
 #include <vector>
 
 #include "leg_math.cuh"
@@ -125,6 +126,67 @@ size_t emu_dist_atlas(const float* xyz, size_t n, const lrm_leg_t* leg, const fl
     }
     delete[] cells;
     return fallback;
+}
+
+// The three-tier distance sweep as the streaming kernel runs it: choice volume (dist_choice) ->
+// dist_fast -> full evaluation.  Cube bytes are computed on demand with the very function the
+// device build kernel uses (choice_cell_byte).  tiers[0..2] = points decided by each tier.
+void emu_dist_choice(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, int dim,
+                     float cell, float vol_h, int vol_dim, float* out_vec, uint8_t* out_flag,
+                     uint8_t* out_reach, size_t* tiers, uint8_t* out_tier) {
+    lrm::LegPlan L;
+    lrm::build_leg_plan(*leg, quat, &L);
+    lrm::SectorTable tab;
+    host_table(L, &tab);
+    lrm::WinnerTable win;
+    lrm::fill_winner_table(L, &win, 0, 1);
+    lrm::FastTables ft;
+    lrm::build_fast_tables(L, &ft);
+    const float origin = -0.5f * dim * cell;
+    std::vector<unsigned char> cells((size_t)dim * dim);
+    const float need = lrm::kAtlasNeedFactor * cell + lrm::kAtlasNeedSlack;
+    for (int iy = 0; iy < dim; iy++)
+        for (int ix = 0; ix < dim; ix++) {
+            const float X = origin + ((float)ix + 0.5f) * cell, Y = origin + ((float)iy + 0.5f) * cell;
+            cells[lrm::atlas_index(dim, ix, iy)] = (unsigned char)lrm::atlas_cell_byte(lrm::plane_probe(L, tab, X, Y), need);
+        }
+    lrm::AtlasView A{cells.data(), 0, 1.0f / cell, -origin / cell, -origin / cell, dim, dim};
+    const lrm::FastView F{ft.pair, ft.code};
+    const lrm::YawSol* sols = reinterpret_cast<const lrm::YawSol*>(ft.pair);
+    std::unordered_map<uint64_t, unsigned char> cubes;
+    const float vo = 0.5f * vol_dim, vinv = 1.0f / vol_h;
+    tiers[0] = tiers[1] = tiers[2] = 0;
+    for (size_t i = 0; i < n; i++) {
+        const lrm::CoxaPoint p = lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        const float fx = fmaf(p.x, vinv, vo), fy = fmaf(p.y, vinv, vo), fz = fmaf(p.z, vinv, vo);
+        unsigned cube = 0;
+        if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)vol_dim && fy < (float)vol_dim && fz < (float)vol_dim) {
+            const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+            const uint64_t key = ((uint64_t)iz * vol_dim + iy) * vol_dim + ix;
+            auto it = cubes.find(key);
+            if (it == cubes.end()) {
+                const unsigned char b = (unsigned char)lrm::choice_cell_byte(
+                    L, tab, ft, ((float)ix - vo) * vol_h, ((float)iy - vo) * vol_h, ((float)iz - vo) * vol_h, vol_h);
+                it = cubes.emplace(key, b).first;
+            }
+            cube = it->second;
+        }
+        lrm::DistResult r;
+        int tier = 0;
+        const int st = lrm::dist_choice<false>(L, sols, cube, A, win, p, &r);
+        if (st != 0) {
+            tier = 1;
+            if (st == 2 || !lrm::dist_fast<false>(L, F, A, win, p, &r)) {
+                r = lrm::dist_coxa_frame<false>(L, tab, p);
+                tier = 2;
+            }
+        }
+        tiers[tier]++;
+        if (out_tier) out_tier[i] = (uint8_t)tier;
+        out_vec[3 * i] = r.dx, out_vec[3 * i + 1] = r.dy, out_vec[3 * i + 2] = r.dz;
+        if (out_flag) out_flag[i] = r.flag ? 1 : 0;
+        if (out_reach) out_reach[i] = r.reach ? 1 : 0;
+    }
 }
 
 // The positionability kernel's per-pose logic (positionability.cu) with brute-force target loops:

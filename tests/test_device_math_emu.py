@@ -158,9 +158,48 @@ def test_fast_path_never_changes_a_result(emu, port):
                                 ctypes.byref(bins), ra.ctypes.data)
         assert np.array_equal(fl, bf) and np.array_equal(rf, br)
         assert np.array_equal(ra, r0)   # reach-only sweep through the atlas' valid bit
-        assert np.abs(out - base).max() < 1e-3, float(np.abs(out - base).max())
+        assert np.array_equal(out, base), float(np.abs(out - base).max())   # same operations on the winner: same bits
         assert pure.value > 0.85 * 1024 * 1024 and fb < 0.35 * len(pts), (pure.value, fb)
         assert bins.value > 0.95 * 1025, bins.value
+
+
+def test_choice_volume_never_changes_a_result(emu, port):
+    """The three-tier distance sweep (leg_math.cuh: choice volume -> dist_fast -> full evaluation) is
+    a pure accelerator and, since every tier applies the same operations to the winning candidate,
+    returns the full evaluation's result BIT FOR BIT whichever tier decides a point — so a ring
+    overflow (which moves a point to a slower tier) cannot change an output either.  Cube bytes come
+    from the function the device build kernel runs (choice_cell_byte)."""
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    emu.emu_dist_choice.argtypes = [vp, sz, vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                    ctypes.c_int, vp, vp, vp, vp, vp]
+    rng = np.random.default_rng(41)
+    idx = rng.integers(0, 1000, (120000, 3))
+    lo, hi = np.array([-100, -400, -500], np.float32), np.array([600, 400, 200], np.float32)
+    lattice = lo + idx.astype(np.float32) * ((hi - lo) / np.float32(999)).astype(np.float32)
+    cloud = np.concatenate([lattice, rng.uniform(-800, 800, (60000, 3))]).astype(np.float32)
+    cases = ((1, 0.0, [1, 0, 0, 0], 4.0, 0.80), (0, 0.7853982, port.quaternion_from_angle_index(0), 4.0, 0.70),
+             (1, 3.9269907, port.full_struct_orientations()[31], 2.0, 0.70))
+    for robot, az, q, cell, want_share in cases:
+        leg = port.get_leg(robot, az)
+        q = np.ascontiguousarray(q, np.float32)
+        ang = np.linspace(-np.pi, np.pi, 3601)
+        near = np.concatenate([ang + d for d in (-1e-4, 0.0, 1e-4)])
+        cx, cy = np.float32(leg[1]) * np.cos(az), np.float32(leg[1]) * np.sin(az)
+        ring = np.stack([cx + 200.0 * np.cos(near), cy + 200.0 * np.sin(near), np.full_like(near, -120.0)], 1)
+        pts = np.ascontiguousarray(np.concatenate([cloud, ring]), np.float32)
+        _, base, bf, br = run_emu(emu, pts, leg, q)
+        out = np.zeros_like(pts)
+        fl = np.zeros(len(pts), np.uint8)
+        rf = np.zeros(len(pts), np.uint8)
+        tier = np.zeros(len(pts), np.uint8)
+        tiers = (ctypes.c_size_t * 3)()
+        emu.emu_dist_choice(pts.ctypes.data, len(pts), leg.ctypes.data, q.ctypes.data, 2048, 1.0, cell,
+                            int(1536 / cell), out.ctypes.data, fl.ctypes.data, rf.ctypes.data, tiers,
+                            tier.ctypes.data)
+        assert np.array_equal(fl, bf) and np.array_equal(rf, br), (robot, az)
+        assert np.array_equal(out, base), (robot, az, float(np.abs(out - base).max()))
+        # the volume must be worth having on the bench box (first 120 000 points)
+        assert (tier[:120000] == 0).mean() > want_share, (robot, az, float((tier[:120000] == 0).mean()))
 
 
 def test_reach_plan_predicates(emu, port):
