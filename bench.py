@@ -261,12 +261,14 @@ def run_b200(args):
                          # ncu dram__bytes_read+write of this kernel (profiles/traffic.json, captured at
                          # 1e9 points per launch; scaled per point for other sizes)
                          "traffic": (traffic["dram_bytes_per_point"] * n) if traffic else None,
-                         "kernel": "one_leg_stream_kernel<both,aos>", "kernel_ms": kernel_ms,
+                         "kernel": "one_leg_tier_kernel<both,aos>", "kernel_ms": kernel_ms,
                          "bytes_per_point": BYTES_PER_POINT},
             "e2e": {"value": e2e_value, "unit": "Gpoints/s", "h2d_bytes_per_step": 12 * ne,
                     "d2h_bytes_per_step": 13 * ne, "points_per_step": ne,
                     "note": "lrm_reach_dist with pinned host buffers, H2D + kernel + D2H per step"},
-            "gpu_launches": args.steps, "clocks": clk,
+            # per step: the coherence probe (1 CTA), the tiered sweep it selects for a lattice, and the
+            # two-tier sweep that reads the verdict and returns at once
+            "gpu_launches": 3 * args.steps, "clocks": clk,
         }
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1

@@ -956,4 +956,23 @@ LRM_HD int dist_choice(const LegPlan& L, const YawSol* sols, unsigned cube, cons
     return (cube & kVolPure) ? ((la & kAtlasPure) ? 0 : 2) : 1;
 }
 
+// The chosen solution of a certified cube with the EXPLICIT plane evaluation (plane_clamp) instead
+// of the plane atlas: for points whose plane cell is uncertified.  Cannot fail.
+LRM_HD void dist_choice_clamp(const LegPlan& L, const SectorTable& tab, const YawSol* sols, unsigned cube,
+                              const CoxaPoint p, DistResult* out) {
+    const YawSol& s = sols[cube & 31u];
+    const float rho2 = fmaf(p.x, p.x, p.y * p.y);
+    const float inv_rho = fast_rsqrt(rho2 > 1.0e-12f ? rho2 : 1.f);
+    const float ux = p.x * inv_rho, uy = p.y * inv_rho;
+    const float cs = fmaf(s.k, ux, s.c_cs), ss = fmaf(s.k, uy, s.c_ss);
+    const float X = fmaf(p.x, cs, p.y * ss) - L.coxa_length;
+    const float yr = fmaf(p.y, cs, -p.x * ss), yl = fmaf(p.y, s.cl, -p.x * s.sl);
+    const BranchResult b = fast_branch(p, s, cs, ss, yr, yl, plane_clamp<false>(L, tab, X, p.z));
+    out->flag = b.res;
+    out->reach = b.res & (((cube & 1u) != 0u) == (f2i(p.x) < 0));
+    out->dx = fmaf(L.Mo[0], b.vx, fmaf(L.Mo[1], b.vy, L.Mo[2] * b.vz));
+    out->dy = fmaf(L.Mo[3], b.vx, fmaf(L.Mo[4], b.vy, L.Mo[5] * b.vz));
+    out->dz = fmaf(L.Mo[6], b.vx, fmaf(L.Mo[7], b.vy, L.Mo[8] * b.vz));
+}
+
 }  // namespace lrm

@@ -155,7 +155,9 @@ __global__ void __launch_bounds__(kThreads)
                           const AtlasView atlas, const float* __restrict__ in_x,
                           const float* __restrict__ in_y, const float* __restrict__ in_z,
                           float* __restrict__ out_x, float* __restrict__ out_y,
-                          float* __restrict__ out_z, uint8_t* __restrict__ out_flag, size_t n) {
+                          float* __restrict__ out_z, uint8_t* __restrict__ out_flag, size_t n,
+                          const int* __restrict__ gate, int gate_want) {
+    if (gate != nullptr && *gate != gate_want) return;  // the coherence probe chose the other sweep
     // keep the pointer provably in the shared window (LDS/STS, not generic LD/ST): no integer
     // round-trip on the address; the bulk engine only needs 16-byte alignment
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -361,17 +363,22 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
-// ---- three-tier distance sweep ------------------------------------------------------------------
+// ---- tiered distance sweep ----------------------------------------------------------------------
 // Tier 1 (every point): the choice volume names the winning coxa solution of the point's cube;
-// that ONE solution is evaluated through the plane atlas (dist_choice).  Tier 2: points of
-// uncertified cubes are parked in ring 2 and redone with dist_fast (both solutions through the
-// tables).  Tier 3: points whose plane cell is uncertified — straight from tier 1, or failing
-// tier 2 — are parked in ring 3 and redone with the full evaluation.  Both rings are drained
-// 256 entries at a time by all threads (dense warps), from / to global memory, and only after the
-// bulk store of the entry's tile has completed (see one_leg_stream_kernel).  A ring that is full
-// refuses the push; the point is then evaluated on the spot (correct, just divergent).
-constexpr int kRingCap = 1024;  // entries per ring (power of two)
-static_assert((kRingCap & (kRingCap - 1)) == 0 && kRingCap >= 2 * kThreads, "ring shape");
+// that ONE solution is evaluated through the plane atlas (dist_choice).  What tier 1 cannot
+// decide is parked in one of three per-CTA rings and redone later, 256 entries at a time by all
+// threads of the CTA (dense warps, every lane on the same path), from / to global memory, and only
+// after the bulk store of the entry's tile has completed (see one_leg_stream_kernel):
+//   ring A: the cube is certified but the chosen solution's plane cell is not -> the same ONE
+//           solution with the explicit plane evaluation (dist_choice_clamp); cannot fail;
+//   ring B: the cube is uncertified -> both solutions through the tables (dist_fast);
+//   ring C: what ring B's redo cannot decide -> the full evaluation.
+// A ring that is full refuses the push; the point then moves to the next ring or is evaluated on
+// the spot (correct, just divergent).  Every path applies the same operations to the winning
+// candidate, so the output does not depend on which one ran.
+constexpr int kRingA = 1024, kRingB = 1024, kRingC = 512;  // entries (powers of two)
+// ring entry: iteration (17 bits) | cube byte bits 0-4 | index in tile (10 bits)
+constexpr int kEntryIterBits = 17;
 
 struct alignas(128) TierSmem {
     float in[3][3 * kTile];  // in-place tiles: being loaded / computed / stored
@@ -380,36 +387,83 @@ struct alignas(128) TierSmem {
     alignas(16) WinnerTable winners;
     alignas(16) YawPair ypair[kYawPairs];
     alignas(16) unsigned char ycode[kYawBins + 16];
-    uint32_t ring2[kRingCap];  // iteration << 10 | index in tile
-    uint32_t ring3[kRingCap];
-    unsigned cnt2[3], cnt3[3];  // pushes attempted in iteration it % 3
+    uint32_t ring_a[kRingA], ring_b[kRingB], ring_c[kRingC];
+    unsigned cnt[3][3];  // [ring][it % 3]: pushes attempted in that iteration
     alignas(8) uint64_t full[3];
 };
 
-// dist_fast for one parked point, global -> global; false (nothing written) if the tables cannot
-// decide it.  Not inlined: see redo_point.
-template <int MODE, bool SOA>
-__device__ __noinline__ bool redo_point_fast(const LegPlan& L, const FastView F, const AtlasView& A,
-                                             const WinnerTable& W, const float* __restrict__ in_x,
-                                             const float* __restrict__ in_y, const float* __restrict__ in_z,
-                                             float* __restrict__ out_x, float* __restrict__ out_y,
-                                             float* __restrict__ out_z, uint8_t* __restrict__ out_flag,
-                                             size_t g) {
+// Per-thread (uniform) bookkeeping of one ring: accepted entries before this iteration (base),
+// before the previous one (elig: their tiles' stores have completed), redone so far (head), and
+// the room the ring had when this iteration's pushes began.
+template <int CAP>
+struct Ring {
+    static_assert((CAP & (CAP - 1)) == 0 && CAP >= 2 * kThreads, "ring shape");
+    uint32_t base = 0, elig = 0, head = 0, room = CAP;
+    // top of an iteration; prev = attempts counted in the previous one.  room is taken BEFORE this
+    // iteration's redo: slots freed now may still be read by slower warps (no barrier in between).
+    __device__ __forceinline__ void advance(unsigned prev) {
+        elig = base;
+        base += prev < room ? prev : room;
+        room = CAP - (base - head);
+    }
+    __device__ __forceinline__ bool push(uint32_t* slots, unsigned* counter, uint32_t entry) const {
+        const uint32_t k = atomicAdd(counter, 1u);
+        if (k >= room) return false;
+        slots[(base + k) & (CAP - 1)] = entry;
+        return true;
+    }
+};
+
+struct RedoIo {
+    const float* __restrict__ in_x;
+    const float* __restrict__ in_y;
+    const float* __restrict__ in_z;
+    float* __restrict__ out_x;
+    float* __restrict__ out_y;
+    float* __restrict__ out_z;
+    uint8_t* __restrict__ out_flag;
+};
+template <bool SOA>
+__device__ __forceinline__ CoxaPoint redo_load(const LegPlan& L, const RedoIo& io, size_t g) {
     float x, y, z;
     if (SOA) {
-        x = in_x[g], y = in_y[g], z = in_z[g];
+        x = io.in_x[g], y = io.in_y[g], z = io.in_z[g];
     } else {
-        x = in_x[3 * g], y = in_x[3 * g + 1], z = in_x[3 * g + 2];
+        x = io.in_x[3 * g], y = io.in_x[3 * g + 1], z = io.in_x[3 * g + 2];
     }
-    DistResult r;
-    if (!dist_fast<true, false>(L, F, A, W, to_coxa_frame(L, x, y, z), &r)) return false;
+    return to_coxa_frame(L, x, y, z);
+}
+template <int MODE, bool SOA>
+__device__ __forceinline__ void redo_store(const RedoIo& io, size_t g, const DistResult& r) {
     if (SOA) {
-        out_x[g] = r.dx, out_y[g] = r.dy, out_z[g] = r.dz;
+        io.out_x[g] = r.dx, io.out_y[g] = r.dy, io.out_z[g] = r.dz;
     } else {
-        out_x[3 * g] = r.dx, out_x[3 * g + 1] = r.dy, out_x[3 * g + 2] = r.dz;
+        io.out_x[3 * g] = r.dx, io.out_x[3 * g + 1] = r.dy, io.out_x[3 * g + 2] = r.dz;
     }
-    if (out_flag) out_flag[g] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
+    if (io.out_flag) io.out_flag[g] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
+}
+// The redo paths are deliberately NOT inlined (see redo_point).
+// ring A: the chosen solution (cube bits carried by the entry) with the explicit plane evaluation
+template <int MODE, bool SOA>
+__device__ __noinline__ void redo_choice(const LegPlan& L, const SectorTable& tab, const YawSol* sols,
+                                         unsigned cube, const RedoIo& io, size_t g) {
+    DistResult r;
+    dist_choice_clamp(L, tab, sols, cube, redo_load<SOA>(L, io, g), &r);
+    redo_store<MODE, SOA>(io, g, r);
+}
+// ring B: dist_fast; false (nothing written) if the tables cannot decide the point
+template <int MODE, bool SOA>
+__device__ __noinline__ bool redo_fast(const LegPlan& L, const FastView F, const AtlasView& A,
+                                       const WinnerTable& W, const RedoIo& io, size_t g) {
+    DistResult r;
+    if (!dist_fast<true, false>(L, F, A, W, redo_load<SOA>(L, io, g), &r)) return false;
+    redo_store<MODE, SOA>(io, g, r);
     return true;
+}
+// ring C: the full evaluation
+template <int MODE, bool SOA>
+__device__ __noinline__ void redo_full(const LegPlan& L, const SectorTable& tab, const RedoIo& io, size_t g) {
+    redo_store<MODE, SOA>(io, g, dist_coxa_frame<false>(L, tab, redo_load<SOA>(L, io, g)));
 }
 
 // full evaluation of one point of the tile in shared memory, in place (ring overflow only); the
@@ -438,10 +492,9 @@ __device__ __noinline__ void tile_point_full(const LegPlan& L, const SectorTable
 template <int MODE, bool SOA>
 __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
     one_leg_tier_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
-                        const AtlasView atlas, const VolumeView vol, const float* __restrict__ in_x,
-                        const float* __restrict__ in_y, const float* __restrict__ in_z,
-                        float* __restrict__ out_x, float* __restrict__ out_y, float* __restrict__ out_z,
-                        uint8_t* __restrict__ out_flag, size_t n, int kshift) {
+                        const AtlasView atlas, const VolumeView vol, const __grid_constant__ RedoIo io,
+                        size_t n, int kshift, const int* __restrict__ gate, int gate_want) {
+    if (gate != nullptr && *gate != gate_want) return;  // the coherence probe chose the other sweep
     extern __shared__ __align__(128) unsigned char smem_raw[];
     auto& S = *reinterpret_cast<TierSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -456,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
     for (int i = tid; i < (kYawBins + 16) / 4; i += kThreads)
         reinterpret_cast<uint32_t*>(S.ycode)[i] = reinterpret_cast<const uint32_t*>(FT.code)[i];
     if (tid == 0) {
-        for (int k = 0; k < 3; k++) S.cnt2[k] = S.cnt3[k] = 0;
+        for (int k = 0; k < 9; k++) (&S.cnt[0][0])[k] = 0;
         for (int s = 0; s < kStages; s++) bulk::mbar_init(&S.full[s], 1);
         bulk::fence_barrier_init();
     }
@@ -471,12 +524,12 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
         const size_t first = tile * kTile;
         if (SOA) {
             bulk::mbar_expect_tx(&S.full[stage], 3 * cnt * 4);
-            bulk::load(&S.in[stage][0], in_x + first, cnt * 4, &S.full[stage]);
-            bulk::load(&S.in[stage][kTile], in_y + first, cnt * 4, &S.full[stage]);
-            bulk::load(&S.in[stage][2 * kTile], in_z + first, cnt * 4, &S.full[stage]);
+            bulk::load(&S.in[stage][0], io.in_x + first, cnt * 4, &S.full[stage]);
+            bulk::load(&S.in[stage][kTile], io.in_y + first, cnt * 4, &S.full[stage]);
+            bulk::load(&S.in[stage][2 * kTile], io.in_z + first, cnt * 4, &S.full[stage]);
         } else {
             bulk::mbar_expect_tx(&S.full[stage], cnt * 12);
-            bulk::load(&S.in[stage][0], in_x + 3 * first, cnt * 12, &S.full[stage]);
+            bulk::load(&S.in[stage][0], io.in_x + 3 * first, cnt * 12, &S.full[stage]);
         }
     };
     // Tiles are dealt to the CTAs in chunks of 2^kshift consecutive tiles: neighbouring tiles of a
@@ -495,38 +548,24 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
     const FastView fview{S.ypair, S.ycode};
     const YawSol* sols = reinterpret_cast<const YawSol*>(S.ypair);
     uint32_t it = 0;
-    // ring bookkeeping, identical in every thread: accepted entries before this iteration (base),
-    // before the previous one (elig: their tiles' stores have completed), redone so far (head),
-    // and the room the ring had when this iteration's pushes began (room)
-    uint32_t base2 = 0, elig2 = 0, head2 = 0, room2 = kRingCap;
-    uint32_t base3 = 0, elig3 = 0, head3 = 0, room3 = kRingCap;
+    Ring<kRingA> ra;
+    Ring<kRingB> rb;
+    Ring<kRingC> rc;
     int rot = 0;  // it % 3
 
-    auto global_index = [&](uint32_t entry, uint32_t it_now) -> size_t {
-        const uint32_t age = (it_now - (entry >> 10)) & 0x3fffffu;
-        return tile_of(it_now - age) * kTile + (entry & 1023u);
+    constexpr uint32_t kIterMask = (1u << kEntryIterBits) - 1u;
+    auto global_index = [&](uint32_t entry) -> size_t {
+        const uint32_t age = (it - (entry >> 15)) & kIterMask;
+        return tile_of(it - age) * kTile + (entry & 1023u);
     };
-    auto push2 = [&](uint32_t entry) -> bool {
-        const uint32_t k = atomicAdd(&S.cnt2[rot], 1u);
-        if (k >= room2) return false;
-        S.ring2[(base2 + k) & (kRingCap - 1)] = entry;
-        return true;
+    auto do_c = [&](uint32_t entry) { redo_full<MODE, SOA>(L, S.table, io, global_index(entry)); };
+    auto do_b = [&](uint32_t entry) {
+        if (!redo_fast<MODE, SOA>(L, fview, atlas, S.winners, io, global_index(entry)))
+            if (!rc.push(S.ring_c, &S.cnt[2][rot], entry)) do_c(entry);
     };
-    auto push3 = [&](uint32_t entry) -> bool {
-        const uint32_t k = atomicAdd(&S.cnt3[rot], 1u);
-        if (k >= room3) return false;
-        S.ring3[(base3 + k) & (kRingCap - 1)] = entry;
-        return true;
+    auto do_a = [&](uint32_t entry) {
+        redo_choice<MODE, SOA>(L, S.table, sols, (entry >> 10) & 31u, io, global_index(entry));
     };
-    auto redo3 = [&](uint32_t entry) {
-        redo_point<MODE, SOA>(L, S.table, in_x, in_y, in_z, out_x, out_y, out_z, out_flag, global_index(entry, it));
-    };
-    auto redo2 = [&](uint32_t entry) {
-        if (!redo_point_fast<MODE, SOA>(L, fview, atlas, S.winners, in_x, in_y, in_z, out_x, out_y, out_z,
-                                        out_flag, global_index(entry, it)))
-            if (!push3(entry)) redo3(entry);
-    };
-    auto min_u = [](uint32_t a, uint32_t b) { return a < b ? a : b; };
 
     for (size_t tile = tile_of(0); tile < n_tiles; tile = tile_of(++it)) {
         const int stage = it % kStages;
@@ -537,22 +576,23 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
 
         // counters of the previous iteration are final since its tile barrier
         const int rot_prev = rot == 0 ? 2 : rot - 1;
-        elig2 = base2, elig3 = base3;
-        base2 += min_u(S.cnt2[rot_prev], room2);
-        base3 += min_u(S.cnt3[rot_prev], room3);
-        // room BEFORE this iteration's redo: slots freed now are still being read by slower warps
-        // (there is no barrier between the redo loops and the pushes of faster warps)
-        room2 = kRingCap - (base2 - head2);
-        room3 = kRingCap - (base3 - head3);
+        ra.advance(S.cnt[0][rot_prev]);
+        rb.advance(S.cnt[1][rot_prev]);
+        rc.advance(S.cnt[2][rot_prev]);
 #pragma unroll 1
-        while (elig3 - head3 >= (uint32_t)kThreads) {
-            redo3(S.ring3[(head3 + tid) & (kRingCap - 1)]);
-            head3 += kThreads;
+        while (rc.elig - rc.head >= (uint32_t)kThreads) {
+            do_c(S.ring_c[(rc.head + tid) & (kRingC - 1)]);
+            rc.head += kThreads;
         }
 #pragma unroll 1
-        while (elig2 - head2 >= (uint32_t)kThreads) {
-            redo2(S.ring2[(head2 + tid) & (kRingCap - 1)]);
-            head2 += kThreads;
+        while (rb.elig - rb.head >= (uint32_t)kThreads) {
+            do_b(S.ring_b[(rb.head + tid) & (kRingB - 1)]);
+            rb.head += kThreads;
+        }
+#pragma unroll 1
+        while (ra.elig - ra.head >= (uint32_t)kThreads) {
+            do_a(S.ring_a[(ra.head + tid) & (kRingA - 1)]);
+            ra.head += kThreads;
         }
 
         auto load_pt = [&](int i, float& x, float& y, float& z) {
@@ -607,10 +647,11 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
             store3(i, r.dx, r.dy, r.dz);
             flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
         };
-        auto park = [&](int i, int why) {
-            const uint32_t entry = (it << 10) | (uint32_t)i;
-            if (why == 1 && push2(entry)) return;
-            if (push3(entry)) return;
+        auto park = [&](int i, int why, unsigned cube) {
+            const uint32_t entry = (it << 15) | ((cube & 31u) << 10) | (uint32_t)i;
+            if (why == 2 && ra.push(S.ring_a, &S.cnt[0][rot], entry)) return;
+            if (why == 1 && rb.push(S.ring_b, &S.cnt[1][rot], entry)) return;
+            if (rc.push(S.ring_c, &S.cnt[2][rot], entry)) return;
             tile_point_full<MODE, SOA>(L, S.table, in, flag, i);
         };
 #pragma unroll 1
@@ -626,27 +667,27 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
             const int sj = dist_choice<true>(L, sols, cj, atlas, S.winners, pj, &rj);
             if (si == 0) store_pt(i, ri);
             if ((sj == 0) & has_j) store_pt(j, rj);
-            if (si != 0) park(i, si);
-            if ((sj != 0) & has_j) park(j, sj);
+            if (si != 0) park(i, si, ci);
+            if ((sj != 0) & has_j) park(j, sj, cj);
         }
 
         bulk::fence_proxy_async();
         if (tid == 0) {
             bulk::wait_group<0>();  // every committed store has COMPLETED: parked points of those tiles may be redone
             const int rot_next = rot == 2 ? 0 : rot + 1;
-            S.cnt2[rot_next] = 0, S.cnt3[rot_next] = 0;
+            S.cnt[0][rot_next] = 0, S.cnt[1][rot_next] = 0, S.cnt[2][rot_next] = 0;
         }
         __syncthreads();
         if (tid == 0) {
             const size_t first = tile * kTile;
             if (SOA) {
-                bulk::store(out_x + first, in, cnt * 4);
-                bulk::store(out_y + first, in + kTile, cnt * 4);
-                bulk::store(out_z + first, in + 2 * kTile, cnt * 4);
+                bulk::store(io.out_x + first, in, cnt * 4);
+                bulk::store(io.out_y + first, in + kTile, cnt * 4);
+                bulk::store(io.out_z + first, in + 2 * kTile, cnt * 4);
             } else {
-                bulk::store(out_x + 3 * first, in, cnt * 12);
+                bulk::store(io.out_x + 3 * first, in, cnt * 12);
             }
-            if (out_flag) bulk::store(out_flag + first, flag, cnt);
+            if (io.out_flag) bulk::store(io.out_flag + first, flag, cnt);
             bulk::commit_group();
             const size_t next = tile_of(it + kPrefetch);
             if (next < n_tiles) issue_load(next, (int)((it + kPrefetch) % kStages));
@@ -658,29 +699,34 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
     {
         const int rot_prev = rot == 0 ? 2 : rot - 1;
         if (it) {
-            base2 += min_u(S.cnt2[rot_prev], room2);
-            base3 += min_u(S.cnt3[rot_prev], room3);
+            ra.advance(S.cnt[0][rot_prev]);
+            rb.advance(S.cnt[1][rot_prev]);
+            rc.advance(S.cnt[2][rot_prev]);
         }
 #pragma unroll 1
-        for (; head3 < base3; head3 += kThreads)
-            if (head3 + tid < base3) redo3(S.ring3[(head3 + tid) & (kRingCap - 1)]);
-        head3 = base3;
-        room3 = kRingCap;  // ring 3 is empty; tier-2 failures of the drain go to cnt3[rot] (zero so far)
+        for (; ra.head < ra.base; ra.head += kThreads)
+            if (ra.head + tid < ra.base) do_a(S.ring_a[(ra.head + tid) & (kRingA - 1)]);
+#pragma unroll 1
+        for (; rc.head < rc.base; rc.head += kThreads)
+            if (rc.head + tid < rc.base) do_c(S.ring_c[(rc.head + tid) & (kRingC - 1)]);
+        // ring C is empty now; what ring B's drain cannot decide goes to cnt[2][rot] (zero so far)
+        rc.head = rc.base, rc.room = kRingC;
         __syncthreads();
 #pragma unroll 1
-        for (; head2 < base2; head2 += kThreads)
-            if (head2 + tid < base2) redo2(S.ring2[(head2 + tid) & (kRingCap - 1)]);
+        for (; rb.head < rb.base; rb.head += kThreads)
+            if (rb.head + tid < rb.base) do_b(S.ring_b[(rb.head + tid) & (kRingB - 1)]);
         __syncthreads();
-        base3 += min_u(S.cnt3[rot], room3);
+        const unsigned late = S.cnt[2][rot];
+        rc.base += late < rc.room ? late : rc.room;
 #pragma unroll 1
-        for (; head3 < base3; head3 += kThreads)
-            if (head3 + tid < base3) redo3(S.ring3[(head3 + tid) & (kRingCap - 1)]);
+        for (; rc.head < rc.base; rc.head += kThreads)
+            if (rc.head + tid < rc.base) do_c(S.ring_c[(rc.head + tid) & (kRingC - 1)]);
     }
 
     // the last n % 16 points bypass the bulk engine
     if (blockIdx.x == 0) {
         const size_t i = n_bulk + tid;
-        if (i < n) redo_point<MODE, SOA>(L, S.table, in_x, in_y, in_z, out_x, out_y, out_z, out_flag, i);
+        if (i < n) redo_full<MODE, SOA>(L, S.table, io, i);
     }
 }
 
@@ -800,7 +846,8 @@ int sm_count() {
 template <int MODE, bool SOA, bool GENERIC, bool FAST, bool TEX>
 cudaError_t launch_stream_impl(const LegPlan& plan, const FastTables& ft, const AtlasView& atlas,
                                const float* ix, const float* iy, const float* iz, float* ox, float* oy,
-                               float* oz, uint8_t* flag, size_t n, cudaStream_t stream) {
+                               float* oz, uint8_t* flag, size_t n, cudaStream_t stream,
+                               const int* gate = nullptr, int gate_want = 0) {
     auto kernel = one_leg_stream_kernel<MODE, SOA, GENERIC, FAST, TEX>;
     constexpr size_t smem = sizeof(StreamSmem<MODE, FAST>);
     // per-device: the attribute belongs to the device's copy of the function
@@ -821,7 +868,8 @@ cudaError_t launch_stream_impl(const LegPlan& plan, const FastTables& ft, const 
     size_t grid = (size_t)sm_count() * ctas_per_sm;
     if (tiles < grid) grid = tiles;
     if (grid == 0) grid = 1;
-    kernel<<<(unsigned)grid, kThreads, smem, stream>>>(plan, ft, atlas, ix, iy, iz, ox, oy, oz, flag, n);
+    kernel<<<(unsigned)grid, kThreads, smem, stream>>>(plan, ft, atlas, ix, iy, iz, ox, oy, oz, flag, n, gate,
+                                                       gate_want);
     return cudaGetLastError();
 }
 
@@ -835,7 +883,8 @@ int tier_chunk_shift_max() {
 template <int MODE, bool SOA>
 cudaError_t launch_tier_impl(const LegPlan& plan, const FastTables& ft, const AtlasView& atlas,
                              const VolumeView& vol, const float* ix, const float* iy, const float* iz,
-                             float* ox, float* oy, float* oz, uint8_t* flag, size_t n, cudaStream_t stream) {
+                             float* ox, float* oy, float* oz, uint8_t* flag, size_t n, cudaStream_t stream,
+                             const int* gate, int gate_want) {
     auto kernel = one_leg_tier_kernel<MODE, SOA>;
     constexpr size_t smem = sizeof(TierSmem);
     static int ctas_per_sm_dev[64] = {0};
@@ -857,14 +906,57 @@ cudaError_t launch_tier_impl(const LegPlan& plan, const FastTables& ft, const At
     // chunks of up to 8 consecutive tiles per CTA, fewer on small sweeps (keep >= 16 chunks per CTA)
     int kshift = 0;
     while (kshift < tier_chunk_shift_max() && (tiles >> (kshift + 1)) >= grid * 16) kshift++;
-    kernel<<<(unsigned)grid, kThreads, smem, stream>>>(plan, ft, atlas, vol, ix, iy, iz, ox, oy, oz, flag, n, kshift);
+    const RedoIo io{ix, iy, iz, ox, oy, oz, flag};
+    kernel<<<(unsigned)grid, kThreads, smem, stream>>>(plan, ft, atlas, vol, io, n, kshift, gate, gate_want);
     return cudaGetLastError();
 }
 
-// LRM_CHOICE_VOLUME=0 keeps the two-tier sweep (dist_fast + full evaluation) for A/B measurements
-bool choice_volume_enabled() {
-    const char* e = getenv("LRM_CHOICE_VOLUME");  // read per launch: tools switch it inside one process
-    return !(e && e[0] == '0');
+// Which sweep suits the input?  The tiered sweep adds a fetch from the 3-D choice volume (tens of
+// MB): a win when neighbouring points of the array are neighbours in space (lattices, scan lines,
+// sorted clouds: the fetches of a warp share a few sectors), a loss on shuffled clouds, where every
+// fetch is its own DRAM sector.  256 pairs of consecutive points spread over the array vote; the
+// verdict goes to a device word that both sweeps read first — the one that is not chosen returns
+// at once.  No host synchronisation: device-pointer calls stay asynchronous.
+template <bool SOA>
+__global__ void coherence_probe_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                       const float* __restrict__ z, size_t n, float near_mm, int* verdict) {
+    const size_t s = n < 2 ? 0 : (size_t)threadIdx.x * ((n - 2) / blockDim.x);
+    const size_t t = s + 1 < n ? s + 1 : s;
+    float dx, dy, dz;
+    if (SOA) {
+        dx = x[s] - x[t], dy = y[s] - y[t], dz = z[s] - z[t];
+    } else {
+        dx = x[3 * s] - x[3 * t], dy = x[3 * s + 1] - x[3 * t + 1], dz = x[3 * s + 2] - x[3 * t + 2];
+    }
+    const bool near = fmaf(dx, dx, fmaf(dy, dy, dz * dz)) < near_mm * near_mm;
+    const int votes = __syncthreads_count(near);
+    if (threadIdx.x == 0) *verdict = (4 * votes >= 3 * (int)blockDim.x) ? 1 : 0;
+}
+
+// verdict words: a small per-device pool handed out round-robin (a word is reused 4096 launches later)
+int* next_verdict_word() {
+    constexpr int kWords = 4096;
+    static int* pool[64] = {nullptr};
+    static std::atomic<unsigned> next{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int*& p = pool[dev & 63];
+    if (p == nullptr && cudaMalloc((void**)&p, kWords * sizeof(int)) != cudaSuccess) {
+        p = nullptr;
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p + (next.fetch_add(1u, std::memory_order_relaxed) % kWords);
+}
+
+// LRM_CHOICE_VOLUME: 0 = always the two-tier sweep (dist_fast + full evaluation), 1 = always the
+// tiered sweep, unset = decided per launch by the coherence probe.  Read per launch: tools switch
+// it inside one process.
+int choice_volume_mode() {
+    const char* e = getenv("LRM_CHOICE_VOLUME");
+    if (e && e[0] == '0') return 0;
+    if (e && e[0] == '1') return 1;
+    return 2;
 }
 
 // LRM_ATLAS_TEX=0 selects plain loads from the blocked copy of the atlas instead of the texture
@@ -913,11 +1005,25 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
         cudaError_t e = get_plane_atlas(plan, stream, &atlas, &ft);
         if (e != cudaSuccess) return e;
         if constexpr (kDist) {
-            if (atlas_through_texture() && choice_volume_enabled() && ft.both_unsat == 0) {
+            // ring entries of the tiered sweep hold a 17-bit per-CTA iteration count
+            const int vmode = choice_volume_mode();
+            if (atlas_through_texture() && vmode != 0 && ft.both_unsat == 0 &&
+                n / kTile / (size_t)sm_count() < (size_t(1) << (kEntryIterBits - 1))) {
                 VolumeView vol;
                 e = get_choice_volume(plan, stream, &vol);
+                int* verdict = (e == cudaSuccess && vmode == 2) ? next_verdict_word() : nullptr;
+                if (e == cudaSuccess && vmode == 2 && verdict != nullptr) {
+                    // "near" = within two cubes of the volume
+                    coherence_probe_kernel<SOA><<<1, 256, 0, stream>>>(ix, iy, iz, n, 2.0f / vol.inv_cell, verdict);
+                    e = launch_tier_impl<MODE, SOA>(plan, ft, atlas, vol, ix, iy, iz, ox, oy, oz, flag, n, stream,
+                                                    verdict, 1);
+                    if (e != cudaSuccess) return e;
+                    return launch_stream_impl<MODE, SOA, false, kDist, kDist>(plan, ft, atlas, ix, iy, iz, ox, oy,
+                                                                              oz, flag, n, stream, verdict, 0);
+                }
                 if (e == cudaSuccess)
-                    return launch_tier_impl<MODE, SOA>(plan, ft, atlas, vol, ix, iy, iz, ox, oy, oz, flag, n, stream);
+                    return launch_tier_impl<MODE, SOA>(plan, ft, atlas, vol, ix, iy, iz, ox, oy, oz, flag, n, stream,
+                                                       nullptr, 0);
                 (void)cudaGetLastError();  // no memory for the volume: the two-tier sweep still works
             }
         }

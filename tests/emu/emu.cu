@@ -130,7 +130,7 @@ size_t emu_dist_atlas(const float* xyz, size_t n, const lrm_leg_t* leg, const fl
 
 // The three-tier distance sweep as the streaming kernel runs it: choice volume (dist_choice) ->
 // dist_fast -> full evaluation.  Cube bytes are computed on demand with the very function the
-// device build kernel uses (choice_cell_byte).  tiers[0..2] = points decided by each tier.
+// device build kernel uses (choice_cell_byte).  tiers[0..3] = points decided by tier 1, dist_fast, dist_choice_clamp, the full evaluation.
 void emu_dist_choice(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, int dim,
                      float cell, float vol_h, int vol_dim, float* out_vec, uint8_t* out_flag,
                      uint8_t* out_reach, size_t* tiers, uint8_t* out_tier) {
@@ -155,7 +155,7 @@ void emu_dist_choice(const float* xyz, size_t n, const lrm_leg_t* leg, const flo
     const lrm::YawSol* sols = reinterpret_cast<const lrm::YawSol*>(ft.pair);
     std::unordered_map<uint64_t, unsigned char> cubes;
     const float vo = 0.5f * vol_dim, vinv = 1.0f / vol_h;
-    tiers[0] = tiers[1] = tiers[2] = 0;
+    tiers[0] = tiers[1] = tiers[2] = tiers[3] = 0;
     for (size_t i = 0; i < n; i++) {
         const lrm::CoxaPoint p = lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
         const float fx = fmaf(p.x, vinv, vo), fy = fmaf(p.y, vinv, vo), fz = fmaf(p.z, vinv, vo);
@@ -174,11 +174,14 @@ void emu_dist_choice(const float* xyz, size_t n, const lrm_leg_t* leg, const flo
         lrm::DistResult r;
         int tier = 0;
         const int st = lrm::dist_choice<false>(L, sols, cube, A, win, p, &r);
-        if (st != 0) {
+        if (st == 2) {  // cube certified, plane cell not: the chosen solution, explicit plane evaluation
+            lrm::dist_choice_clamp(L, tab, sols, cube, p, &r);
+            tier = 2;
+        } else if (st == 1) {
             tier = 1;
-            if (st == 2 || !lrm::dist_fast<false>(L, F, A, win, p, &r)) {
+            if (!lrm::dist_fast<false>(L, F, A, win, p, &r)) {
                 r = lrm::dist_coxa_frame<false>(L, tab, p);
-                tier = 2;
+                tier = 3;
             }
         }
         tiers[tier]++;

@@ -192,7 +192,7 @@ def test_choice_volume_never_changes_a_result(emu, port):
         fl = np.zeros(len(pts), np.uint8)
         rf = np.zeros(len(pts), np.uint8)
         tier = np.zeros(len(pts), np.uint8)
-        tiers = (ctypes.c_size_t * 3)()
+        tiers = (ctypes.c_size_t * 4)()
         emu.emu_dist_choice(pts.ctypes.data, len(pts), leg.ctypes.data, q.ctypes.data, 2048, 1.0, cell,
                             int(1536 / cell), out.ctypes.data, fl.ctypes.data, rf.ctypes.data, tiers,
                             tier.ctypes.data)

@@ -33,7 +33,7 @@ if "--traffic" in sys.argv:
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
     rd = float(r[hdr.index("dram__bytes_read.sum")]) * scale[units[hdr.index("dram__bytes_read.sum")]]
     wr = float(r[hdr.index("dram__bytes_write.sum")]) * scale[units[hdr.index("dram__bytes_write.sum")]]
-    json.dump({"kernel": "one_leg_stream_kernel<both,aos,fast,tex>", "points_per_launch": pts, "dram_bytes_read": rd,
+    json.dump({"kernel": r[ik].split("(")[0].strip(), "points_per_launch": pts, "dram_bytes_read": rd,
                "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr, "dram_bytes_per_point": round((rd + wr) / pts, 3),
                "source": f"{out} (ncu --set full, bench.py default config)"},
               open("profiles/traffic.json", "w"), indent=1)

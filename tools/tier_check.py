@@ -19,8 +19,11 @@ else:
     lrm.make_lattice(pts, lo, step, dims, 0, n)
 out = {"points": n}
 res = {}
-for name, env in (("two_tier", "0"), ("three_tier", "1")):
-    os.environ["LRM_CHOICE_VOLUME"] = env
+for name, env in (("two_tier", "0"), ("three_tier", "1"), ("auto", None)):
+    if env is None:
+        os.environ.pop("LRM_CHOICE_VOLUME", None)
+    else:
+        os.environ["LRM_CHOICE_VOLUME"] = env
     flags = torch.empty(n, dtype=torch.uint8, device="cuda")
     vec = torch.empty((n, 3), dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
@@ -57,4 +60,6 @@ out["max_vec_diff_mm"] = float(diff.max())
 out["points_over_1e-3"] = int((diff > 1e-3).sum())
 out["dist_mode_max_diff_mm"] = float((da - db).abs().max())
 out["reachable"] = int(fb.sum())
+fc, vc, dc = res["auto"]
+out["auto_equal"] = bool(torch.equal(fc, fa) and torch.equal(vc, va) and torch.equal(dc, da))
 print(json.dumps(out))
