@@ -43,9 +43,10 @@ cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView*
                             FastTables* tables);
 
 // Choice volume of a plan whose atlas is cached (get_plane_atlas first): 3-D texture of the winning
-// coxa solution per cube, built on first request (plane_atlas.cu).
+// coxa solution per cube (plane_atlas.cu).  Built in the background on first request: until it is
+// there the call returns cudaErrorNotReady (wait = false) or blocks (wait = true).
 struct VolumeView;
-cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeView* view);
+cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeView* view, bool wait);
 
 // Multi-leg positionability (positionability.cu).  All pointers are device pointers.
 struct PositParams {

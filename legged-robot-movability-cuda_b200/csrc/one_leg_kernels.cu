@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
     auto& S = *reinterpret_cast<TierSmem*>(smem_raw);
     const int tid = threadIdx.x;
     const size_t n_bulk = n & ~size_t(15);
-    const size_t n_tiles = (n_bulk + kTile - 1) / kTile;
+    const uint32_t n_tiles = (uint32_t)((n_bulk + kTile - 1) / kTile);  // the launcher keeps n below 2^40
     constexpr int kStages = 3;
 
     fill_sector_table(L, &S.table, tid, kThreads);
@@ -515,13 +515,12 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
     }
     __syncthreads();
 
-    auto tile_count = [&](size_t tile) -> uint32_t {
-        const size_t first = tile * kTile;
-        return (uint32_t)((n_bulk - first < (size_t)kTile) ? (n_bulk - first) : kTile);
+    auto tile_count = [&](uint32_t tile) -> uint32_t {
+        return tile + 1u < n_tiles ? (uint32_t)kTile : (uint32_t)(n_bulk - (size_t)tile * kTile);
     };
-    auto issue_load = [&](size_t tile, int stage) {
+    auto issue_load = [&](uint32_t tile, int stage) {
         const uint32_t cnt = tile_count(tile);
-        const size_t first = tile * kTile;
+        const size_t first = (size_t)tile * kTile;
         if (SOA) {
             bulk::mbar_expect_tx(&S.full[stage], 3 * cnt * 4);
             bulk::load(&S.in[stage][0], io.in_x + first, cnt * 4, &S.full[stage]);
@@ -535,12 +534,12 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
     // Tiles are dealt to the CTAs in chunks of 2^kshift consecutive tiles: neighbouring tiles of a
     // lattice sweep are neighbouring columns, whose points fall into the same cubes and plane
     // cells, so a CTA's texture fetches keep hitting lines it has just brought in.
-    auto tile_of = [&](uint32_t iter) -> size_t {
-        return ((((size_t)(iter >> kshift) * gridDim.x + blockIdx.x)) << kshift) + (iter & ((1u << kshift) - 1u));
+    auto tile_of = [&](uint32_t iter) -> uint32_t {
+        return (((iter >> kshift) * gridDim.x + blockIdx.x) << kshift) + (iter & ((1u << kshift) - 1u));
     };
     if (tid == 0) {
         for (int s = 0; s < kPrefetch; s++) {
-            const size_t tile = tile_of((uint32_t)s);
+            const uint32_t tile = tile_of((uint32_t)s);
             if (tile < n_tiles) issue_load(tile, s);
         }
     }
@@ -551,12 +550,13 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
     Ring<kRingA> ra;
     Ring<kRingB> rb;
     Ring<kRingC> rc;
-    int rot = 0;  // it % 3
+    int rot = 0;           // it % 3: also the tile buffer of this iteration
+    uint32_t parity = 0;   // (it / 3) & 1: phase of that buffer's mbarrier
 
     constexpr uint32_t kIterMask = (1u << kEntryIterBits) - 1u;
     auto global_index = [&](uint32_t entry) -> size_t {
         const uint32_t age = (it - (entry >> 15)) & kIterMask;
-        return tile_of(it - age) * kTile + (entry & 1023u);
+        return (size_t)tile_of(it - age) * kTile + (entry & 1023u);
     };
     auto do_c = [&](uint32_t entry) { redo_full<MODE, SOA>(L, S.table, io, global_index(entry)); };
     auto do_b = [&](uint32_t entry) {
@@ -567,11 +567,10 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
         redo_choice<MODE, SOA>(L, S.table, sols, (entry >> 10) & 31u, io, global_index(entry));
     };
 
-    for (size_t tile = tile_of(0); tile < n_tiles; tile = tile_of(++it)) {
-        const int stage = it % kStages;
+    for (uint32_t tile = tile_of(0); tile < n_tiles; tile = tile_of(++it)) {
         const uint32_t cnt = tile_count(tile);
-        bulk::mbar_wait(&S.full[stage], (it / kStages) & 1);
-        float* in = S.in[stage];
+        bulk::mbar_wait(&S.full[rot], parity);
+        float* in = S.in[rot];
         uint8_t* flag = S.flag[it & 1];
 
         // counters of the previous iteration are final since its tile barrier
@@ -679,7 +678,7 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
         }
         __syncthreads();
         if (tid == 0) {
-            const size_t first = tile * kTile;
+            const size_t first = (size_t)tile * kTile;
             if (SOA) {
                 bulk::store(io.out_x + first, in, cnt * 4);
                 bulk::store(io.out_y + first, in + kTile, cnt * 4);
@@ -689,10 +688,12 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
             }
             if (io.out_flag) bulk::store(io.out_flag + first, flag, cnt);
             bulk::commit_group();
-            const size_t next = tile_of(it + kPrefetch);
-            if (next < n_tiles) issue_load(next, (int)((it + kPrefetch) % kStages));
+            static_assert(kPrefetch == 2 && kStages == 3, "the buffer two tiles ahead is the previous one");
+            const uint32_t next = tile_of(it + kPrefetch);
+            if (next < n_tiles) issue_load(next, rot == 0 ? 2 : rot - 1);
         }
         rot = rot == 2 ? 0 : rot + 1;
+        parity ^= (rot == 0) ? 1u : 0u;
     }
     if (tid == 0) bulk::wait_group<0>();
     __syncthreads();  // every store has completed, every counter is final
@@ -1008,9 +1009,9 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
             // ring entries of the tiered sweep hold a 17-bit per-CTA iteration count
             const int vmode = choice_volume_mode();
             if (atlas_through_texture() && vmode != 0 && ft.both_unsat == 0 &&
-                n / kTile / (size_t)sm_count() < (size_t(1) << (kEntryIterBits - 1))) {
+                n / kTile / (size_t)sm_count() < (size_t(1) << (kEntryIterBits - 1)) && n < (size_t(1) << 40)) {
                 VolumeView vol;
-                e = get_choice_volume(plan, stream, &vol);
+                e = get_choice_volume(plan, stream, &vol, /*wait=*/vmode == 1);
                 int* verdict = (e == cudaSuccess && vmode == 2) ? next_verdict_word() : nullptr;
                 if (e == cudaSuccess && vmode == 2 && verdict != nullptr) {
                     // "near" = within two cubes of the volume
@@ -1024,7 +1025,7 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
                 if (e == cudaSuccess)
                     return launch_tier_impl<MODE, SOA>(plan, ft, atlas, vol, ix, iy, iz, ox, oy, oz, flag, n, stream,
                                                        nullptr, 0);
-                (void)cudaGetLastError();  // no memory for the volume: the two-tier sweep still works
+                (void)cudaGetLastError();  // volume still being built, or no memory for it: the two-tier sweep gives the same bits
             }
         }
         if (atlas_through_texture())

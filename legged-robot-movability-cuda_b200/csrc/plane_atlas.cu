@@ -76,8 +76,23 @@ struct Entry {
     int vol_dim = 0;
     float vol_cell = 0.f;
     bool vol_ready = false;
+    // a build in flight on the entry's own stream (see get_choice_volume)
+    bool vol_building = false;
+    cudaStream_t vol_stream = nullptr;
+    cudaEvent_t vol_done = nullptr;
+    unsigned char* vol_linear = nullptr;  // staging copy, freed once the build has finished
 };
+// a build in flight must finish before its buffers or its plan's atlas go away
+void settle_volume(Entry* c) {
+    if (c->vol_building) {
+        cudaEventSynchronize(c->vol_done);
+        c->vol_building = false;
+    }
+    if (c->vol_linear) cudaFree(c->vol_linear);
+    c->vol_linear = nullptr;
+}
 void release_volume(Entry* c) {
+    settle_volume(c);
     if (c->vol_tex) cudaDestroyTextureObject(c->vol_tex);
     if (c->vol_array) cudaFreeArray(c->vol_array);
     c->vol_tex = 0, c->vol_array = nullptr, c->vol_ready = false, c->vol_dim = 0;
@@ -147,6 +162,7 @@ cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView*
             if (e != cudaSuccess) return e;
         }
         victim->used = false;
+        settle_volume(victim);
         victim->vol_ready = false;  // the volume belongs to the evicted plan: rebuilt on request
         if (!victim->cells) {
             e = allocate(victim);
@@ -198,7 +214,12 @@ void volume_shape(int* dim, float* cell) {
     *dim = d, *cell = c;
 }
 
-cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeView* view) {
+// wait = false: a volume that is not built yet is built in the BACKGROUND, on the entry's own
+// stream, and cudaErrorNotReady is returned — the caller runs the two-tier sweep meanwhile (same
+// results, bit for bit), so a one-off call never waits ~10 ms for a table it would use once;
+// calls that come after the build has finished get the volume.  wait = true blocks until it is there.
+cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeView* view, bool wait) {
+    (void)stream;
     std::lock_guard<std::mutex> lock(g_mutex);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -210,8 +231,14 @@ cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeVi
     int dim;
     float cell;
     volume_shape(&dim, &cell);
-    if (!hit->vol_ready) {
+    if (!hit->vol_ready && !hit->vol_building) {
         if (hit->vol_array && hit->vol_dim != dim) release_volume(hit);
+        if (!hit->vol_stream) {
+            e = cudaStreamCreateWithFlags(&hit->vol_stream, cudaStreamNonBlocking);
+            if (e != cudaSuccess) return e;
+            e = cudaEventCreateWithFlags(&hit->vol_done, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
         if (!hit->vol_array) {
             const cudaChannelFormatDesc fmt = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
             e = cudaMalloc3DArray(&hit->vol_array, &fmt, make_cudaExtent(dim, dim, dim));
@@ -232,32 +259,50 @@ cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeVi
                 return e;
             }
             hit->vol_dim = dim;
+        } else {
+            // a sweep of the evicted plan may still read the array that is about to be rewritten
+            e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) return e;
         }
-        // earlier sweeps on other streams may still read a volume being rebuilt for a new plan
-        e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) return e;
         const size_t bytes = (size_t)dim * dim * dim;
-        unsigned char* linear = nullptr;
-        e = cudaMalloc((void**)&linear, bytes);
+        e = cudaMalloc((void**)&hit->vol_linear, bytes);
         if (e != cudaSuccess) return e;
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        volume_build_kernel<<<sms * 16, 128, 0, stream>>>(plan, hit->tables, linear, dim, cell);
+        // the atlas build (caller's stream) has been synchronised by get_plane_atlas; the volume
+        // build only needs the plan and the host-built yaw tables
+        volume_build_kernel<<<sms * 16, 128, 0, hit->vol_stream>>>(plan, hit->tables, hit->vol_linear, dim, cell);
         e = cudaGetLastError();
         if (e == cudaSuccess) {
             cudaMemcpy3DParms cp;
             std::memset(&cp, 0, sizeof cp);
-            cp.srcPtr = make_cudaPitchedPtr(linear, (size_t)dim, (size_t)dim, (size_t)dim);
+            cp.srcPtr = make_cudaPitchedPtr(hit->vol_linear, (size_t)dim, (size_t)dim, (size_t)dim);
             cp.dstArray = hit->vol_array;
             cp.extent = make_cudaExtent(dim, dim, dim);
             cp.kind = cudaMemcpyDeviceToDevice;
-            e = cudaMemcpy3DAsync(&cp, stream);
+            e = cudaMemcpy3DAsync(&cp, hit->vol_stream);
         }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        cudaFree(linear);
-        if (e != cudaSuccess) return e;
+        if (e == cudaSuccess) e = cudaEventRecord(hit->vol_done, hit->vol_stream);
+        if (e != cudaSuccess) {
+            cudaStreamSynchronize(hit->vol_stream);
+            cudaFree(hit->vol_linear);
+            hit->vol_linear = nullptr;
+            return e;
+        }
         hit->vol_cell = cell;
+        hit->vol_building = true;
+    }
+    if (hit->vol_building) {
+        e = wait ? cudaEventSynchronize(hit->vol_done) : cudaEventQuery(hit->vol_done);
+        if (e == cudaErrorNotReady) {
+            (void)cudaGetLastError();
+            return cudaErrorNotReady;
+        }
+        if (e != cudaSuccess) return e;
+        hit->vol_building = false;
         hit->vol_ready = true;
+        cudaFree(hit->vol_linear);
+        hit->vol_linear = nullptr;
     }
     view->tex = hit->vol_tex;
     view->inv_cell = 1.0f / hit->vol_cell;

@@ -159,7 +159,7 @@ def test_soa_matches_aos(lrm):
     assert torch.equal(f3, lrm.reachability(dev, leg, q))
 
 
-def test_distance_lands_on_boundary_at_scale(lrm):
+def test_distance_lands_on_boundary_at_scale(lrm, sweep):
     """Size-independent property at 2e7 points: |d(p - d(p))| ~ 0 and the fused flag
     equals the stand-alone reach kernel's."""
     lo, step, dims = lrm.lattice_spec((-100, -400, -500), (600, 400, 200), (272, 272, 272))
@@ -219,6 +219,15 @@ def test_kernel_ms_is_reported(lrm):
     assert 0 < ms < 50
 
 
+@pytest.fixture(params=["two-tier", "tiered"])
+def sweep(request, monkeypatch):
+    """LRM_CHOICE_VOLUME (read per launch): 0 = the two-tier sweep (certified tables + full
+    evaluation), 1 = the tiered sweep through the choice volume, waiting for the volume instead of
+    letting it build in the background.  Unset, a coherence probe picks one per launch."""
+    monkeypatch.setenv("LRM_CHOICE_VOLUME", "0" if request.param == "two-tier" else "1")
+    return request.param
+
+
 # ---- the fast path (certified tables + deferred redo) only runs on sweeps of >= 4 Mi points -------
 def _sample_check(lrm, oracle, dev_pts, leg, q, label, n_sample=250_000, seed=0):
     """Fused + stand-alone distance on the whole device array, oracle on a random sample."""
@@ -245,7 +254,7 @@ def _sample_check(lrm, oracle, dev_pts, leg, q, label, n_sample=250_000, seed=0)
     return vec, fr
 
 
-def test_fast_path_parity_on_large_sweeps(lrm, oracle):
+def test_fast_path_parity_on_large_sweeps(lrm, oracle, sweep):
     """6 Mi-point clouds (bench box + far field), both robots, identity and tilted orientations."""
     g = torch.Generator(device="cuda").manual_seed(5)
     n = 6 * (1 << 20) + 37
@@ -257,7 +266,7 @@ def test_fast_path_parity_on_large_sweeps(lrm, oracle):
         _sample_check(lrm, oracle, pts, lrm.get_leg(robot, az), q, f"fast robot{robot} az{az}")
 
 
-def test_fast_path_with_every_point_parked(lrm, oracle):
+def test_fast_path_with_every_point_parked(lrm, oracle, sweep):
     """Points on / next to the coxa axis and on the yaw seam cannot be certified: the whole sweep
     goes through the deferred redo (ring wrap-around, partial last block, drain at the end)."""
     leg = lrm.get_M2_leg(0.0)
@@ -274,7 +283,7 @@ def test_fast_path_with_every_point_parked(lrm, oracle):
     assert bool(torch.isfinite(vec).all())
 
 
-def test_fast_path_soa_matches_aos_at_scale(lrm):
+def test_fast_path_soa_matches_aos_at_scale(lrm, sweep):
     g = torch.Generator(device="cuda").manual_seed(2)
     n = 5 * (1 << 20)
     pts = torch.rand((n, 3), device="cuda", generator=g) * 900.0 - 300.0
@@ -285,7 +294,7 @@ def test_fast_path_soa_matches_aos_at_scale(lrm):
     assert torch.equal(f2, fr) and torch.equal(torch.stack([dx, dy, dz], 1), vec)
 
 
-def test_golden_vectors_through_the_fast_path(lrm, oracle, golden):
+def test_golden_vectors_through_the_fast_path(lrm, oracle, golden, sweep):
     """The committed golden vectors (lattices, the bench slice, random clouds, 2 robots x 2 azimuths
     x 4 orientations) with the certified tables forced on for every size: the fast path and its
     deferred redo must meet the same bars as the plain kernels on the reference's own outputs."""
@@ -304,3 +313,33 @@ def test_golden_vectors_through_the_fast_path(lrm, oracle, golden):
                    f"fast ragged {n}")
     finally:
         lrm.set_fast_path_min_points(old)
+
+
+def test_every_sweep_returns_the_same_bits(lrm, monkeypatch):
+    """The two-tier sweep, the tiered sweep and the probe's own pick return identical bytes — on a
+    lattice slab (coherent: the probe picks the tiered sweep), on a shuffled cloud reaching beyond
+    the choice volume (the probe picks the two-tier sweep), and on points lying ON the reachability
+    edge (every plane cell uncertified: all three rings wrap and overflow)."""
+    leg = lrm.get_M2_leg(0.0)
+    n = 6 * (1 << 20) + 123
+    lo, step, dims = lrm.lattice_spec((-100, -400, -500), (600, 400, 200), (7, 1000, 1000))
+    lattice = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    lrm.make_lattice(lattice, lo, step, dims, 0, n)
+    g = torch.Generator(device="cuda").manual_seed(12)
+    cloud = torch.rand((n, 3), device="cuda", generator=g) * 2000.0 - 1000.0
+    monkeypatch.setenv("LRM_CHOICE_VOLUME", "0")
+    _, v = lrm.reach_dist(lattice, leg)
+    edge = (lattice - v).contiguous()
+    for name, pts in (("lattice", lattice), ("cloud", cloud), ("edge", edge)):
+        got = {}
+        for mode in ("0", "1", None):
+            if mode is None:
+                monkeypatch.delenv("LRM_CHOICE_VOLUME")
+            else:
+                monkeypatch.setenv("LRM_CHOICE_VOLUME", mode)
+            fr, vec = lrm.reach_dist(pts, leg)
+            d, f = lrm.distance(pts, leg)
+            got[mode] = (fr, vec, d, f)
+        for mode in ("1", None):
+            for a, b in zip(got["0"], got[mode]):
+                assert torch.equal(a, b), (name, mode)
