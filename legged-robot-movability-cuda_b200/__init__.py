@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblrm_b200.so")
+LIB_PATH = os.environ.get("LRM_B200_LIB") or os.path.join(_HERE, "liblrm_b200.so")   # override: measurement builds
 
 LRM_OK = 0
 

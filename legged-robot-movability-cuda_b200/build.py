@@ -41,7 +41,8 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB]
+    # LRM_NVCC_EXTRA: extra flags for measurement builds (e.g. "-DLRM_TIER_THREADS=192 -DLRM_TIER_TILE=768")
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("LRM_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB]
     cmd += ["-x", "cu"] + [os.path.join(CSRC, s) for s in SOURCES]
     cmd += ["-lcudart"]
     if verbose:

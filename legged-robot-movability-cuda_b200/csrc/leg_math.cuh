@@ -739,6 +739,8 @@ LRM_HD DistResult dist_coxa_frame(const LegPlan& L, const SectorTable& tab, cons
 struct FastView {
     const YawPair* pair;        // [kYawPairs]
     const unsigned char* code;  // [kYawBins + 1]
+    const int32_t* combo;       // [ncombo]: the yaw_combo each pair stands for (EXACT_YAW only)
+    int ncombo;
 };
 
 // Diamond angle bin of a unit direction: d = uy / (|ux| + |uy|) in the right half plane, mirrored
@@ -769,7 +771,10 @@ LRM_HD BranchResult fast_branch(const CoxaPoint p, const YawSol& s, float cs, fl
 // Straight-line on purpose (one exit, no early returns): a thread's two consecutive points can
 // then be interleaved by the compiler, so that their texture fetches overlap.  A point the tables
 // cannot certify runs to the end on harmless values and reports false.
-template <bool TEX, bool SKIP_B = true>
+// EXACT_YAW (the dense redo of the tiered sweep): a direction whose bin is uncertified — it holds
+// a decision boundary — has its yaw decisions evaluated for the point itself (yaw_combo: the very
+// tests the full evaluation runs) and mapped to its solution pair, instead of giving up.
+template <bool TEX, bool SKIP_B = true, bool EXACT_YAW = false>
 LRM_HD bool dist_fast(const LegPlan& L, const FastView& F, const AtlasView& A, const WinnerTable& W,
                       const CoxaPoint p, DistResult* out) {
     const float rho2 = fmaf(p.x, p.x, p.y * p.y);
@@ -780,6 +785,13 @@ LRM_HD bool dist_fast(const LegPlan& L, const FastView& F, const AtlasView& A, c
     ok = ok & ((unsigned)bin <= (unsigned)kYawBins);
     bin = ok ? bin : 0;
     unsigned code = F.code[bin];
+    if (EXACT_YAW) {
+        if (ok && code == kYawImpure) {
+            const int combo = yaw_combo(L, p.x, p.y);
+            for (int i = 0; i < F.ncombo; i++)
+                if (F.combo[i] == combo) code = (unsigned)i;
+        }
+    }
     ok = ok & (code != kYawImpure);
     code = ok ? code : 0u;
     const YawPair& pr = F.pair[code];
@@ -851,9 +863,13 @@ LRM_HD bool dist_fast(const LegPlan& L, const FastView& F, const AtlasView& A, c
 constexpr unsigned kVolPure = 0x80u;
 struct VolumeView {
     cudaTextureObject_t tex;  // 3-D texture of cube bytes (point sampling, border = 0)
-    float inv_cell, o;        // cube coordinates = p * inv_cell + o on every axis
+    float inv_cell, o, oy;    // cube coordinates = p * inv_cell + o (x, z), + oy (y)
     int dim;
 };
+// The grid is shifted by half a cube along y: the y = 0 plane (a decision boundary for every leg:
+// the sign of y picks the coxa limit of the limit-plane rule, and carries atan2f's signed-zero
+// rules) then cuts ONE layer of cubes through the middle instead of touching two.
+constexpr float kVolShiftY = 0.5f;
 
 // Both solutions of one point through the full evaluation, with what the certification needs.
 struct ChoiceProbe {
@@ -889,45 +905,73 @@ LRM_HD ChoiceProbe choice_probe(const LegPlan& L, const SectorTable& tab, const 
     return out;
 }
 
-// Cube byte of the cube [x0, x0+h] x [y0, y0+h] x [z0, z0+h] of the coxa frame.
-LRM_HD unsigned choice_cell_byte(const LegPlan& L, const SectorTable& tab, const FastTables& FT, float x0,
-                                 float y0, float z0, float h) {
+// Cube byte of the cube [x0, x0+h] x [y0, y0+h] x [z0, z0+h] of the coxa frame, in two steps so
+// that the device build can share the refinement of a cube among the lanes of a warp:
+// choice_cell_first decides everything the cube centre can decide, choice_cell_sub checks one of
+// the 4^3 sub-cubes.  choice_cell_byte is the serial composition (host emulation, reference).
+constexpr int kVolSub = 4;  // sub-cubes per axis of the refinement
+struct CellFirst {
+    unsigned byte;  // the cube byte if certified (after refinement, when refine is set), else 0
+    bool refine;    // the centre could not decide: all kVolSub^3 sub-cubes must pass choice_cell_sub
+    bool direct;    // the centre's choice (what every sub-cube must agree with)
+};
+LRM_HD float vol_pad(float h) {
     // the texture unit resolves cube coordinates to 1/256 of a cube; float rounding of the
     // coordinate itself is far below 0.01 mm
-    const float pad = h * (1.f / 64.f) + 0.01f;
+    return h * (1.f / 64.f) + 0.01f;
+}
+LRM_HD CellFirst choice_cell_first(const LegPlan& L, const SectorTable& tab, const FastTables& FT, float x0,
+                                   float y0, float z0, float h) {
+    CellFirst out;
+    out.byte = 0u, out.refine = false, out.direct = true;
+    const float pad = vol_pad(h);
     const float xa = x0 - pad, xb = x0 + h + pad, ya = y0 - pad, yb = y0 + h + pad;
-    if (ya <= 0.f && yb >= 0.f) return 0u;
+    if (ya <= 0.f && yb >= 0.f) return out;
     const int combo = yaw_combo(L, xa, ya);
     if (yaw_combo(L, xb, ya) != combo || yaw_combo(L, xa, yb) != combo || yaw_combo(L, xb, yb) != combo)
-        return 0u;
+        return out;
     int id = -1;
     for (int i = 0; i < FT.ncombo; i++)
         if (FT.combo[i] == combo) id = i;
-    if (id < 0 || FT.both_unsat) return 0u;
+    if (id < 0 || FT.both_unsat) return out;
     const bool has_a = (combo & 7) != kYawSkipped, has_b = (combo >> 3) != kYawSkipped;
-    if (!has_b) return kVolPure | ((unsigned)id << 1);
-    if (!has_a) return kVolPure | ((unsigned)id << 1) | 1u;
+    if (!has_b || !has_a) {
+        out.byte = kVolPure | ((unsigned)id << 1) | (has_b ? 1u : 0u);
+        return out;
+    }
     const float side = h + 2.f * pad;
     const float r0 = 0.8660255f * side;
     CoxaPoint c;
     c.x = xa + 0.5f * side, c.y = ya + 0.5f * side, c.z = z0 - pad + 0.5f * side;
     const ChoiceProbe pc = choice_probe(L, tab, c);
-    bool ok = pc.margin > r0;
-    if (!ok && pc.margin > -0.5f * r0) {  // hopeless cubes are not refined
-        constexpr int S = 4;
-        const float sub = side * (1.f / S), r1 = 0.8660255f * sub;
-        ok = true;
-        for (int k = 0; k < S * S * S && ok; k++) {
-            CoxaPoint q;
-            q.x = xa + ((float)(k % S) + 0.5f) * sub;
-            q.y = ya + ((float)((k / S) % S) + 0.5f) * sub;
-            q.z = z0 - pad + ((float)(k / (S * S)) + 0.5f) * sub;
-            const ChoiceProbe ps = choice_probe(L, tab, q);
-            ok = ps.direct == pc.direct && ps.margin > r1;
-        }
+    out.direct = pc.direct;
+    if (pc.margin > r0) {
+        out.byte = kVolPure | ((unsigned)id << 1) | (pc.direct ? 0u : 1u);
+    } else if (pc.margin > -0.5f * r0) {  // hopeless cubes are not refined
+        out.byte = kVolPure | ((unsigned)id << 1) | (pc.direct ? 0u : 1u);
+        out.refine = true;
     }
-    if (!ok) return 0u;
-    return kVolPure | ((unsigned)id << 1) | (pc.direct ? 0u : 1u);
+    return out;
+}
+LRM_HD bool choice_cell_sub(const LegPlan& L, const SectorTable& tab, float x0, float y0, float z0, float h,
+                            int k, bool direct) {
+    const float pad = vol_pad(h);
+    const float side = h + 2.f * pad;
+    const float sub = side * (1.f / kVolSub), r1 = 0.8660255f * sub;
+    CoxaPoint q;
+    q.x = x0 - pad + ((float)(k % kVolSub) + 0.5f) * sub;
+    q.y = y0 - pad + ((float)((k / kVolSub) % kVolSub) + 0.5f) * sub;
+    q.z = z0 - pad + ((float)(k / (kVolSub * kVolSub)) + 0.5f) * sub;
+    const ChoiceProbe ps = choice_probe(L, tab, q);
+    return ps.direct == direct && ps.margin > r1;
+}
+LRM_HD unsigned choice_cell_byte(const LegPlan& L, const SectorTable& tab, const FastTables& FT, float x0,
+                                 float y0, float z0, float h) {
+    const CellFirst f = choice_cell_first(L, tab, FT, x0, y0, z0, h);
+    if (!f.refine) return f.byte;
+    for (int k = 0; k < kVolSub * kVolSub * kVolSub; k++)
+        if (!choice_cell_sub(L, tab, x0, y0, z0, h, k, f.direct)) return 0u;
+    return f.byte;
 }
 
 // One point of a certified cube: the chosen solution only.  Same arithmetic as dist_fast for that

@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(kThreads)
         }
     }
 
-    FastView fview{nullptr, nullptr};
-    if constexpr (kRedo) fview = FastView{S.fast.ypair, S.fast.ycode};
+    FastView fview{nullptr, nullptr, nullptr, 0};
+    if constexpr (kRedo) fview = FastView{S.fast.ypair, S.fast.ycode, nullptr, 0};
     uint32_t it = 0;
     // ring bookkeeping, identical in every thread: entries appended before this iteration (base),
     // before the previous one (elig: their tiles' stores have completed), and redone so far (head)
@@ -376,13 +376,31 @@ __global__ void __launch_bounds__(kThreads)
 // A ring that is full refuses the push; the point then moves to the next ring or is evaluated on
 // the spot (correct, just divergent).  Every path applies the same operations to the winning
 // candidate, so the output does not depend on which one ran.
-constexpr int kRingA = 1024, kRingB = 1024, kRingC = 512;  // entries (powers of two)
+// CTA shape of the tiered sweep (its own: the other sweeps keep kThreads / kTile)
+#ifndef LRM_TIER_THREADS
+#define LRM_TIER_THREADS 256
+#endif
+#ifndef LRM_TIER_TILE
+#define LRM_TIER_TILE 1024
+#endif
+#ifndef LRM_TIER_CTAS
+#define LRM_TIER_CTAS 4
+#endif
+constexpr int kTT = LRM_TIER_THREADS;  // threads per CTA
+constexpr int kTL = LRM_TIER_TILE;     // points per tile
+static_assert(kTL % kTT == 0 && kTL % 16 == 0 && kTL <= 1024 && kTL / kTT == 4, "tier tile shape");
+#ifndef LRM_RING_A
+#define LRM_RING_A 512
+#define LRM_RING_B 512
+#define LRM_RING_C 512
+#endif
+constexpr int kRingA = LRM_RING_A, kRingB = LRM_RING_B, kRingC = LRM_RING_C;  // entries (powers of two)
 // ring entry: iteration (17 bits) | cube byte bits 0-4 | index in tile (10 bits)
 constexpr int kEntryIterBits = 17;
 
 struct alignas(128) TierSmem {
-    float in[3][3 * kTile];  // in-place tiles: being loaded / computed / stored
-    uint8_t flag[2][kTile];
+    float in[3][3 * kTL];  // in-place tiles: being loaded / computed / stored
+    uint8_t flag[2][kTL];
     alignas(16) SectorTable table;
     alignas(16) WinnerTable winners;
     alignas(16) YawPair ypair[kYawPairs];
@@ -397,7 +415,7 @@ struct alignas(128) TierSmem {
 // the room the ring had when this iteration's pushes began.
 template <int CAP>
 struct Ring {
-    static_assert((CAP & (CAP - 1)) == 0 && CAP >= 2 * kThreads, "ring shape");
+    static_assert((CAP & (CAP - 1)) == 0 && CAP >= 2 * kTT, "ring shape");
     uint32_t base = 0, elig = 0, head = 0, room = CAP;
     // top of an iteration; prev = attempts counted in the previous one.  room is taken BEFORE this
     // iteration's redo: slots freed now may still be read by slower warps (no barrier in between).
@@ -456,7 +474,7 @@ template <int MODE, bool SOA>
 __device__ __noinline__ bool redo_fast(const LegPlan& L, const FastView F, const AtlasView& A,
                                        const WinnerTable& W, const RedoIo& io, size_t g) {
     DistResult r;
-    if (!dist_fast<true, false>(L, F, A, W, redo_load<SOA>(L, io, g), &r)) return false;
+    if (!dist_fast<true, false, true>(L, F, A, W, redo_load<SOA>(L, io, g), &r)) return false;
     redo_store<MODE, SOA>(io, g, r);
     return true;
 }
@@ -473,24 +491,21 @@ __device__ __noinline__ void tile_point_full(const LegPlan& L, const SectorTable
                                              uint8_t* flag, int i) {
     CoxaPoint p;
     if (SOA) {
-        p.x = tile[i], p.y = tile[kTile + i], p.z = tile[2 * kTile + i];
+        p.x = tile[i], p.y = tile[kTL + i], p.z = tile[2 * kTL + i];
     } else {
         p.x = tile[3 * i], p.y = tile[3 * i + 1], p.z = tile[3 * i + 2];
     }
     const DistResult r = dist_coxa_frame<false>(L, tab, p);
     if (SOA) {
-        tile[i] = r.dx, tile[kTile + i] = r.dy, tile[2 * kTile + i] = r.dz;
+        tile[i] = r.dx, tile[kTL + i] = r.dy, tile[2 * kTL + i] = r.dz;
     } else {
         tile[3 * i] = r.dx, tile[3 * i + 1] = r.dy, tile[3 * i + 2] = r.dz;
     }
     flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
 }
 
-#ifndef LRM_TIER_CTAS
-#define LRM_TIER_CTAS 4
-#endif
 template <int MODE, bool SOA>
-__global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
+__global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
     one_leg_tier_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
                         const AtlasView atlas, const VolumeView vol, const __grid_constant__ RedoIo io,
                         size_t n, int kshift, const int* __restrict__ gate, int gate_want) {
@@ -499,14 +514,14 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
     auto& S = *reinterpret_cast<TierSmem*>(smem_raw);
     const int tid = threadIdx.x;
     const size_t n_bulk = n & ~size_t(15);
-    const uint32_t n_tiles = (uint32_t)((n_bulk + kTile - 1) / kTile);  // the launcher keeps n below 2^40
+    const uint32_t n_tiles = (uint32_t)((n_bulk + kTL - 1) / kTL);  // the launcher keeps n below 2^40
     constexpr int kStages = 3;
 
-    fill_sector_table(L, &S.table, tid, kThreads);
-    fill_winner_table(L, &S.winners, tid, kThreads);
-    for (int i = tid; i < kYawPairs * (int)(sizeof(YawPair) / 4); i += kThreads)
+    fill_sector_table(L, &S.table, tid, kTT);
+    fill_winner_table(L, &S.winners, tid, kTT);
+    for (int i = tid; i < kYawPairs * (int)(sizeof(YawPair) / 4); i += kTT)
         reinterpret_cast<float*>(S.ypair)[i] = reinterpret_cast<const float*>(FT.pair)[i];
-    for (int i = tid; i < (kYawBins + 16) / 4; i += kThreads)
+    for (int i = tid; i < (kYawBins + 16) / 4; i += kTT)
         reinterpret_cast<uint32_t*>(S.ycode)[i] = reinterpret_cast<const uint32_t*>(FT.code)[i];
     if (tid == 0) {
         for (int k = 0; k < 9; k++) (&S.cnt[0][0])[k] = 0;
@@ -516,16 +531,16 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
     __syncthreads();
 
     auto tile_count = [&](uint32_t tile) -> uint32_t {
-        return tile + 1u < n_tiles ? (uint32_t)kTile : (uint32_t)(n_bulk - (size_t)tile * kTile);
+        return tile + 1u < n_tiles ? (uint32_t)kTL : (uint32_t)(n_bulk - (size_t)tile * kTL);
     };
     auto issue_load = [&](uint32_t tile, int stage) {
         const uint32_t cnt = tile_count(tile);
-        const size_t first = (size_t)tile * kTile;
+        const size_t first = (size_t)tile * kTL;
         if (SOA) {
             bulk::mbar_expect_tx(&S.full[stage], 3 * cnt * 4);
             bulk::load(&S.in[stage][0], io.in_x + first, cnt * 4, &S.full[stage]);
-            bulk::load(&S.in[stage][kTile], io.in_y + first, cnt * 4, &S.full[stage]);
-            bulk::load(&S.in[stage][2 * kTile], io.in_z + first, cnt * 4, &S.full[stage]);
+            bulk::load(&S.in[stage][kTL], io.in_y + first, cnt * 4, &S.full[stage]);
+            bulk::load(&S.in[stage][2 * kTL], io.in_z + first, cnt * 4, &S.full[stage]);
         } else {
             bulk::mbar_expect_tx(&S.full[stage], cnt * 12);
             bulk::load(&S.in[stage][0], io.in_x + 3 * first, cnt * 12, &S.full[stage]);
@@ -544,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
         }
     }
 
-    const FastView fview{S.ypair, S.ycode};
+    const FastView fview{S.ypair, S.ycode, FT.combo, FT.ncombo};
     const YawSol* sols = reinterpret_cast<const YawSol*>(S.ypair);
     uint32_t it = 0;
     Ring<kRingA> ra;
@@ -556,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
     constexpr uint32_t kIterMask = (1u << kEntryIterBits) - 1u;
     auto global_index = [&](uint32_t entry) -> size_t {
         const uint32_t age = (it - (entry >> 15)) & kIterMask;
-        return (size_t)tile_of(it - age) * kTile + (entry & 1023u);
+        return (size_t)tile_of(it - age) * kTL + (entry & 1023u);
     };
     auto do_c = [&](uint32_t entry) { redo_full<MODE, SOA>(L, S.table, io, global_index(entry)); };
     auto do_b = [&](uint32_t entry) {
@@ -579,31 +594,31 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
         rb.advance(S.cnt[1][rot_prev]);
         rc.advance(S.cnt[2][rot_prev]);
 #pragma unroll 1
-        while (rc.elig - rc.head >= (uint32_t)kThreads) {
+        while (rc.elig - rc.head >= (uint32_t)kTT) {
             do_c(S.ring_c[(rc.head + tid) & (kRingC - 1)]);
-            rc.head += kThreads;
+            rc.head += kTT;
         }
 #pragma unroll 1
-        while (rb.elig - rb.head >= (uint32_t)kThreads) {
+        while (rb.elig - rb.head >= (uint32_t)kTT) {
             do_b(S.ring_b[(rb.head + tid) & (kRingB - 1)]);
-            rb.head += kThreads;
+            rb.head += kTT;
         }
 #pragma unroll 1
-        while (ra.elig - ra.head >= (uint32_t)kThreads) {
+        while (ra.elig - ra.head >= (uint32_t)kTT) {
             do_a(S.ring_a[(ra.head + tid) & (kRingA - 1)]);
-            ra.head += kThreads;
+            ra.head += kTT;
         }
 
         auto load_pt = [&](int i, float& x, float& y, float& z) {
             if (SOA) {
-                x = in[i], y = in[kTile + i], z = in[2 * kTile + i];
+                x = in[i], y = in[kTL + i], z = in[2 * kTL + i];
             } else {
                 x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
             }
         };
         auto store3 = [&](int i, float x, float y, float z) {
             if (SOA) {
-                in[i] = x, in[kTile + i] = y, in[2 * kTile + i] = z;
+                in[i] = x, in[kTL + i] = y, in[2 * kTL + i] = z;
             } else {
                 in[3 * i] = x, in[3 * i + 1] = y, in[3 * i + 2] = z;
             }
@@ -612,29 +627,29 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
         // and its cube byte is requested; the bytes are parked in the flag slots.  All of a
         // thread's volume fetches are in flight together, off the critical path of phase 2.
         {
-            constexpr int kPer = kTile / kThreads;
+            constexpr int kPer = kTL / kTT;
             unsigned cube[kPer];
-            if (cnt == (uint32_t)kTile) {
+            if (cnt == (uint32_t)kTL) {
 #pragma unroll
                 for (int k = 0; k < kPer; k++) {
-                    const int i = tid + k * kThreads;
+                    const int i = tid + k * kTT;
                     float x, y, z;
                     load_pt(i, x, y, z);
                     const CoxaPoint p = to_coxa_frame(L, x, y, z);
                     cube[k] = tex3D<unsigned char>(vol.tex, fmaf(p.x, vol.inv_cell, vol.o),
-                                                   fmaf(p.y, vol.inv_cell, vol.o), fmaf(p.z, vol.inv_cell, vol.o));
+                                                   fmaf(p.y, vol.inv_cell, vol.oy), fmaf(p.z, vol.inv_cell, vol.o));
                     store3(i, p.x, p.y, p.z);
                 }
 #pragma unroll
-                for (int k = 0; k < kPer; k++) flag[tid + k * kThreads] = (uint8_t)cube[k];
+                for (int k = 0; k < kPer; k++) flag[tid + k * kTT] = (uint8_t)cube[k];
             } else {
 #pragma unroll 1
-                for (int i = tid; i < (int)cnt; i += kThreads) {
+                for (int i = tid; i < (int)cnt; i += kTT) {
                     float x, y, z;
                     load_pt(i, x, y, z);
                     const CoxaPoint p = to_coxa_frame(L, x, y, z);
                     flag[i] = (uint8_t)tex3D<unsigned char>(vol.tex, fmaf(p.x, vol.inv_cell, vol.o),
-                                                            fmaf(p.y, vol.inv_cell, vol.o), fmaf(p.z, vol.inv_cell, vol.o));
+                                                            fmaf(p.y, vol.inv_cell, vol.oy), fmaf(p.z, vol.inv_cell, vol.o));
                     store3(i, p.x, p.y, p.z);
                 }
             }
@@ -654,9 +669,9 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
             tile_point_full<MODE, SOA>(L, S.table, in, flag, i);
         };
 #pragma unroll 1
-        for (int i = tid; i < (int)cnt; i += 2 * kThreads) {
-            const bool has_j = i + kThreads < (int)cnt;
-            const int j = has_j ? i + kThreads : i;
+        for (int i = tid; i < (int)cnt; i += 2 * kTT) {
+            const bool has_j = i + kTT < (int)cnt;
+            const int j = has_j ? i + kTT : i;
             CoxaPoint pi, pj;
             load_pt(i, pi.x, pi.y, pi.z);
             load_pt(j, pj.x, pj.y, pj.z);  // both loads before any store: the tile is updated in place
@@ -678,11 +693,11 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
         }
         __syncthreads();
         if (tid == 0) {
-            const size_t first = (size_t)tile * kTile;
+            const size_t first = (size_t)tile * kTL;
             if (SOA) {
                 bulk::store(io.out_x + first, in, cnt * 4);
-                bulk::store(io.out_y + first, in + kTile, cnt * 4);
-                bulk::store(io.out_z + first, in + 2 * kTile, cnt * 4);
+                bulk::store(io.out_y + first, in + kTL, cnt * 4);
+                bulk::store(io.out_z + first, in + 2 * kTL, cnt * 4);
             } else {
                 bulk::store(io.out_x + 3 * first, in, cnt * 12);
             }
@@ -705,22 +720,22 @@ __global__ void __launch_bounds__(kThreads, LRM_TIER_CTAS)
             rc.advance(S.cnt[2][rot_prev]);
         }
 #pragma unroll 1
-        for (; ra.head < ra.base; ra.head += kThreads)
+        for (; ra.head < ra.base; ra.head += kTT)
             if (ra.head + tid < ra.base) do_a(S.ring_a[(ra.head + tid) & (kRingA - 1)]);
 #pragma unroll 1
-        for (; rc.head < rc.base; rc.head += kThreads)
+        for (; rc.head < rc.base; rc.head += kTT)
             if (rc.head + tid < rc.base) do_c(S.ring_c[(rc.head + tid) & (kRingC - 1)]);
         // ring C is empty now; what ring B's drain cannot decide goes to cnt[2][rot] (zero so far)
         rc.head = rc.base, rc.room = kRingC;
         __syncthreads();
 #pragma unroll 1
-        for (; rb.head < rb.base; rb.head += kThreads)
+        for (; rb.head < rb.base; rb.head += kTT)
             if (rb.head + tid < rb.base) do_b(S.ring_b[(rb.head + tid) & (kRingB - 1)]);
         __syncthreads();
         const unsigned late = S.cnt[2][rot];
         rc.base += late < rc.room ? late : rc.room;
 #pragma unroll 1
-        for (; rc.head < rc.base; rc.head += kThreads)
+        for (; rc.head < rc.base; rc.head += kTT)
             if (rc.head + tid < rc.base) do_c(S.ring_c[(rc.head + tid) & (kRingC - 1)]);
     }
 
@@ -896,11 +911,11 @@ cudaError_t launch_tier_impl(const LegPlan& plan, const FastTables& ft, const At
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTT, smem);
         if (e != cudaSuccess) return e;
         ctas_per_sm = occ < 1 ? 1 : occ;
     }
-    const size_t tiles = ((n & ~size_t(15)) + kTile - 1) / kTile;
+    const size_t tiles = ((n & ~size_t(15)) + kTL - 1) / kTL;
     size_t grid = (size_t)sm_count() * ctas_per_sm;
     if (tiles < grid) grid = tiles;
     if (grid == 0) grid = 1;
@@ -908,7 +923,7 @@ cudaError_t launch_tier_impl(const LegPlan& plan, const FastTables& ft, const At
     int kshift = 0;
     while (kshift < tier_chunk_shift_max() && (tiles >> (kshift + 1)) >= grid * 16) kshift++;
     const RedoIo io{ix, iy, iz, ox, oy, oz, flag};
-    kernel<<<(unsigned)grid, kThreads, smem, stream>>>(plan, ft, atlas, vol, io, n, kshift, gate, gate_want);
+    kernel<<<(unsigned)grid, kTT, smem, stream>>>(plan, ft, atlas, vol, io, n, kshift, gate, gate_want);
     return cudaGetLastError();
 }
 
@@ -1009,7 +1024,7 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
             // ring entries of the tiered sweep hold a 17-bit per-CTA iteration count
             const int vmode = choice_volume_mode();
             if (atlas_through_texture() && vmode != 0 && ft.both_unsat == 0 &&
-                n / kTile / (size_t)sm_count() < (size_t(1) << (kEntryIterBits - 1)) && n < (size_t(1) << 40)) {
+                n / kTL / (size_t)sm_count() < (size_t(1) << (kEntryIterBits - 1)) && n < (size_t(1) << 40)) {
                 VolumeView vol;
                 e = get_choice_volume(plan, stream, &vol, /*wait=*/vmode == 1);
                 int* verdict = (e == cudaSuccess && vmode == 2) ? next_verdict_word() : nullptr;

@@ -43,20 +43,43 @@ __global__ void atlas_build_kernel(const __grid_constant__ LegPlan L, unsigned c
     }
 }
 
-// One thread per cube of the choice volume (leg_math.cuh): x fastest, like the 3-D array upload.
+// One lane per cube of the choice volume (x fastest, like the 3-D array upload).  Cubes whose centre
+// cannot decide are refined on 4^3 sub-cubes; those cubes hug the decision surfaces (a few lanes
+// per warp), so the warp refines them one after the other with all 32 lanes, two sub-cubes each,
+// instead of leaving 29 lanes idle while three of them run 64 probes.
 __global__ void __launch_bounds__(128)
     volume_build_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
                         unsigned char* __restrict__ linear, int dim, float cell) {
     __shared__ SectorTable table;
     fill_sector_table(L, &table, threadIdx.x, blockDim.x);
     __syncthreads();
+    static_assert(kVolSub * kVolSub * kVolSub == 64, "two sub-cubes per lane");
     const size_t total = (size_t)dim * dim * dim;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;  // a multiple of 32: whole warps step together
     const float half = 0.5f * (float)dim;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int lane = threadIdx.x & 31;
+    const size_t rounds = (total + stride - 1) / stride;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t r = 0; r < rounds; r++, i += stride) {
+        const bool live = i < total;
         const int ix = (int)(i % dim), iy = (int)((i / dim) % dim), iz = (int)(i / ((size_t)dim * dim));
-        linear[i] = (unsigned char)choice_cell_byte(L, table, FT, ((float)ix - half) * cell,
-                                                    ((float)iy - half) * cell, ((float)iz - half) * cell, cell);
+        const float x0 = ((float)ix - half) * cell, y0 = ((float)iy - half - kVolShiftY) * cell, z0 = ((float)iz - half) * cell;
+        CellFirst f;
+        f.byte = 0u, f.refine = false, f.direct = true;
+        if (live) f = choice_cell_first(L, table, FT, x0, y0, z0, cell);
+        unsigned need = __ballot_sync(0xffffffffu, f.refine);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const float sx = __shfl_sync(0xffffffffu, x0, src), sy = __shfl_sync(0xffffffffu, y0, src),
+                        sz = __shfl_sync(0xffffffffu, z0, src);
+            const bool sdir = __shfl_sync(0xffffffffu, (int)f.direct, src) != 0;
+            const bool ok = choice_cell_sub(L, table, sx, sy, sz, cell, lane, sdir) &&
+                            choice_cell_sub(L, table, sx, sy, sz, cell, lane + 32, sdir);
+            const bool all = __all_sync(0xffffffffu, ok);
+            if (lane == src && !all) f.byte = 0u;
+        }
+        if (live) linear[i] = (unsigned char)f.byte;
     }
 }
 
@@ -307,6 +330,7 @@ cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeVi
     view->tex = hit->vol_tex;
     view->inv_cell = 1.0f / hit->vol_cell;
     view->o = 0.5f * (float)hit->vol_dim;
+    view->oy = view->o + kVolShiftY;
     view->dim = hit->vol_dim;
     return cudaSuccess;
 }

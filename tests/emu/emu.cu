@@ -110,7 +110,7 @@ size_t emu_dist_atlas(const float* xyz, size_t n, const lrm_leg_t* leg, const fl
         }
     if (pure_cells) *pure_cells = pure;
     lrm::AtlasView A{cells, 0, 1.0f / cell, -origin / cell, -origin / cell, dim, dim};
-    const lrm::FastView F{ft.pair, ft.code};
+    const lrm::FastView F{ft.pair, ft.code, ft.combo, ft.ncombo};
     size_t fallback = 0;
     for (size_t i = 0; i < n; i++) {
         const lrm::CoxaPoint p = lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
@@ -151,14 +151,14 @@ void emu_dist_choice(const float* xyz, size_t n, const lrm_leg_t* leg, const flo
             cells[lrm::atlas_index(dim, ix, iy)] = (unsigned char)lrm::atlas_cell_byte(lrm::plane_probe(L, tab, X, Y), need);
         }
     lrm::AtlasView A{cells.data(), 0, 1.0f / cell, -origin / cell, -origin / cell, dim, dim};
-    const lrm::FastView F{ft.pair, ft.code};
+    const lrm::FastView F{ft.pair, ft.code, ft.combo, ft.ncombo};
     const lrm::YawSol* sols = reinterpret_cast<const lrm::YawSol*>(ft.pair);
     std::unordered_map<uint64_t, unsigned char> cubes;
     const float vo = 0.5f * vol_dim, vinv = 1.0f / vol_h;
     tiers[0] = tiers[1] = tiers[2] = tiers[3] = 0;
     for (size_t i = 0; i < n; i++) {
         const lrm::CoxaPoint p = lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
-        const float fx = fmaf(p.x, vinv, vo), fy = fmaf(p.y, vinv, vo), fz = fmaf(p.z, vinv, vo);
+        const float fx = fmaf(p.x, vinv, vo), fy = fmaf(p.y, vinv, vo + lrm::kVolShiftY), fz = fmaf(p.z, vinv, vo);
         unsigned cube = 0;
         if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)vol_dim && fy < (float)vol_dim && fz < (float)vol_dim) {
             const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
@@ -166,7 +166,7 @@ void emu_dist_choice(const float* xyz, size_t n, const lrm_leg_t* leg, const flo
             auto it = cubes.find(key);
             if (it == cubes.end()) {
                 const unsigned char b = (unsigned char)lrm::choice_cell_byte(
-                    L, tab, ft, ((float)ix - vo) * vol_h, ((float)iy - vo) * vol_h, ((float)iz - vo) * vol_h, vol_h);
+                    L, tab, ft, ((float)ix - vo) * vol_h, ((float)iy - vo - lrm::kVolShiftY) * vol_h, ((float)iz - vo) * vol_h, vol_h);
                 it = cubes.emplace(key, b).first;
             }
             cube = it->second;
@@ -179,7 +179,7 @@ void emu_dist_choice(const float* xyz, size_t n, const lrm_leg_t* leg, const flo
             tier = 2;
         } else if (st == 1) {
             tier = 1;
-            if (!lrm::dist_fast<false>(L, F, A, win, p, &r)) {
+            if (!lrm::dist_fast<false, false, true>(L, F, A, win, p, &r)) {  // as ring B's redo runs it
                 r = lrm::dist_coxa_frame<false>(L, tab, p);
                 tier = 3;
             }
