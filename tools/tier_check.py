@@ -48,18 +48,29 @@ for name, env in (("two_tier", "0"), ("three_tier", "1"), ("auto", None)):
     e1.record()
     torch.cuda.synchronize()
     dms = e0.elapsed_time(e1) / 5
+    rflags = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        lrm.reachability(pts, leg, out=rflags)
+    e0.record()
+    for _ in range(5):
+        lrm.reachability(pts, leg, out=rflags)
+    e1.record()
+    torch.cuda.synchronize()
+    rms = e0.elapsed_time(e1) / 5
     out[name] = {"first_call_s": first, "fused_ms": ms, "fused_gpoints_s": n / ms / 1e6, "dist_ms": dms,
-                 "dist_gpoints_s": n / dms / 1e6}
-    res[name] = (flags, vec, dvec)
+                 "dist_gpoints_s": n / dms / 1e6, "reach_ms": rms, "reach_gpoints_s": n / rms / 1e6}
+    res[name] = (flags, vec, dvec, rflags)
     del dvec
-fa, va, da = res["two_tier"]
-fb, vb, db = res["three_tier"]
+fa, va, da, ra = res["two_tier"]
+fb, vb, db, rb = res["three_tier"]
 diff = (va - vb).abs().amax(dim=1)
 out["flags_equal"] = bool(torch.equal(fa, fb))
 out["max_vec_diff_mm"] = float(diff.max())
 out["points_over_1e-3"] = int((diff > 1e-3).sum())
 out["dist_mode_max_diff_mm"] = float((da - db).abs().max())
 out["reachable"] = int(fb.sum())
-fc, vc, dc = res["auto"]
+fc, vc, dc, rc = res["auto"]
 out["auto_equal"] = bool(torch.equal(fc, fa) and torch.equal(vc, va) and torch.equal(dc, da))
+out["reach_equal"] = bool(torch.equal(ra, rb) and torch.equal(ra, rc))
+out["reach_vs_fused_mismatch"] = int((ra != fa).sum())
 print(json.dumps(out))
