@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
                     return __any_sync(0xffffffffu, ok && t.w != 0.f && d < P.r_near_any) != 0;
                 });
             const int nq = (collide_all || !near_any) ? 0 : P.nq;
+            int first_leg = 0;
             for (int o = 0; o < nq && result == 0; o++) {
                 const OrientConsts& O = P.orient[o];
                 const float3 B = rotate(O.R, bx, by, bz);
@@ -256,8 +257,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
                     });
                 if (!near) continue;
                 // eliminateUnreachable (:633-706): every leg needs one reachable map point
+                // The legs are tried starting with the one that failed last (move-to-front): a pose
+                // that cannot stand usually fails on the same leg under the next orientation too,
+                // and a failing walk is the expensive one (no early exit).  The outcome is an AND
+                // over the legs, so the order does not matter.
                 bool all = true;
-                for (int l = 0; l < P.nlegs && all; l++) {
+                for (int ll = 0; ll < P.nlegs && all; ll++) {
+                    const int l = first_leg + ll < P.nlegs ? first_leg + ll : first_leg + ll - P.nlegs;
                     const ReachPlan& L = plans[o * P.nlegs + l];
                     all = walk_filtered(
                         P.map, bx, by, P.r_leg, lane,
@@ -273,6 +279,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
                             const bool r = ok && t.w != 0.f && reach_offset(L, T.x - B.x, T.y - B.y, T.z - B.z, &gc);
                             return __any_sync(0xffffffffu, r) != 0;
                         });
+                    if (!all) first_leg = l;
                 }
                 if (all) result = (uint8_t)(o + 1);
             }
