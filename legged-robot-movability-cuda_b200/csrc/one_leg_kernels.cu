@@ -404,7 +404,6 @@ struct alignas(128) TierSmem {
     alignas(16) SectorTable table;
     alignas(16) WinnerTable winners;
     alignas(16) YawPair ypair[kYawPairs];
-    alignas(16) unsigned char ycode[kYawBins + 16];
     uint32_t ring_a[kRingA], ring_b[kRingB], ring_c[kRingC];
     unsigned cnt[3][3];  // [ring][it % 3]: pushes attempted in that iteration
     alignas(8) uint64_t full[3];
@@ -521,8 +520,6 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
     fill_winner_table(L, &S.winners, tid, kTT);
     for (int i = tid; i < kYawPairs * (int)(sizeof(YawPair) / 4); i += kTT)
         reinterpret_cast<float*>(S.ypair)[i] = reinterpret_cast<const float*>(FT.pair)[i];
-    for (int i = tid; i < (kYawBins + 16) / 4; i += kTT)
-        reinterpret_cast<uint32_t*>(S.ycode)[i] = reinterpret_cast<const uint32_t*>(FT.code)[i];
     if (tid == 0) {
         for (int k = 0; k < 9; k++) (&S.cnt[0][0])[k] = 0;
         for (int s = 0; s < kStages; s++) bulk::mbar_init(&S.full[s], 1);
@@ -559,7 +556,8 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
         }
     }
 
-    const FastView fview{S.ypair, S.ycode, FT.combo, FT.ncombo};
+    // the bin codes stay in the constant bank: only ring B's redo reads them
+    const FastView fview{S.ypair, FT.code, FT.combo, FT.ncombo};
     const YawSol* sols = reinterpret_cast<const YawSol*>(S.ypair);
     uint32_t it = 0;
     Ring<kRingA> ra;
