@@ -507,8 +507,12 @@ template <int MODE, bool SOA>
 __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
     one_leg_tier_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
                         const AtlasView atlas, const VolumeView vol, const __grid_constant__ RedoIo io,
-                        size_t n, int kshift, const int* __restrict__ gate, int gate_want) {
+                        size_t n, int kshift_arg, const int* __restrict__ gate, int gate_want) {
     if (gate != nullptr && *gate != gate_want) return;  // the coherence probe chose the other sweep
+    // bit 8 of the argument (LRM_TIER_SKELETON=1, measurements only): move the tiles but skip the
+    // arithmetic — the ceiling of the staging pipeline itself
+    const int kshift = kshift_arg & 0xff;
+    const bool skeleton = (kshift_arg & 0x100) != 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     auto& S = *reinterpret_cast<TierSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -624,7 +628,7 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
         // Phase 1: every point of the thread goes to the coxa frame (kept in the point's own slot)
         // and its cube byte is requested; the bytes are parked in the flag slots.  All of a
         // thread's volume fetches are in flight together, off the critical path of phase 2.
-        {
+        if (!skeleton) {
             constexpr int kPer = kTL / kTT;
             unsigned cube[kPer];
             if (cnt == (uint32_t)kTL) {
@@ -667,7 +671,7 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
             tile_point_full<MODE, SOA>(L, S.table, in, flag, i);
         };
 #pragma unroll 1
-        for (int i = tid; i < (int)cnt; i += 2 * kTT) {
+        for (int i = tid; i < (skeleton ? 0 : (int)cnt); i += 2 * kTT) {
             const bool has_j = i + kTT < (int)cnt;
             const int j = has_j ? i + kTT : i;
             CoxaPoint pi, pj;
@@ -920,6 +924,8 @@ cudaError_t launch_tier_impl(const LegPlan& plan, const FastTables& ft, const At
     // chunks of up to 8 consecutive tiles per CTA, fewer on small sweeps (keep >= 16 chunks per CTA)
     int kshift = 0;
     while (kshift < tier_chunk_shift_max() && (tiles >> (kshift + 1)) >= grid * 16) kshift++;
+    if (const char* sk = getenv("LRM_TIER_SKELETON"))
+        if (sk[0] == '1') kshift |= 0x100;
     const RedoIo io{ix, iy, iz, ox, oy, oz, flag};
     kernel<<<(unsigned)grid, kTT, smem, stream>>>(plan, ft, atlas, vol, io, n, kshift, gate, gate_want);
     return cudaGetLastError();
