@@ -18,6 +18,7 @@ struct CellGrid {
     const int* cell_start;   // nx*ny + 1
     const float4* pts;       // cell-sorted (x, y, z, keep)
     const float2* cell_z;    // per cell (zmin, zmax)
+    const float2* cell_ball; // per cell (z of the centre, radius of the bounding ball); radius < 0: empty cell
     int n;
 };
 
@@ -105,7 +106,8 @@ __global__ void scan_kernel(const int* __restrict__ counts, int* __restrict__ st
 __global__ void scatter_kernel(CellGrid g, const float* __restrict__ xyz,
                                const uint8_t* __restrict__ keep, int* __restrict__ cursor,
                                float4* __restrict__ sorted, const int* __restrict__ zmin,
-                               const int* __restrict__ zmax, float2* __restrict__ cell_z) {
+                               const int* __restrict__ zmax, float2* __restrict__ cell_z,
+                               float2* __restrict__ cell_ball, const int* __restrict__ counts) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t i = tid; i < (size_t)g.n; i += stride) {
@@ -117,7 +119,13 @@ __global__ void scatter_kernel(CellGrid g, const float* __restrict__ xyz,
     const int ncell = g.nx * g.ny;
     for (size_t c = tid; c < (size_t)ncell; c += stride) {
         auto dec = [](int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); };
-        cell_z[c] = make_float2(dec(zmin[c]), dec(zmax[c]));
+        const float z0 = dec(zmin[c]), z1 = dec(zmax[c]);
+        cell_z[c] = make_float2(z0, z1);
+        // bounding ball of the cell's points: half diagonal of the cell (+0.2 % for points binned
+        // across an edge by rounding) and half the z range
+        const float cell = 1.0f / g.inv_cell, hz = 0.5f * (z1 - z0);
+        cell_ball[c] = counts[c] > 0 ? make_float2(0.5f * (z0 + z1), sqrtf(0.5f * cell * cell * 1.004f + hz * hz) + 1.0e-3f)
+                                     : make_float2(0.f, -1.f);
     }
 }
 
@@ -176,7 +184,7 @@ cudaError_t build_grid(DevBuf& mem, const float* xyz, size_t n, const uint8_t* k
     const int ncell = g.nx * g.ny;
     int *counts, *start, *zmin, *zmax, *cursor;
     float4* sorted;
-    float2* cell_z;
+    float2 *cell_z, *cell_ball;
     POSIT_CHECK(mem.alloc(&counts, ncell));
     POSIT_CHECK(mem.alloc(&start, ncell + 1));
     POSIT_CHECK(mem.alloc(&cursor, ncell));
@@ -184,15 +192,16 @@ cudaError_t build_grid(DevBuf& mem, const float* xyz, size_t n, const uint8_t* k
     POSIT_CHECK(mem.alloc(&zmax, ncell));
     POSIT_CHECK(mem.alloc(&sorted, n));
     POSIT_CHECK(mem.alloc(&cell_z, ncell));
+    POSIT_CHECK(mem.alloc(&cell_ball, ncell));
     POSIT_CHECK(cudaMemsetAsync(counts, 0, ncell * sizeof(int), stream));
     POSIT_CHECK(cudaMemsetAsync(zmin, 0x7f, ncell * sizeof(int), stream));  // large positive
     POSIT_CHECK(cudaMemsetAsync(zmax, 0x80, ncell * sizeof(int), stream));  // large negative
     if (n) count_kernel<<<592, 256, 0, stream>>>(g, xyz, counts, zmin, zmax);
     scan_kernel<<<1, 1024, 0, stream>>>(counts, start, ncell);
     POSIT_CHECK(cudaMemcpyAsync(cursor, start, ncell * sizeof(int), cudaMemcpyDeviceToDevice, stream));
-    scatter_kernel<<<592, 256, 0, stream>>>(g, xyz, keep, cursor, sorted, zmin, zmax, cell_z);
+    scatter_kernel<<<592, 256, 0, stream>>>(g, xyz, keep, cursor, sorted, zmin, zmax, cell_z, cell_ball, counts);
     POSIT_CHECK(cudaGetLastError());
-    g.cell_start = start, g.pts = sorted, g.cell_z = cell_z;
+    g.cell_start = start, g.pts = sorted, g.cell_z = cell_z, g.cell_ball = cell_ball;
     *out = g;
     return cudaSuccess;
 }

@@ -219,6 +219,9 @@ struct alignas(16) ReachPlan {
     float r_min, r_max;      // inner / outer circle radii   (cell-level pruning)
     float yaw_min, yaw_max;  // coxa yaw limits, radians     (cell-level pruning)
     float az_cos, az_sin;    // sincosf(-body_angle) as the reference evaluates it (knife-edge recheck)
+    // unit directions of the two yaw limits; wedge != 0 when the limits span less than pi, i.e.
+    // the allowed yaws are the intersection of two half-planes through the coxa axis (cell pruning)
+    float cmin, smin, cmax, smax, wedge;
 };
 
 LRM_HD void make_reach_plan(const LegPlan& L, float yaw_min, float yaw_max, float az_cos, float az_sin,
@@ -236,6 +239,8 @@ LRM_HD void make_reach_plan(const LegPlan& L, float yaw_min, float yaw_max, floa
     R->r_min = L.inner.r, R->r_max = L.outer.r;
     R->yaw_min = yaw_min, R->yaw_max = yaw_max;
     R->az_cos = az_cos, R->az_sin = az_sin;
+    R->cmin = cosf(yaw_min), R->smin = sinf(yaw_min), R->cmax = cosf(yaw_max), R->smax = sinf(yaw_max);
+    R->wedge = (yaw_max >= yaw_min && yaw_max - yaw_min < 3.0f) ? 1.f : 0.f;
 }
 
 // ---- the gravity-side test on its knife edge -----------------------------------------------------
@@ -343,18 +348,30 @@ LRM_HD bool reach_ball_possible(const ReachPlan& L, float vx, float vy, float vz
     const float px = fmaf(L.M[0], vx, fmaf(L.M[1], vy, fmaf(L.M[2], vz, L.t[0])));
     const float py = fmaf(L.M[3], vx, fmaf(L.M[4], vy, fmaf(L.M[5], vz, L.t[1])));
     const float pz = fmaf(L.M[6], vx, fmaf(L.M[7], vy, fmaf(L.M[8], vz, L.t[2])));
-    const float rho = sqrtf(fmaf(px, px, py * py));
-    const float lo = L.r_min - rc - 0.01f, hi = L.r_max + rc + 0.01f;
+    const float rho2 = fmaf(px, px, py * py);
+    const float rho = sqrtf(rho2);
+    const float lo = fmaxf(L.r_min - rc - 0.01f, 0.f), hi = L.r_max + rc + 0.01f;
     const float xa = rho - L.coxa_length, xb = -rho - L.coxa_length;
-    const float da = sqrtf(fmaf(xa, xa, pz * pz)), db = sqrtf(fmaf(xb, xb, pz * pz));
-    bool ring_a = da >= lo && da <= hi, ring_b = db >= lo && db <= hi;
+    const float da2 = fmaf(xa, xa, pz * pz), db2 = fmaf(xb, xb, pz * pz);
+    bool ring_a = da2 >= lo * lo && da2 <= hi * hi, ring_b = db2 >= lo * lo && db2 <= hi * hi;
     if (rho > rc) {  // yaw only constrains balls that stay clear of the coxa axis
-        const float pi = 3.14159265358979f;
-        const float phi = atan2f(py, px);
-        const float del = asinf(fminf(1.f, rc / rho)) + 1.0e-4f;
-        const float phf = phi > 0.f ? phi - pi : phi + pi;  // folded yaw of the flipped solution
-        ring_a = ring_a && px > -rc && phi + del >= L.yaw_min && phi - del <= L.yaw_max;
-        ring_b = ring_b && px < rc && phf + del >= L.yaw_min && phf - del <= L.yaw_max;
+        if (L.wedge != 0.f) {
+            // A reachable point has its (own-side) yaw between the limits: it lies on the inner side
+            // of both limit lines through the coxa axis, so the ball's centre is at most rc outside
+            // of each.  d_min = rho sin(phi - yaw_min), d_max = rho sin(yaw_max - phi); the
+            // pi-flipped solution sees the mirrored direction, i.e. both with the opposite sign.
+            const float d_min = fmaf(L.cmin, py, -L.smin * px), d_max = fmaf(L.smax, px, -L.cmax * py);
+            const float slack = rc + 0.01f;
+            ring_a = ring_a && px > -rc && d_min >= -slack && d_max >= -slack;
+            ring_b = ring_b && px < rc && d_min <= slack && d_max <= slack;
+        } else {
+            const float pi = 3.14159265358979f;
+            const float phi = atan2f(py, px);
+            const float del = asinf(fminf(1.f, rc / rho)) + 1.0e-4f;
+            const float phf = phi > 0.f ? phi - pi : phi + pi;  // folded yaw of the flipped solution
+            ring_a = ring_a && px > -rc && phi + del >= L.yaw_min && phi - del <= L.yaw_max;
+            ring_b = ring_b && px < rc && phf + del >= L.yaw_min && phf - del <= L.yaw_max;
+        }
     }
     return ring_a || ring_b;
 }

@@ -140,21 +140,20 @@ __device__ __forceinline__ bool walk_filtered(const CellGrid& g, float bx, float
     if (w <= 0 || h <= 0) return false;
     const int ncell = w * h;
     const float cell = 1.0f / g.inv_cell;
+    // k / w without an integer division: (k + 0.5) / w is at least 0.5 / w away from an integer,
+    // far more than the rounding of the float product (k < 2^20, w < 2^10)
+    const float inv_w = 1.0f / (float)w;
     for (int base = 0; base < ncell; base += 32) {
         const int k = base + lane;
         bool keep = false;
         int c = 0;
         if (k < ncell) {
-            const int cy = cy0 + k / w, cx = cx0 + k % w;
+            const int row = (int)(((float)k + 0.5f) * inv_w);
+            const int cy = cy0 + row, cx = cx0 + (k - row * w);
             c = cy * g.nx + cx;
-            if (g.cell_start[c + 1] > g.cell_start[c]) {
-                const float2 zr = g.cell_z[c];
-                const float hz = 0.5f * (zr.y - zr.x);
-                // half diagonal of the cell (+0.2 % for points binned across an edge by rounding)
-                const float rc = sqrtf(0.5f * cell * cell * 1.004f + hz * hz) + 1.0e-3f;
-                keep = keep_cell(g.x0 + ((float)cx + 0.5f) * cell, g.y0 + ((float)cy + 0.5f) * cell,
-                                 0.5f * (zr.x + zr.y), rc);
-            }
+            const float2 ball = g.cell_ball[c];  // (z of the centre, radius); radius < 0: empty cell
+            if (ball.y >= 0.f)
+                keep = keep_cell(g.x0 + ((float)cx + 0.5f) * cell, g.y0 + ((float)cy + 0.5f) * cell, ball.x, ball.y);
         }
         unsigned mask = __ballot_sync(0xffffffffu, keep);
         while (mask) {
@@ -228,8 +227,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
                     [&](float x, float y, float z, float rc) {
                         const float3 T = rotate(O.R, x, y, z);
                         const float dz = T.z - B.z;
-                        return norm3df(T.x - B.x, T.y - B.y, 0.f) < O.radius_out + rc && dz < 250.f + rc &&
-                               dz > -110.f - rc;
+                        const float dx = T.x - B.x, dy = T.y - B.y, rr = O.radius_out + rc;
+                        return fmaf(dx, dx, dy * dy) < rr * rr && dz < 250.f + rc && dz > -110.f - rc;
                     },
                     [&](float4 t, bool ok) {
                         const float3 T = rotate(O.R, t.x, t.y, t.z);
@@ -245,8 +244,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
                     [&](float x, float y, float z, float rc) {
                         const float3 T = rotate(O.R, x, y, z);
                         const float dz = T.z - B.z;
-                        return norm3df(T.x - B.x, T.y - B.y, 0.f) < O.radius_in + rc &&
-                               dz < O.plus_in + rc && dz > O.minus_in - rc;
+                        const float dx = T.x - B.x, dy = T.y - B.y, rr = O.radius_in + rc;
+                        return fmaf(dx, dx, dy * dy) < rr * rr && dz < O.plus_in + rc && dz > O.minus_in - rc;
                     },
                     [&](float4 t, bool ok) {
                         const float3 T = rotate(O.R, t.x, t.y, t.z);
