@@ -143,11 +143,16 @@ __device__ __forceinline__ bool walk_filtered(const CellGrid& g, float bx, float
     // k / w without an integer division: (k + 0.5) / w is at least 0.5 / w away from an integer,
     // far more than the rounding of the float product (k < 2^20, w < 2^10)
     const float inv_w = 1.0f / (float)w;
+    // Every question asked through this walk is "is there a point such that ...", and the witness
+    // is usually close to the body: the cells are visited starting with the middle row of the
+    // square (wrapping around), not from its corner, so that a positive answer comes early.
+    const int first = (h >> 1) * w;
     for (int base = 0; base < ncell; base += 32) {
-        const int k = base + lane;
+        const int kk = base + lane;
         bool keep = false;
         int c = 0;
-        if (k < ncell) {
+        if (kk < ncell) {
+            const int k = kk + first < ncell ? kk + first : kk + first - ncell;
             const int row = (int)(((float)k + 0.5f) * inv_w);
             const int cy = cy0 + row, cx = cx0 + (k - row * w);
             c = cy * g.nx + cx;
@@ -233,7 +238,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
                     [&](float4 t, bool ok) {
                         const float3 T = rotate(O.R, t.x, t.y, t.z);
                         const float dz = T.z - B.z;
-                        const bool in_body = norm3df(T.x - B.x, T.y - B.y, 0.f) < O.radius_out &&
+                        const float dx = T.x - B.x, dy = T.y - B.y;
+                        const bool in_body = fmaf(dx, dx, dy * dy) < O.radius_out * O.radius_out &&
                                              dz < 250.f && dz > -110.f;
                         return __any_sync(0xffffffffu, ok && t.w != 0.f && in_body) != 0;
                     });
@@ -250,7 +256,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
                     [&](float4 t, bool ok) {
                         const float3 T = rotate(O.R, t.x, t.y, t.z);
                         const float dz = T.z - B.z;
-                        const bool in_reach = norm3df(T.x - B.x, T.y - B.y, 0.f) < O.radius_in &&
+                        const float dx = T.x - B.x, dy = T.y - B.y;
+                        const bool in_reach = fmaf(dx, dx, dy * dy) < O.radius_in * O.radius_in &&
                                               dz < O.plus_in && dz > O.minus_in;
                         return __any_sync(0xffffffffu, ok && t.w != 0.f && in_reach) != 0;
                     });
