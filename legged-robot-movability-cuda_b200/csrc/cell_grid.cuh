@@ -19,6 +19,8 @@ struct CellGrid {
     const float4* pts;       // cell-sorted (x, y, z, keep)
     const float2* cell_z;    // per cell (zmin, zmax)
     const float2* cell_ball; // per cell (z of the centre, radius of the bounding ball); radius < 0: empty cell
+    const float2* blk_ball;  // the same per block of 4 x 4 cells (nbx x nby blocks, aligned to cell 0)
+    int nbx, nby;
     int n;
 };
 
@@ -129,6 +131,31 @@ __global__ void scatter_kernel(CellGrid g, const float* __restrict__ xyz,
     }
 }
 
+// bounding ball of every block of 4 x 4 cells (two-level cell pruning of the positionability search)
+__global__ void block_ball_kernel(CellGrid g, const int* __restrict__ counts, const float2* __restrict__ cell_z,
+                                  float2* __restrict__ blk_ball) {
+    const int nblk = g.nbx * g.nby;
+    const float cell = 1.0f / g.inv_cell;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += gridDim.x * blockDim.x) {
+        const int bx = b % g.nbx, by = b / g.nbx;
+        float z0 = INFINITY, z1 = -INFINITY;
+        for (int j = 0; j < 16; j++) {
+            const int cx = 4 * bx + (j & 3), cy = 4 * by + (j >> 2);
+            if (cx < g.nx && cy < g.ny && counts[cy * g.nx + cx] > 0) {
+                const float2 zr = cell_z[cy * g.nx + cx];
+                z0 = fminf(z0, zr.x), z1 = fmaxf(z1, zr.y);
+            }
+        }
+        if (z1 >= z0) {
+            // half diagonal of the 4-cell square (+0.2 % as for the cells) and half the z range
+            const float hz = 0.5f * (z1 - z0);
+            blk_ball[b] = make_float2(0.5f * (z0 + z1), sqrtf(8.0f * cell * cell * 1.004f + hz * hz) + 1.0e-3f);
+        } else {
+            blk_ball[b] = make_float2(0.f, -1.f);
+        }
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 struct DevBuf {
     std::vector<void*> ptrs;
@@ -184,7 +211,9 @@ cudaError_t build_grid(DevBuf& mem, const float* xyz, size_t n, const uint8_t* k
     const int ncell = g.nx * g.ny;
     int *counts, *start, *zmin, *zmax, *cursor;
     float4* sorted;
-    float2 *cell_z, *cell_ball;
+    float2 *cell_z, *cell_ball, *blk_ball;
+    g.nbx = (g.nx + 3) / 4, g.nby = (g.ny + 3) / 4;
+    POSIT_CHECK(mem.alloc(&blk_ball, (size_t)g.nbx * g.nby));
     POSIT_CHECK(mem.alloc(&counts, ncell));
     POSIT_CHECK(mem.alloc(&start, ncell + 1));
     POSIT_CHECK(mem.alloc(&cursor, ncell));
@@ -200,8 +229,9 @@ cudaError_t build_grid(DevBuf& mem, const float* xyz, size_t n, const uint8_t* k
     scan_kernel<<<1, 1024, 0, stream>>>(counts, start, ncell);
     POSIT_CHECK(cudaMemcpyAsync(cursor, start, ncell * sizeof(int), cudaMemcpyDeviceToDevice, stream));
     scatter_kernel<<<592, 256, 0, stream>>>(g, xyz, keep, cursor, sorted, zmin, zmax, cell_z, cell_ball, counts);
+    block_ball_kernel<<<296, 256, 0, stream>>>(g, counts, cell_z, blk_ball);
     POSIT_CHECK(cudaGetLastError());
-    g.cell_start = start, g.pts = sorted, g.cell_z = cell_z, g.cell_ball = cell_ball;
+    g.cell_start = start, g.pts = sorted, g.cell_z = cell_z, g.cell_ball = cell_ball, g.blk_ball = blk_ball;
     *out = g;
     return cudaSuccess;
 }

@@ -125,10 +125,14 @@ __device__ __forceinline__ float3 rotate(const float* R, float x, float y, float
                        fmaf(R[6], x, fmaf(R[7], y, R[8] * z)));
 }
 
-// Two-level walk over the cells around (bx, by): the lanes of the warp first classify 32 cells at
-// a time with `keep_cell(centre, radius)` (a conservative "could hold a witness" test on the
-// cell's bounding ball), then the warp scans the points of the surviving cells 32 at a time.
-// `visit` returns true to stop.
+// Walk over the cells around (bx, by) with three levels of pruning.  The lanes first classify the
+// blocks of 4 x 4 cells that overlap the query square with `keep_cell(centre, radius)` — a
+// conservative "could hold a witness" test on the block's bounding ball —, then, two surviving
+// blocks at a time, their 16 cells each with the same test on the cell's ball, and the warp scans
+// the points of the surviving cells 32 at a time.  `visit` returns true to stop.
+// Every question asked through this walk is "is there a point such that ...", and the witness is
+// usually close to the body: blocks are visited starting with the middle row of the square
+// (wrapping around), not from its corner, so that a positive answer comes early.
 template <class CellF, class PointF>
 __device__ __forceinline__ bool walk_filtered(const CellGrid& g, float bx, float by, float r_xy,
                                               int lane, CellF keep_cell, PointF visit) {
@@ -136,41 +140,59 @@ __device__ __forceinline__ bool walk_filtered(const CellGrid& g, float bx, float
     const int cx1 = min((int)floorf((bx + r_xy - g.x0) * g.inv_cell), g.nx - 1);
     const int cy0 = max((int)floorf((by - r_xy - g.y0) * g.inv_cell), 0);
     const int cy1 = min((int)floorf((by + r_xy - g.y0) * g.inv_cell), g.ny - 1);
-    const int w = cx1 - cx0 + 1, h = cy1 - cy0 + 1;
-    if (w <= 0 || h <= 0) return false;
-    const int ncell = w * h;
+    if (cx1 < cx0 || cy1 < cy0) return false;
+    const int bx0 = cx0 >> 2, by0 = cy0 >> 2;
+    const int w = (cx1 >> 2) - bx0 + 1, h = (cy1 >> 2) - by0 + 1;
+    const int nblk = w * h;
     const float cell = 1.0f / g.inv_cell;
     // k / w without an integer division: (k + 0.5) / w is at least 0.5 / w away from an integer,
     // far more than the rounding of the float product (k < 2^20, w < 2^10)
     const float inv_w = 1.0f / (float)w;
-    // Every question asked through this walk is "is there a point such that ...", and the witness
-    // is usually close to the body: the cells are visited starting with the middle row of the
-    // square (wrapping around), not from its corner, so that a positive answer comes early.
     const int first = (h >> 1) * w;
-    for (int base = 0; base < ncell; base += 32) {
+    const int half = lane >> 4, sub = lane & 15;
+    for (int base = 0; base < nblk; base += 32) {
         const int kk = base + lane;
-        bool keep = false;
-        int c = 0;
-        if (kk < ncell) {
-            const int k = kk + first < ncell ? kk + first : kk + first - ncell;
+        bool keepb = false;
+        int gx = 0, gy = 0;  // block coordinates
+        if (kk < nblk) {
+            const int k = kk + first < nblk ? kk + first : kk + first - nblk;
             const int row = (int)(((float)k + 0.5f) * inv_w);
-            const int cy = cy0 + row, cx = cx0 + (k - row * w);
-            c = cy * g.nx + cx;
-            const float2 ball = g.cell_ball[c];  // (z of the centre, radius); radius < 0: empty cell
+            gy = by0 + row, gx = bx0 + (k - row * w);
+            const float2 ball = g.blk_ball[gy * g.nbx + gx];  // radius < 0: empty block
             if (ball.y >= 0.f)
-                keep = keep_cell(g.x0 + ((float)cx + 0.5f) * cell, g.y0 + ((float)cy + 0.5f) * cell, ball.x, ball.y);
+                keepb = keep_cell(g.x0 + ((float)(4 * gx) + 2.0f) * cell, g.y0 + ((float)(4 * gy) + 2.0f) * cell,
+                                  ball.x, ball.y);
         }
-        unsigned mask = __ballot_sync(0xffffffffu, keep);
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int cc = __shfl_sync(0xffffffffu, c, src);
-            const int beg = g.cell_start[cc], end = g.cell_start[cc + 1];
-            for (int i = beg; i < end; i += 32) {
-                const int q = i + lane;
-                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (q < end) p = g.pts[q];
-                if (visit(p, q < end)) return true;
+        unsigned maskb = __ballot_sync(0xffffffffu, keepb);
+        while (maskb) {
+            // two blocks at a time: lanes 0-15 take the cells of the first, lanes 16-31 of the second
+            const int s0 = __ffs(maskb) - 1;
+            maskb &= maskb - 1;
+            const int s1 = maskb ? __ffs(maskb) - 1 : -1;
+            if (s1 >= 0) maskb &= maskb - 1;
+            const int src = half ? (s1 >= 0 ? s1 : s0) : s0;
+            const int cx = 4 * __shfl_sync(0xffffffffu, gx, src) + (sub & 3);
+            const int cy = 4 * __shfl_sync(0xffffffffu, gy, src) + (sub >> 2);
+            bool keep = false;
+            int c = 0;
+            if ((half == 0 || s1 >= 0) && cx >= cx0 && cx <= cx1 && cy >= cy0 && cy <= cy1) {
+                c = cy * g.nx + cx;
+                const float2 ball = g.cell_ball[c];  // (z of the centre, radius); radius < 0: empty cell
+                if (ball.y >= 0.f)
+                    keep = keep_cell(g.x0 + ((float)cx + 0.5f) * cell, g.y0 + ((float)cy + 0.5f) * cell, ball.x, ball.y);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, keep);
+            while (mask) {
+                const int srcc = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int cc = __shfl_sync(0xffffffffu, c, srcc);
+                const int beg = g.cell_start[cc], end = g.cell_start[cc + 1];
+                for (int i = beg; i < end; i += 32) {
+                    const int q = i + lane;
+                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q < end) p = g.pts[q];
+                    if (visit(p, q < end)) return true;
+                }
             }
         }
     }
