@@ -24,7 +24,8 @@ PRESETS = {
     "c3": dict(map=[1024, 1024], poses=[256, 256, 256], legs=4, yaws=0, oct_depth=-1),
     # configs[3]: 50 M-point terrain (7168 x 7040 lattice), map replicated per GPU; the body-space
     # octree (apply_oct semantics) over all footholds + the pose search on the same map
-    "c4": dict(map=[7168, 7040], poses=[128, 128, 64], legs=4, yaws=0, oct_depth=6),
+    # (the CPU oracle manages ~5 poses/s on this map: check fewer poses)
+    "c4": dict(map=[7168, 7040], poses=[128, 128, 64], legs=4, yaws=0, oct_depth=6, check=200),
     # configs[4]: hexapod, mounts k*pi/3, dense pose lattice x yaw grid
     "c5": dict(map=[1024, 1024], poses=[256, 256, 64], legs=6, yaws=16, oct_depth=-1),
 }
