@@ -343,3 +343,24 @@ def test_every_sweep_returns_the_same_bits(lrm, monkeypatch):
         for mode in ("1", None):
             for a, b in zip(got["0"], got[mode]):
                 assert torch.equal(a, b), (name, mode)
+
+
+def test_plan_cache_eviction_keeps_results(lrm, monkeypatch):
+    """More distinct (leg, orientation) plans than the table cache holds (4), swept back to back
+    with the choice volume forced on: every sweep must rebuild / reuse atlas and volume correctly
+    (eviction while earlier sweeps are still in flight, rebuild into the evicted entry's arrays)
+    and return the bytes of the two-tier sweep."""
+    n = 4 * (1 << 20) + 77
+    lo, step, dims = lrm.lattice_spec((-100, -400, -500), (600, 400, 200), (5, 1000, 1000))
+    pts = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    lrm.make_lattice(pts, lo, step, dims, 0, n)
+    plans = [(robot, az) for robot in (1, 0) for az in (0.0, 0.7, 1.4)] + [(1, 0.0), (0, 0.7)]
+    want = {}
+    monkeypatch.setenv("LRM_CHOICE_VOLUME", "0")
+    for robot, az in plans[:6]:
+        want[(robot, az)] = lrm.reach_dist(pts, lrm.get_leg(robot, az))
+    monkeypatch.setenv("LRM_CHOICE_VOLUME", "1")
+    got = [lrm.reach_dist(pts, lrm.get_leg(robot, az)) for robot, az in plans]   # no sync in between
+    torch.cuda.synchronize()
+    for (robot, az), (fr, vec) in zip(plans, got):
+        assert torch.equal(fr, want[(robot, az)][0]) and torch.equal(vec, want[(robot, az)][1]), (robot, az)
