@@ -878,6 +878,9 @@ LRM_HD bool dist_fast(const LegPlan& L, const FastView& F, const AtlasView& A, c
 // cube byte: 0 = uncertified; else bit 7 | pair index << 1 | side (0 direct, 1 flipped) — bits 0-4
 // index the pair table viewed as YawSol[2 * kYawPairs].
 constexpr unsigned kVolPure = 0x80u;
+// bits 5-6, independent of the choice bits: reachability_circles is the same for every point of the
+// cube (bit 5), and its value (bit 6) — the reach-only sweep reads nothing else for such a point
+constexpr unsigned kVolReachKnown = 0x20u, kVolReachValue = 0x40u;
 struct VolumeView {
     cudaTextureObject_t tex;  // 3-D texture of cube bytes (point sampling, border = 0)
     float inv_cell, o, oy;    // cube coordinates = p * inv_cell + o (x, z), + oy (y)
@@ -928,9 +931,12 @@ LRM_HD ChoiceProbe choice_probe(const LegPlan& L, const SectorTable& tab, const 
 // the 4^3 sub-cubes.  choice_cell_byte is the serial composition (host emulation, reference).
 constexpr int kVolSub = 4;  // sub-cubes per axis of the refinement
 struct CellFirst {
-    unsigned byte;  // the cube byte if certified (after refinement, when refine is set), else 0
+    unsigned byte;  // the choice bits if certified (after refinement, when refine is set), else 0
     bool refine;    // the centre could not decide: all kVolSub^3 sub-cubes must pass choice_cell_sub
     bool direct;    // the centre's choice (what every sub-cube must agree with)
+    unsigned reach;      // the reach bits if certified (after refinement, when reach_refine is set), else 0
+    bool reach_refine;   // ... all sub-cubes must pass reach_cell_sub
+    bool reach_flip;     // the cube lies behind the coxa axis (x < 0): the pi-flipped solution's plane
 };
 LRM_HD float vol_pad(float h) {
     // the texture unit resolves cube coordinates to 1/256 of a cube; float rounding of the
@@ -941,12 +947,35 @@ LRM_HD CellFirst choice_cell_first(const LegPlan& L, const SectorTable& tab, con
                                    float y0, float z0, float h) {
     CellFirst out;
     out.byte = 0u, out.refine = false, out.direct = true;
+    out.reach = 0u, out.reach_refine = false, out.reach_flip = false;
     const float pad = vol_pad(h);
     const float xa = x0 - pad, xb = x0 + h + pad, ya = y0 - pad, yb = y0 + h + pad;
     if (ya <= 0.f && yb >= 0.f) return out;
     const int combo = yaw_combo(L, xa, ya);
     if (yaw_combo(L, xb, ya) != combo || yaw_combo(L, xa, yb) != combo || yaw_combo(L, xb, yb) != combo)
         return out;
+    // reachability_circles (one_leg.cu:280-319): the solution on the point's own side of the coxa
+    // axis, unsaturated yaw, plane point valid.  Needs the cube clear of the x = 0 plane too.  The
+    // plane point (+-rho - coxa, z) moves at most as far as the point does, so plane_probe's
+    // valid_safety at the centre bounds the radius within which validity cannot change.
+    if (xa > 0.f || xb < 0.f) {
+        out.reach_flip = xb < 0.f;
+        const int kind = out.reach_flip ? (combo >> 3) : (combo & 7);
+        if (kind > 1) {
+            out.reach = kVolReachKnown;  // yaw outside the coxa limits all over the cube: unreachable
+        } else {
+            const float side = h + 2.f * pad, hs = 0.5f * side;
+            const float cx = xa + hs, cy = ya + hs, cz = z0 - pad + hs;
+            const float rho = sqrtf(fmaf(cx, cx, cy * cy));
+            const PlaneProbe pr = plane_probe(L, tab, (out.reach_flip ? -rho : rho) - L.coxa_length, cz);
+            const unsigned bits = kVolReachKnown | ((pr.label & 0x40) ? kVolReachValue : 0u);
+            if (pr.valid_safety > 0.8660255f * side + 0.01f) {
+                out.reach = bits;
+            } else if (pr.valid_safety > 0.8660255f * side * (1.f / kVolSub) + 0.01f) {
+                out.reach = bits, out.reach_refine = true;
+            }
+        }
+    }
     int id = -1;
     for (int i = 0; i < FT.ncombo; i++)
         if (FT.combo[i] == combo) id = i;
@@ -982,13 +1011,30 @@ LRM_HD bool choice_cell_sub(const LegPlan& L, const SectorTable& tab, float x0, 
     const ChoiceProbe ps = choice_probe(L, tab, q);
     return ps.direct == direct && ps.margin > r1;
 }
+// sub-cube k of a cube whose centre left the reach bit open: same validity, safely
+LRM_HD bool reach_cell_sub(const LegPlan& L, const SectorTable& tab, float x0, float y0, float z0, float h,
+                           int k, bool flip, bool valid) {
+    const float pad = vol_pad(h);
+    const float side = h + 2.f * pad;
+    const float sub = side * (1.f / kVolSub), r1 = 0.8660255f * sub;
+    const float qx = x0 - pad + ((float)(k % kVolSub) + 0.5f) * sub;
+    const float qy = y0 - pad + ((float)((k / kVolSub) % kVolSub) + 0.5f) * sub;
+    const float qz = z0 - pad + ((float)(k / (kVolSub * kVolSub)) + 0.5f) * sub;
+    const float rho = sqrtf(fmaf(qx, qx, qy * qy));
+    const PlaneProbe pr = plane_probe(L, tab, (flip ? -rho : rho) - L.coxa_length, qz);
+    return ((pr.label & 0x40) != 0) == valid && pr.valid_safety > r1 + 0.01f;
+}
 LRM_HD unsigned choice_cell_byte(const LegPlan& L, const SectorTable& tab, const FastTables& FT, float x0,
                                  float y0, float z0, float h) {
     const CellFirst f = choice_cell_first(L, tab, FT, x0, y0, z0, h);
-    if (!f.refine) return f.byte;
-    for (int k = 0; k < kVolSub * kVolSub * kVolSub; k++)
-        if (!choice_cell_sub(L, tab, x0, y0, z0, h, k, f.direct)) return 0u;
-    return f.byte;
+    unsigned byte = f.byte, reach = f.reach;
+    if (f.refine)
+        for (int k = 0; k < kVolSub * kVolSub * kVolSub && byte; k++)
+            if (!choice_cell_sub(L, tab, x0, y0, z0, h, k, f.direct)) byte = 0u;
+    if (f.reach_refine)
+        for (int k = 0; k < kVolSub * kVolSub * kVolSub && reach; k++)
+            if (!reach_cell_sub(L, tab, x0, y0, z0, h, k, f.reach_flip, (reach & kVolReachValue) != 0)) reach = 0u;
+    return byte | reach;
 }
 
 // One point of a certified cube: the chosen solution only.  Same arithmetic as dist_fast for that

@@ -156,8 +156,11 @@ __global__ void __launch_bounds__(kThreads)
                           const float* __restrict__ in_y, const float* __restrict__ in_z,
                           float* __restrict__ out_x, float* __restrict__ out_y,
                           float* __restrict__ out_z, uint8_t* __restrict__ out_flag, size_t n,
-                          const int* __restrict__ gate, int gate_want) {
-    if (gate != nullptr && *gate != gate_want) return;  // the coherence probe chose the other sweep
+                          const int* __restrict__ gate, int gate_want, const VolumeView vol) {
+    if (gate != nullptr && gate_want >= 0 && *gate != gate_want) return;  // the coherence probe chose the other sweep
+    // reach-only: gate_want < 0 means "read the reach bits of the choice volume if the probe found
+    // the input coherent"; vol.tex == 0: no volume (yet)
+    const bool reach_vol = vol.tex != 0 && (gate == nullptr || *gate == 1);
     // keep the pointer provably in the shared window (LDS/STS, not generic LD/ST): no integer
     // round-trip on the address; the bulk engine only needs 16-byte alignment
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -234,6 +237,34 @@ __global__ void __launch_bounds__(kThreads)
         float* vec = in;  // in place (unused in reach-only mode)
         uint8_t* flag = S.flag[ob];
         if constexpr (kReachAtlas) {
+            if (reach_vol && cnt == (uint32_t)kTile) {
+                // The cube of a point may be reachable, or unreachable, as a whole (reach bits of
+                // the choice volume): such a point needs nothing but its cube byte.  All of a
+                // thread's volume fetches are in flight together; the few points in undecided
+                // cubes take the yaw tests + atlas cell below.
+                constexpr int kPer = kTile / kThreads;
+                CoxaPoint p[kPer];
+                unsigned c[kPer];
+#pragma unroll
+                for (int k = 0; k < kPer; k++) {
+                    const int i = tid + k * kThreads;
+                    float x, y, z;
+                    if (SOA) {
+                        x = in[i], y = in[kTile + i], z = in[2 * kTile + i];
+                    } else {
+                        x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+                    }
+                    p[k] = to_coxa_frame(L, x, y, z);
+                    c[k] = tex3D<unsigned char>(vol.tex, fmaf(p[k].x, vol.inv_cell, vol.o),
+                                                fmaf(p[k].y, vol.inv_cell, vol.oy), fmaf(p[k].z, vol.inv_cell, vol.o));
+                }
+#pragma unroll
+                for (int k = 0; k < kPer; k++) {
+                    const bool r = (c[k] & kVolReachKnown) ? (c[k] & kVolReachValue) != 0u
+                                                           : reach_coxa_frame_atlas<TEX>(L, S.table, atlas, p[k]);
+                    flag[tid + k * kThreads] = r ? 1 : 0;
+                }
+            } else
 #pragma unroll 2
             for (int i = tid; i < (int)cnt; i += kThreads) {
                 float x, y, z;
@@ -865,7 +896,7 @@ template <int MODE, bool SOA, bool GENERIC, bool FAST, bool TEX>
 cudaError_t launch_stream_impl(const LegPlan& plan, const FastTables& ft, const AtlasView& atlas,
                                const float* ix, const float* iy, const float* iz, float* ox, float* oy,
                                float* oz, uint8_t* flag, size_t n, cudaStream_t stream,
-                               const int* gate = nullptr, int gate_want = 0) {
+                               const int* gate = nullptr, int gate_want = 0, const VolumeView* vol = nullptr) {
     auto kernel = one_leg_stream_kernel<MODE, SOA, GENERIC, FAST, TEX>;
     constexpr size_t smem = sizeof(StreamSmem<MODE, FAST>);
     // per-device: the attribute belongs to the device's copy of the function
@@ -886,8 +917,9 @@ cudaError_t launch_stream_impl(const LegPlan& plan, const FastTables& ft, const 
     size_t grid = (size_t)sm_count() * ctas_per_sm;
     if (tiles < grid) grid = tiles;
     if (grid == 0) grid = 1;
+    VolumeView no_volume{};
     kernel<<<(unsigned)grid, kThreads, smem, stream>>>(plan, ft, atlas, ix, iy, iz, ox, oy, oz, flag, n, gate,
-                                                       gate_want);
+                                                       gate_want, vol ? *vol : no_volume);
     return cudaGetLastError();
 }
 
@@ -1004,9 +1036,25 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
             AtlasView atlas;
             cudaError_t e = get_plane_atlas(plan, stream, &atlas, nullptr);
             if (e != cudaSuccess) return e;
-            if (atlas_through_texture())
+            if (atlas_through_texture()) {
+                // reach bits of the choice volume (built in the background on first request); as for
+                // the distance sweeps, only for inputs the coherence probe finds spatially ordered
+                FastTables ft;
+                const int vmode = choice_volume_mode();
+                VolumeView vol{};
+                if (vmode != 0 && get_plane_atlas(plan, stream, &atlas, &ft) == cudaSuccess &&
+                    get_choice_volume(plan, stream, &vol, /*wait=*/vmode == 1) == cudaSuccess) {
+                    int* verdict = vmode == 2 ? next_verdict_word() : nullptr;
+                    if (verdict != nullptr)
+                        coherence_probe_kernel<SOA><<<1, 256, 0, stream>>>(ix, iy, iz, n, 2.0f / vol.inv_cell, verdict);
+                    if (vmode == 1 || verdict != nullptr)
+                        return launch_stream_impl<MODE, SOA, false, MODE == kModeReach, true>(
+                            plan, no_tables, atlas, ix, iy, iz, ox, oy, oz, flag, n, stream, verdict, -1, &vol);
+                }
+                (void)cudaGetLastError();
                 return launch_stream_impl<MODE, SOA, false, MODE == kModeReach, true>(
                     plan, no_tables, atlas, ix, iy, iz, ox, oy, oz, flag, n, stream);
+            }
             return launch_stream_impl<MODE, SOA, false, MODE == kModeReach, false>(
                 plan, no_tables, atlas, ix, iy, iz, ox, oy, oz, flag, n, stream);
         }

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128)
         const int ix = (int)(i % dim), iy = (int)((i / dim) % dim), iz = (int)(i / ((size_t)dim * dim));
         const float x0 = ((float)ix - half) * cell, y0 = ((float)iy - half - kVolShiftY) * cell, z0 = ((float)iz - half) * cell;
         CellFirst f;
-        f.byte = 0u, f.refine = false, f.direct = true;
+        f.byte = 0u, f.refine = false, f.direct = true, f.reach = 0u, f.reach_refine = false, f.reach_flip = false;
         if (live) f = choice_cell_first(L, table, FT, x0, y0, z0, cell);
         unsigned need = __ballot_sync(0xffffffffu, f.refine);
         while (need) {
@@ -79,7 +79,20 @@ __global__ void __launch_bounds__(128)
             const bool all = __all_sync(0xffffffffu, ok);
             if (lane == src && !all) f.byte = 0u;
         }
-        if (live) linear[i] = (unsigned char)f.byte;
+        need = __ballot_sync(0xffffffffu, f.reach_refine);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const float sx = __shfl_sync(0xffffffffu, x0, src), sy = __shfl_sync(0xffffffffu, y0, src),
+                        sz = __shfl_sync(0xffffffffu, z0, src);
+            const unsigned sbits = __shfl_sync(0xffffffffu, f.reach | (f.reach_flip ? 1u : 0u), src);
+            const bool flip = (sbits & 1u) != 0u, valid = (sbits & kVolReachValue) != 0u;
+            const bool ok = reach_cell_sub(L, table, sx, sy, sz, cell, lane, flip, valid) &&
+                            reach_cell_sub(L, table, sx, sy, sz, cell, lane + 32, flip, valid);
+            const bool all = __all_sync(0xffffffffu, ok);
+            if (lane == src && !all) f.reach = 0u;
+        }
+        if (live) linear[i] = (unsigned char)(f.byte | f.reach);
     }
 }
 

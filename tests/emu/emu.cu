@@ -133,7 +133,8 @@ size_t emu_dist_atlas(const float* xyz, size_t n, const lrm_leg_t* leg, const fl
 // device build kernel uses (choice_cell_byte).  tiers[0..3] = points decided by tier 1, dist_fast, dist_choice_clamp, the full evaluation.
 void emu_dist_choice(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, int dim,
                      float cell, float vol_h, int vol_dim, float* out_vec, uint8_t* out_flag,
-                     uint8_t* out_reach, size_t* tiers, uint8_t* out_tier) {
+                     uint8_t* out_reach, size_t* tiers, uint8_t* out_tier, uint8_t* out_reach_vol,
+                     size_t* reach_known) {
     lrm::LegPlan L;
     lrm::build_leg_plan(*leg, quat, &L);
     lrm::SectorTable tab;
@@ -142,6 +143,7 @@ void emu_dist_choice(const float* xyz, size_t n, const lrm_leg_t* leg, const flo
     lrm::fill_winner_table(L, &win, 0, 1);
     lrm::FastTables ft;
     lrm::build_fast_tables(L, &ft);
+    if (reach_known) *reach_known = 0;
     const float origin = -0.5f * dim * cell;
     std::vector<unsigned char> cells((size_t)dim * dim);
     const float need = lrm::kAtlasNeedFactor * cell + lrm::kAtlasNeedSlack;
@@ -170,6 +172,14 @@ void emu_dist_choice(const float* xyz, size_t n, const lrm_leg_t* leg, const flo
                 it = cubes.emplace(key, b).first;
             }
             cube = it->second;
+        }
+        if (out_reach_vol) {  // the reach-only sweep: reach bits of the cube, else the atlas path
+            if (cube & lrm::kVolReachKnown) {
+                out_reach_vol[i] = (cube & lrm::kVolReachValue) ? 1 : 0;
+                if (reach_known) ++*reach_known;
+            } else {
+                out_reach_vol[i] = lrm::reach_coxa_frame_atlas<false>(L, tab, A, p) ? 1 : 0;
+            }
         }
         lrm::DistResult r;
         int tier = 0;

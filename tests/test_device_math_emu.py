@@ -171,7 +171,7 @@ def test_choice_volume_never_changes_a_result(emu, port):
     from the function the device build kernel runs (choice_cell_byte)."""
     vp, sz = ctypes.c_void_p, ctypes.c_size_t
     emu.emu_dist_choice.argtypes = [vp, sz, vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float,
-                                    ctypes.c_int, vp, vp, vp, vp, vp]
+                                    ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
     rng = np.random.default_rng(41)
     idx = rng.integers(0, 1000, (120000, 3))
     lo, hi = np.array([-100, -400, -500], np.float32), np.array([600, 400, 200], np.float32)
@@ -187,16 +187,22 @@ def test_choice_volume_never_changes_a_result(emu, port):
         cx, cy = np.float32(leg[1]) * np.cos(az), np.float32(leg[1]) * np.sin(az)
         ring = np.stack([cx + 200.0 * np.cos(near), cy + 200.0 * np.sin(near), np.full_like(near, -120.0)], 1)
         pts = np.ascontiguousarray(np.concatenate([cloud, ring]), np.float32)
-        _, base, bf, br = run_emu(emu, pts, leg, q)
+        r0, base, bf, br = run_emu(emu, pts, leg, q)
         out = np.zeros_like(pts)
         fl = np.zeros(len(pts), np.uint8)
         rf = np.zeros(len(pts), np.uint8)
+        rv = np.zeros(len(pts), np.uint8)
         tier = np.zeros(len(pts), np.uint8)
         tiers = (ctypes.c_size_t * 4)()
+        known = ctypes.c_size_t(0)
         emu.emu_dist_choice(pts.ctypes.data, len(pts), leg.ctypes.data, q.ctypes.data, 2048, 1.0, cell,
                             int(1536 / cell), out.ctypes.data, fl.ctypes.data, rf.ctypes.data, tiers,
-                            tier.ctypes.data)
+                            tier.ctypes.data, rv.ctypes.data, ctypes.byref(known))
         assert np.array_equal(fl, bf) and np.array_equal(rf, br), (robot, az)
+        # the reach-only sweep through the cube's reach bits equals reachability_circles, and most
+        # of the cloud is decided by those bits alone
+        assert np.array_equal(rv, r0), (robot, az, int((rv != r0).sum()))
+        assert known.value > 0.8 * len(pts), (robot, az, known.value / len(pts))
         assert np.array_equal(out, base), (robot, az, float(np.abs(out - base).max()))
         # the volume must be worth having on the bench box (first 120 000 points)
         assert (tier[:120000] == 0).mean() > want_share, (robot, az, float((tier[:120000] == 0).mean()))
