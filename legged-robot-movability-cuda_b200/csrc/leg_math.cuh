@@ -1082,4 +1082,26 @@ LRM_HD void dist_choice_clamp(const LegPlan& L, const SectorTable& tab, const Ya
     out->dz = fmaf(L.Mo[6], b.vx, fmaf(L.Mo[7], b.vy, L.Mo[8] * b.vz));
 }
 
+// The same question for the full plan of the distance entry points (no gravity side, both coxa
+// solutions count: distance_circles' flag is res || resflip): can any point within `rc` of the
+// coxa-frame point p be reachable?  Conservative; `wedge` says the yaw limits span less than pi.
+// Used by the body-space octree: a foothold farther than the child's half diagonal from a leg's
+// workspace can neither be reached by that leg nor have its distance vector land inside the child.
+LRM_HD bool leg_ball_possible(const LegPlan& L, const CoxaPoint p, float rc, bool wedge) {
+    const float rho2 = fmaf(p.x, p.x, p.y * p.y);
+    const float rho = sqrtf(rho2);
+    const float lo = fmaxf(L.inner.r - rc - 0.01f, 0.f), hi = L.outer.r + rc + 0.01f;
+    const float xa = rho - L.coxa_length, xb = -rho - L.coxa_length;
+    const float da2 = fmaf(xa, xa, p.z * p.z), db2 = fmaf(xb, xb, p.z * p.z);
+    bool ring_a = da2 >= lo * lo && da2 <= hi * hi, ring_b = db2 >= lo * lo && db2 <= hi * hi;
+    if (wedge && rho > rc) {
+        // inner side of both limit lines through the coxa axis, see reach_ball_possible
+        const float d_min = fmaf(L.cos_min, p.y, -L.sin_min * p.x), d_max = fmaf(L.sin_max, p.x, -L.cos_max * p.y);
+        const float slack = rc + 0.01f;
+        ring_a = ring_a && d_min >= -slack && d_max >= -slack;
+        ring_b = ring_b && d_min <= slack && d_max <= slack;
+    }
+    return ring_a || ring_b;
+}
+
 }  // namespace lrm

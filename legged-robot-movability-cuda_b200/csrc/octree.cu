@@ -87,7 +87,7 @@ struct ChildTask {
     int n_samples;      // 27 when parent half extent < EnableRotBelow, else 1
     int parent_valid;
     int skip;           // child already valid before the pass (dead quadrant or processed)
-    int pad;
+    int wedge;          // the coxa yaw limits span less than pi (cell / foothold pruning)
 };
 
 __device__ __forceinline__ bool in_box(float x, float y, float z, const float* h) {
@@ -106,6 +106,11 @@ __global__ void __launch_bounds__(256) oct_validity_kernel(const ChildTask* __re
     const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const float edge_raw = T.box.h[0] * T.box.h[0] + T.box.h[1] * T.box.h[1] + T.box.h[2] * T.box.h[2];
     const bool by_box = edge_raw > kConvexRadius * kConvexRadius;
+    // A leg matters for a foothold only if it reaches it or its distance vector lands inside the
+    // child (|d| at most the child's half diagonal, or the convex radius rule): a foothold farther
+    // than that from the leg's workspace skips the leg's distance evaluation — exactly, the
+    // returned vector always ends on the workspace boundary, so it is at least that long.
+    const float far = sqrtf(edge_raw + T.margin) * 1.001f + 0.05f;
 
     // cells overlapping the elongated box around the child centre
     const int cx0 = max((int)floorf((T.box.c[0] - T.elong[0] - g.x0) * g.inv_cell), 0);
@@ -132,9 +137,11 @@ __global__ void __launch_bounds__(256) oct_validity_kernel(const ChildTask* __re
                     for (int leg = 0; leg < kLegs; leg++) {
                         const LegPlan& L = plans[a * kLegs + leg];
                         const SectorTable& tab = *reinterpret_cast<const SectorTable*>(&L.sector[0]);
+                        const CoxaPoint pc = to_coxa_frame(L, vx, vy, vz);
+                        if (!leg_ball_possible(L, pc, far, T.wedge != 0)) continue;
                         // distance() = distance_global (one_leg_global.cu:253-264)
-                        const DistResult d = L.generic ? dist_coxa_frame<true>(L, tab, to_coxa_frame(L, vx, vy, vz))
-                                                       : dist_coxa_frame<false>(L, tab, to_coxa_frame(L, vx, vy, vz));
+                        const DistResult d = L.generic ? dist_coxa_frame<true>(L, tab, pc)
+                                                       : dist_coxa_frame<false>(L, tab, pc);
                         reach += d.flag ? 1 : 0;
                         const bool in = by_box ? in_box(d.dx, d.dy, d.dz, T.box.h)  // :99-103
                                                : (d.dx * d.dx + d.dy * d.dy + d.dz * d.dz) < edge_raw + T.margin;
@@ -257,6 +264,7 @@ cudaError_t run_octree(const float* d_footholds, size_t nt, const lrm_leg_t& leg
                 t.margin = rot ? 0.f : kRotBelow / 3;
                 t.n_samples = rot ? kSamples : 1;
                 t.parent_valid = parent.validity ? 1 : 0;
+                t.wedge = (leg.max_angle_coxa >= leg.min_angle_coxa && leg.max_angle_coxa - leg.min_angle_coxa < 3.0f) ? 1 : 0;
                 tasks.push_back(t);
             }
             parent.raw = false;
