@@ -123,9 +123,28 @@ __global__ void __launch_bounds__(256) oct_validity_kernel(const ChildTask* __re
         const int ncell = w * h;
         // (slice, warp) pairs stride over the cells; lanes over the footholds of a cell
         for (int k = blockIdx.x * nwarp + warp; k < ncell; k += slices * nwarp) {
-            const int c = (cy0 + k / w) * g.nx + cx0 + k % w;
+            const int ccx = cx0 + k % w, ccy = cy0 + k / w;
+            const int c = ccy * g.nx + ccx;
             const float2 zr = g.cell_z[c];
             if (zr.x > T.box.c[2] + T.elong[2] || zr.y < T.box.c[2] - T.elong[2]) continue;
+            // the same question for the whole cell (its bounding ball): lanes 0..n_samples*4-1 take
+            // one (sample, leg) plan each; a cell no plan can care about is not even read
+            {
+                const float2 ball = g.cell_ball[c];
+                if (ball.y < 0.f) continue;
+                const float cell = 1.0f / g.inv_cell;
+                const float bx = g.x0 + ((float)ccx + 0.5f) * cell - T.box.c[0];
+                const float by = g.y0 + ((float)ccy + 0.5f) * cell - T.box.c[1];
+                const float bz = ball.x - T.box.c[2];
+                bool any = false;
+                for (int q = lane; q < T.n_samples * kLegs; q += 32) {
+                    const LegPlan& L = plans[q];
+                    any = any || leg_ball_possible(L, to_coxa_frame(L, bx, by, bz), far + ball.y, T.wedge != 0);
+                }
+                // a valid parent marks the child for ANY foothold inside the elongated box (bit 1/2
+                // of the flags do not depend on the legs then): such cells must be read
+                if (!__any_sync(0xffffffffu, any) && !T.parent_valid) continue;
+            }
             const int beg = g.cell_start[c], end = g.cell_start[c + 1];
             for (int i = beg + lane; i < end; i += 32) {
                 const float4 f = g.pts[i];
