@@ -31,68 +31,6 @@ namespace {
 
 constexpr int kWarpsPerCta = 16;
 
-// ---- warp-level cell walk ----------------------------------------------------------------------
-// Calls visit(point) for map points near (bx, by, bz); `visit` returns true to stop the walk.
-// Visits a superset of every point with |xy offset| <= r_xy and |z offset| <= r_z.
-template <class F>
-__device__ __forceinline__ bool walk_cells(const CellGrid& g, float bx, float by, float bz,
-                                           float r_xy, float r_z, int lane, F visit) {
-    const int cx0 = max((int)floorf((bx - r_xy - g.x0) * g.inv_cell), 0);
-    const int cx1 = min((int)floorf((bx + r_xy - g.x0) * g.inv_cell), g.nx - 1);
-    const int cy0 = max((int)floorf((by - r_xy - g.y0) * g.inv_cell), 0);
-    const int cy1 = min((int)floorf((by + r_xy - g.y0) * g.inv_cell), g.ny - 1);
-    for (int cy = cy0; cy <= cy1; cy++) {
-        for (int cx = cx0; cx <= cx1; cx++) {
-            const int c = cy * g.nx + cx;
-            const float2 zr = g.cell_z[c];
-            if (zr.x > bz + r_z || zr.y < bz - r_z) continue;
-            const int beg = g.cell_start[c], end = g.cell_start[c + 1];
-            for (int i = beg; i < end; i += 32) {
-                const int k = i + lane;
-                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k < end) p = g.pts[k];
-                if (visit(p, k < end)) return true;
-            }
-        }
-    }
-    return false;
-}
-
-// ---- pre-cull (multi_rot_estimator constructor, several_leg.cu:371-374,413-502) ----------------
-__global__ void body_precull_kernel(CellGrid map, const float* __restrict__ bodies, size_t nb,
-                                    uint8_t* __restrict__ alive) {
-    const int lane = threadIdx.x & 31;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t b = warp; b < nb; b += nwarps) {
-        const float bx = bodies[3 * b], by = bodies[3 * b + 1], bz = bodies[3 * b + 2];
-        bool close = false;
-        const bool collide = walk_cells(map, bx, by, bz, 400.f, 400.f, lane, [&](float4 t, bool ok) {
-            const float d = norm3df(bx - t.x, by - t.y, bz - t.z);
-            const bool c400 = __any_sync(0xffffffffu, ok && d < 400.f) != 0;  // eliminateFarBody
-            close = close || c400;
-            return __any_sync(0xffffffffu, ok && d < 60.f) != 0;  // eliminateAlwaysColliding
-        });
-        if (lane == 0) alive[b] = (!collide && close) ? 1 : 0;
-    }
-}
-
-// eliminateFarTarget: a map point survives if some surviving body lies within 400 mm of it
-__global__ void target_precull_kernel(CellGrid body_grid, const float* __restrict__ map, size_t nt,
-                                      uint8_t* __restrict__ keep) {
-    const int lane = threadIdx.x & 31;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t t = warp; t < nt; t += nwarps) {
-        const float tx = map[3 * t], ty = map[3 * t + 1], tz = map[3 * t + 2];
-        const bool found = walk_cells(body_grid, tx, ty, tz, 400.f, 400.f, lane, [&](float4 b, bool ok) {
-            return __any_sync(0xffffffffu, ok && b.w != 0.f &&
-                                               norm3df(tx - b.x, ty - b.y, tz - b.z) < 400.f) != 0;
-        });
-        if (lane == 0) keep[t] = found ? 1 : 0;
-    }
-}
-
 // ---- the search --------------------------------------------------------------------------------
 struct OrientConsts {
     float R[9];        // qtRotate(quat, .) as a matrix (rotateData, several_leg.cu:401-411)
@@ -197,6 +135,47 @@ __device__ __forceinline__ bool walk_filtered(const CellGrid& g, float bx, float
         }
     }
     return false;
+}
+
+// ---- pre-cull (multi_rot_estimator constructor, several_leg.cu:371-374,413-502) ----------------
+// eliminateAlwaysColliding (a map point within 60 mm) and eliminateFarBody (none within 400 mm)
+__global__ void body_precull_kernel(CellGrid map, const float* __restrict__ bodies, size_t nb,
+                                    uint8_t* __restrict__ alive) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t b = warp; b < nb; b += nwarps) {
+        const float bx = bodies[3 * b], by = bodies[3 * b + 1], bz = bodies[3 * b + 2];
+        auto within = [&](float r) {
+            return walk_filtered(
+                map, bx, by, r, lane,
+                [&](float x, float y, float z, float rc) { return norm3df(x - bx, y - by, z - bz) < r + rc; },
+                [&](float4 t, bool ok) {
+                    return __any_sync(0xffffffffu, ok && norm3df(bx - t.x, by - t.y, bz - t.z) < r) != 0;
+                });
+        };
+        const bool keep = !within(60.f) && within(400.f);
+        if (lane == 0) alive[b] = keep ? 1 : 0;
+    }
+}
+
+// eliminateFarTarget: a map point survives if some surviving body lies within 400 mm of it
+__global__ void target_precull_kernel(CellGrid body_grid, const float* __restrict__ map, size_t nt,
+                                      uint8_t* __restrict__ keep) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t t = warp; t < nt; t += nwarps) {
+        const float tx = map[3 * t], ty = map[3 * t + 1], tz = map[3 * t + 2];
+        const bool found = walk_filtered(
+            body_grid, tx, ty, 400.f, lane,
+            [&](float x, float y, float z, float rc) { return norm3df(x - tx, y - ty, z - tz) < 400.f + rc; },
+            [&](float4 b, bool ok) {
+                return __any_sync(0xffffffffu, ok && b.w != 0.f &&
+                                                   norm3df(tx - b.x, ty - b.y, tz - b.z) < 400.f) != 0;
+            });
+        if (lane == 0) keep[t] = found ? 1 : 0;
+    }
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(const SearchParams P) {
@@ -325,7 +304,6 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
     DevBuf mem;
     // ~48 map points per cell: fine enough for the cell-level pruning to bite, coarse enough that
     // a query touches a few hundred cells
-    const float cell = 128.f;   // pre-cull grids (400 mm spheres)
     const float map_cell = 0.f; // search grid: sized from the map density inside build_grid
 
     // per-orientation / per-leg constants
@@ -394,13 +372,13 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
     CellGrid map_grid;
     if (p.pre_cull) {
         CellGrid raw;
-        cudaError_t e = build_grid(mem, p.map, p.nt, nullptr, cell, stream, &raw);
+        cudaError_t e = build_grid(mem, p.map, p.nt, nullptr, map_cell, stream, &raw);
         if (e != cudaSuccess) return finish(e);
         if ((e = mem.alloc(&alive, p.nb)) != cudaSuccess) return finish(e);
         if ((e = mem.alloc(&keep, p.nt)) != cudaSuccess) return finish(e);
         body_precull_kernel<<<148 * 8, 256, 0, stream>>>(raw, p.bodies, p.nb, alive);
         CellGrid body_grid;
-        if ((e = build_grid(mem, p.bodies, p.nb, alive, cell, stream, &body_grid)) != cudaSuccess)
+        if ((e = build_grid(mem, p.bodies, p.nb, alive, map_cell, stream, &body_grid)) != cudaSuccess)
             return finish(e);
         target_precull_kernel<<<148 * 8, 256, 0, stream>>>(body_grid, p.map, p.nt, keep);
         if ((e = build_grid(mem, p.map, p.nt, keep, map_cell, stream, &map_grid)) != cudaSuccess)
