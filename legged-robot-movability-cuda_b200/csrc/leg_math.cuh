@@ -1040,6 +1040,51 @@ LRM_HD unsigned choice_cell_byte(const LegPlan& L, const SectorTable& tab, const
 // One point of a certified cube: the chosen solution only.  Same arithmetic as dist_fast for that
 // solution.  Straight-line; returns 0 = done, 1 = cube uncertified (dist_fast can still decide the
 // point), 2 = the chosen solution's plane cell is uncertified (full evaluation).
+// dist_choice in two halves, for the streaming kernel: the front half ends with the atlas fetch,
+// the back half finishes the point.  RULE = false drops the limit-plane rule (one_leg.cu:258-274),
+// which can only fire when the plane point is valid (bit 6 of the cell): the kernel takes that
+// version when no point of a warp's trip has a valid plane point — most of the far field — and
+// gets the same bits for less work.
+struct ChoiceFront {
+    float cs, ss, X;
+    unsigned la;
+};
+template <bool TEX>
+LRM_HD ChoiceFront dist_choice_front(const LegPlan& L, const YawSol* sols, unsigned cube, const AtlasView& A,
+                                     const CoxaPoint p) {
+    const YawSol& s = sols[cube & 31u];
+    const float rho2 = fmaf(p.x, p.x, p.y * p.y);
+    const float inv_rho = fast_rsqrt(rho2 > 1.0e-12f ? rho2 : 1.f);
+    const float ux = p.x * inv_rho, uy = p.y * inv_rho;
+    ChoiceFront f;
+    f.cs = fmaf(s.k, ux, s.c_cs), f.ss = fmaf(s.k, uy, s.c_ss);
+    f.X = fmaf(p.x, f.cs, p.y * f.ss) - L.coxa_length;
+    f.la = atlas_fetch<TEX>(A, fmaf(f.X, A.inv_cell, A.ox), fmaf(p.z, A.inv_cell, A.oy));
+    return f;
+}
+template <bool RULE>
+LRM_HD int dist_choice_back(const LegPlan& L, const YawSol* sols, unsigned cube, const ChoiceFront& f,
+                            const WinnerTable& W, const CoxaPoint p, DistResult* out) {
+    const YawSol& s = sols[cube & 31u];
+    const float yr = fmaf(p.y, f.cs, -p.x * f.ss);
+    const PlaneResult pl = plane_from_label(W, f.la, f.X, p.z);
+    float vx, vy, vz;
+    bool res;
+    if (RULE) {
+        const float yl = fmaf(p.y, s.cl, -p.x * s.sl);
+        const BranchResult b = fast_branch(p, s, f.cs, f.ss, yr, yl, pl);
+        vx = b.vx, vy = b.vy, vz = b.vz, res = b.res;
+    } else {
+        // pl.valid is false: to_plane and res are false, the vector is the in-plane one rotated back
+        vx = fmaf(pl.dx, f.cs, -yr * f.ss), vy = fmaf(pl.dx, f.ss, yr * f.cs), vz = pl.dy, res = false;
+    }
+    out->flag = res;
+    out->reach = res & (((cube & 1u) != 0u) == (f2i(p.x) < 0));
+    out->dx = fmaf(L.Mo[0], vx, fmaf(L.Mo[1], vy, L.Mo[2] * vz));
+    out->dy = fmaf(L.Mo[3], vx, fmaf(L.Mo[4], vy, L.Mo[5] * vz));
+    out->dz = fmaf(L.Mo[6], vx, fmaf(L.Mo[7], vy, L.Mo[8] * vz));
+    return (cube & kVolPure) ? ((f.la & kAtlasPure) ? 0 : 2) : 1;
+}
 template <bool TEX>
 LRM_HD int dist_choice(const LegPlan& L, const YawSol* sols, unsigned cube, const AtlasView& A,
                        const WinnerTable& W, const CoxaPoint p, DistResult* out) {

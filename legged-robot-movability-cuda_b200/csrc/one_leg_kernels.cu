@@ -710,8 +710,18 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
             load_pt(j, pj.x, pj.y, pj.z);  // both loads before any store: the tile is updated in place
             const unsigned ci = flag[i], cj = flag[j];
             DistResult ri, rj;
-            const int si = dist_choice<true>(L, sols, ci, atlas, S.winners, pi, &ri);
-            const int sj = dist_choice<true>(L, sols, cj, atlas, S.winners, pj, &rj);
+            const ChoiceFront fi = dist_choice_front<true>(L, sols, ci, atlas, pi);
+            const ChoiceFront fj = dist_choice_front<true>(L, sols, cj, atlas, pj);
+            // the limit-plane rule needs a valid plane point: skipped when no lane of the warp has
+            // one in this trip (full tiles: the warp is converged here)
+            int si, sj;
+            if (cnt != (uint32_t)kTL || __any_sync(0xffffffffu, ((fi.la | fj.la) & 0x40u) != 0u)) {
+                si = dist_choice_back<true>(L, sols, ci, fi, S.winners, pi, &ri);
+                sj = dist_choice_back<true>(L, sols, cj, fj, S.winners, pj, &rj);
+            } else {
+                si = dist_choice_back<false>(L, sols, ci, fi, S.winners, pi, &ri);
+                sj = dist_choice_back<false>(L, sols, cj, fj, S.winners, pj, &rj);
+            }
             if (si == 0) store_pt(i, ri);
             if ((sj == 0) & has_j) store_pt(j, rj);
             if (si != 0) park(i, si, ci);
