@@ -993,7 +993,10 @@ LRM_HD CellFirst choice_cell_first(const LegPlan& L, const SectorTable& tab, con
     out.direct = pc.direct;
     if (pc.margin > r0) {
         out.byte = kVolPure | ((unsigned)id << 1) | (pc.direct ? 0u : 1u);
-    } else if (pc.margin > -0.5f * r0) {  // hopeless cubes are not refined
+    } else if (pc.margin > 0.25f * r0) {
+        // Refinement needs every sub-cube centre to clear r0 / 4.  Below -r0 / 2 at the centre that is
+        // impossible (the margin is 1-Lipschitz), below r0 / 4 it would take a local minimum of the
+        // margin at the centre: not worth 64 probes.
         out.byte = kVolPure | ((unsigned)id << 1) | (pc.direct ? 0u : 1u);
         out.refine = true;
     }

@@ -43,13 +43,46 @@ __global__ void atlas_build_kernel(const __grid_constant__ LegPlan L, unsigned c
     }
 }
 
+// Coarse pass of the volume build: one thread per block of 4 x 4 x 4 cubes.  The certification is
+// scale-free: a block whose centre decides both the choice and the reach bits for the WHOLE block
+// (no refinement needed) hands that byte to its 64 cubes; the fine pass below only looks at the
+// cubes of the other blocks — the shells around the decision surfaces.
+__global__ void __launch_bounds__(128)
+    volume_coarse_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
+                         unsigned char* __restrict__ linear, unsigned char* __restrict__ block_done, int dim,
+                         float cell) {
+    __shared__ SectorTable table;
+    fill_sector_table(L, &table, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int bd = dim >> 2;
+    const size_t total = (size_t)bd * bd * bd;
+    const float half = 0.5f * (float)dim;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int bx = (int)(i % bd), by = (int)((i / bd) % bd), bz = (int)(i / ((size_t)bd * bd));
+        const float x0 = ((float)(4 * bx) - half) * cell, y0 = ((float)(4 * by) - half - kVolShiftY) * cell,
+                    z0 = ((float)(4 * bz) - half) * cell;
+        const CellFirst f = choice_cell_first(L, table, FT, x0, y0, z0, 4.f * cell);
+        const bool done = f.byte != 0u && !f.refine && f.reach != 0u && !f.reach_refine;
+        block_done[i] = done ? 1 : 0;
+        if (done) {
+            const unsigned b = f.byte | f.reach;
+            const uint32_t four = b * 0x01010101u;  // four cubes along x, 4-byte aligned (dim % 4 == 0)
+            for (int dz = 0; dz < 4; dz++)
+                for (int dy = 0; dy < 4; dy++)
+                    *reinterpret_cast<uint32_t*>(linear + ((size_t)(4 * bz + dz) * dim + (size_t)(4 * by + dy)) * dim +
+                                                 4 * bx) = four;
+        }
+    }
+}
+
 // One lane per cube of the choice volume (x fastest, like the 3-D array upload).  Cubes whose centre
 // cannot decide are refined on 4^3 sub-cubes; those cubes hug the decision surfaces (a few lanes
 // per warp), so the warp refines them one after the other with all 32 lanes, two sub-cubes each,
 // instead of leaving 29 lanes idle while three of them run 64 probes.
 __global__ void __launch_bounds__(128)
     volume_build_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
-                        unsigned char* __restrict__ linear, int dim, float cell) {
+                        unsigned char* __restrict__ linear, const unsigned char* __restrict__ block_done, int dim,
+                        float cell) {
     __shared__ SectorTable table;
     fill_sector_table(L, &table, threadIdx.x, blockDim.x);
     __syncthreads();
@@ -61,8 +94,10 @@ __global__ void __launch_bounds__(128)
     const size_t rounds = (total + stride - 1) / stride;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t r = 0; r < rounds; r++, i += stride) {
-        const bool live = i < total;
         const int ix = (int)(i % dim), iy = (int)((i / dim) % dim), iz = (int)(i / ((size_t)dim * dim));
+        // cubes of a block the coarse pass has settled are already written
+        const bool live = i < total && !(block_done != nullptr &&
+                                         block_done[((size_t)(iz >> 2) * (dim >> 2) + (iy >> 2)) * (dim >> 2) + (ix >> 2)]);
         const float x0 = ((float)ix - half) * cell, y0 = ((float)iy - half - kVolShiftY) * cell, z0 = ((float)iz - half) * cell;
         CellFirst f;
         f.byte = 0u, f.refine = false, f.direct = true, f.reach = 0u, f.reach_refine = false, f.reach_flip = false;
@@ -303,13 +338,21 @@ cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeVi
             if (e != cudaSuccess) return e;
         }
         const size_t bytes = (size_t)dim * dim * dim;
-        e = cudaMalloc((void**)&hit->vol_linear, bytes);
+        e = cudaMalloc((void**)&hit->vol_linear, bytes + bytes / 64 + 64);
         if (e != cudaSuccess) return e;
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         // the atlas build (caller's stream) has been synchronised by get_plane_atlas; the volume
         // build only needs the plan and the host-built yaw tables
-        volume_build_kernel<<<sms * 16, 128, 0, hit->vol_stream>>>(plan, hit->tables, hit->vol_linear, dim, cell);
+        unsigned char* block_done = nullptr;
+        if (dim % 4 == 0) {
+            // the block map lives behind the cube bytes in the same staging allocation
+            block_done = hit->vol_linear + bytes;
+            volume_coarse_kernel<<<sms * 8, 128, 0, hit->vol_stream>>>(plan, hit->tables, hit->vol_linear, block_done,
+                                                                      dim, cell);
+        }
+        volume_build_kernel<<<sms * 16, 128, 0, hit->vol_stream>>>(plan, hit->tables, hit->vol_linear, block_done, dim,
+                                                                   cell);
         e = cudaGetLastError();
         if (e == cudaSuccess) {
             cudaMemcpy3DParms cp;

@@ -168,7 +168,8 @@ def test_choice_volume_never_changes_a_result(emu, port):
     a pure accelerator and, since every tier applies the same operations to the winning candidate,
     returns the full evaluation's result BIT FOR BIT whichever tier decides a point — so a ring
     overflow (which moves a point to a slower tier) cannot change an output either.  Cube bytes come
-    from the function the device build kernel runs (choice_cell_byte)."""
+    from the per-cube function of the device build (choice_cell_byte; the device additionally lets a
+    block of 4^3 cubes inherit a byte certified for the whole block by the same function)."""
     vp, sz = ctypes.c_void_p, ctypes.c_size_t
     emu.emu_dist_choice.argtypes = [vp, sz, vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float,
                                     ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
