@@ -293,6 +293,15 @@ void emu_reach_offset(const float* offsets, size_t n, const lrm_leg_t* leg, cons
     }
 }
 
+// leg_ball_possible (the octree's per-leg pruning test) for world points (full plan with `quat`)
+void emu_leg_ball(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, float rc, uint8_t* out) {
+    lrm::LegPlan L;
+    lrm::build_leg_plan(*leg, quat, &L);
+    const bool wedge = leg->max_angle_coxa >= leg->min_angle_coxa && leg->max_angle_coxa - leg->min_angle_coxa < 3.0f;
+    for (size_t i = 0; i < n; i++)
+        out[i] = lrm::leg_ball_possible(L, lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]), rc, wedge) ? 1 : 0;
+}
+
 int emu_plan_is_generic(const lrm_leg_t* leg, const float* quat) {
     lrm::LegPlan L;
     lrm::build_leg_plan(*leg, quat, &L);

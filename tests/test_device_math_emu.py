@@ -243,3 +243,35 @@ def test_reach_plan_predicates(emu, port):
             assert not (any_reach & ~ball.astype(bool)).any(), (robot, az, o, rc)
             # ... and it does prune: most far-away balls are rejected
             assert ball.mean() < 0.9
+
+
+def test_octree_leg_pruning_is_conservative(emu, port):
+    """octree.cu skips a leg's distance evaluation for a foothold when leg_ball_possible(v, rc) is
+    false, rc = the child's half diagonal: that is exact iff no point within rc of v is reachable
+    by that leg (flag of distance_global) — then the leg cannot reach v, and its distance vector,
+    which ends on the workspace boundary, is longer than rc, so it cannot land inside the child."""
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    emu.emu_leg_ball.argtypes = [vp, sz, vp, vp, ctypes.c_float, vp]
+    rng = np.random.default_rng(90)
+    centres = rng.uniform(-700, 700, (20000, 3)).astype(np.float32)
+    wide = port.get_leg(1, 0.0).copy()
+    wide[11], wide[12] = 3.0, -3.0          # max / min coxa angle: the wide-coxa leg of the octree tests
+    for leg, q in ((port.get_leg(1, 0.7853982), port.quaternion_from_angle_index(0)),
+                   (port.get_leg(0, 2.3561945), port.quaternion_from_angle_index(13)), (wide, [1, 0, 0, 0])):
+        q = np.ascontiguousarray(q, np.float32)
+        leg = np.ascontiguousarray(leg, np.float32)
+        for rc in (60.0, 140.0, 300.0):
+            ball = np.zeros(len(centres), np.uint8)
+            emu.emu_leg_ball(centres.ctypes.data, len(centres), leg.ctypes.data, q.ctypes.data, rc, ball.ctypes.data)
+            pruned = ball == 0
+            assert 0.2 < pruned.mean() < 0.99, (rc, float(pruned.mean()))   # it prunes, and not everything
+            # the centre itself: unreachable, and its distance vector is longer than rc
+            _, d, f, _ = run_emu(emu, centres[pruned], leg, q)
+            assert not f.any()
+            assert (np.linalg.norm(d, axis=1) > rc).all(), float(np.linalg.norm(d, axis=1).min())
+            # no reachable point anywhere in a pruned ball
+            for _ in range(8):
+                step = rng.normal(size=(int(pruned.sum()), 3))
+                step *= (rng.uniform(0, 1, (len(step), 1)) ** (1 / 3)) * rc / np.linalg.norm(step, axis=1, keepdims=True)
+                _, _, f2, _ = run_emu(emu, (centres[pruned] + step).astype(np.float32), leg, q)
+                assert not f2.any(), (rc, int(f2.sum()))
