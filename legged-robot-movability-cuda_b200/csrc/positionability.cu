@@ -222,73 +222,83 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
                     return __any_sync(0xffffffffu, ok && t.w != 0.f && d < P.r_near_any) != 0;
                 });
             const int nq = (collide_all || !near_any) ? 0 : P.nq;
+            // An orientation passes when no map point is inside the body cylinder, one is inside the
+            // reach cylinder, and every leg reaches one: an AND, so the order of the tests is free.
+            // A pose that cannot stand usually fails the same test under the next orientation:
+            // the legs are tried starting with the one that failed last (a failing walk has no
+            // early exit), and when a leg failed last that leg goes before the two cylinder walks.
             int first_leg = 0;
+            bool leg_failed_last = false;
             for (int o = 0; o < nq && result == 0; o++) {
                 const OrientConsts& O = P.orient[o];
                 const float3 B = rotate(O.R, bx, by, bz);
-                // eliminateFarAndColliding (several_leg.cu:504-559): no map point inside the body
-                // cylinder (r = dim.body, z in (-110, 250)) ...
-                const bool hit = walk_filtered(
-                    P.map, bx, by, O.r_hit, lane,
-                    [&](float x, float y, float z, float rc) {
-                        const float3 T = rotate(O.R, x, y, z);
-                        const float dz = T.z - B.z;
-                        const float dx = T.x - B.x, dy = T.y - B.y, rr = O.radius_out + rc;
-                        return fmaf(dx, dx, dy * dy) < rr * rr && dz < 250.f + rc && dz > -110.f - rc;
-                    },
-                    [&](float4 t, bool ok) {
-                        const float3 T = rotate(O.R, t.x, t.y, t.z);
-                        const float dz = T.z - B.z;
-                        const float dx = T.x - B.x, dy = T.y - B.y;
-                        const bool in_body = fmaf(dx, dx, dy * dy) < O.radius_out * O.radius_out &&
-                                             dz < 250.f && dz > -110.f;
-                        return __any_sync(0xffffffffu, ok && t.w != 0.f && in_body) != 0;
-                    });
-                if (hit) continue;
-                // ... and at least one inside the reach cylinder
-                const bool near = walk_filtered(
-                    P.map, bx, by, O.r_near, lane,
-                    [&](float x, float y, float z, float rc) {
-                        const float3 T = rotate(O.R, x, y, z);
-                        const float dz = T.z - B.z;
-                        const float dx = T.x - B.x, dy = T.y - B.y, rr = O.radius_in + rc;
-                        return fmaf(dx, dx, dy * dy) < rr * rr && dz < O.plus_in + rc && dz > O.minus_in - rc;
-                    },
-                    [&](float4 t, bool ok) {
-                        const float3 T = rotate(O.R, t.x, t.y, t.z);
-                        const float dz = T.z - B.z;
-                        const float dx = T.x - B.x, dy = T.y - B.y;
-                        const bool in_reach = fmaf(dx, dx, dy * dy) < O.radius_in * O.radius_in &&
-                                              dz < O.plus_in && dz > O.minus_in;
-                        return __any_sync(0xffffffffu, ok && t.w != 0.f && in_reach) != 0;
-                    });
-                if (!near) continue;
-                // eliminateUnreachable (:633-706): every leg needs one reachable map point
-                // The legs are tried starting with the one that failed last (move-to-front): a pose
-                // that cannot stand usually fails on the same leg under the next orientation too,
-                // and a failing walk is the expensive one (no early exit).  The outcome is an AND
-                // over the legs, so the order does not matter.
-                bool all = true;
-                for (int ll = 0; ll < P.nlegs && all; ll++) {
-                    const int l = first_leg + ll < P.nlegs ? first_leg + ll : first_leg + ll - P.nlegs;
-                    const ReachPlan& L = plans[o * P.nlegs + l];
-                    all = walk_filtered(
-                        P.map, bx, by, P.r_leg, lane,
-                        [&](float x, float y, float z, float rc) {
-                            const float3 T = rotate(O.R, x, y, z);
-                            return reach_ball_possible(L, T.x - B.x, T.y - B.y, T.z - B.z, rc);
-                        },
-                        [&](float4 t, bool ok) {
-                            // reachable_rotate_leg (several_leg.cu:48-67): offset in the
-                            // orientation frame, gravity-side test, leg frame, reachability_circles
-                            const float3 T = rotate(O.R, t.x, t.y, t.z);
-                            const GravCtx gc{&O.grav, bx, by, bz, t.x, t.y, t.z};
-                            const bool r = ok && t.w != 0.f && reach_offset(L, T.x - B.x, T.y - B.y, T.z - B.z, &gc);
-                            return __any_sync(0xffffffffu, r) != 0;
-                        });
-                    if (!all) first_leg = l;
+                bool pass = true;
+                for (int step = 0; step < 2 + P.nlegs && pass; step++) {
+                    // leg first: [failed leg, body cylinder, reach cylinder, other legs]; else
+                    // [body cylinder, reach cylinder, legs from the one that failed last]
+                    const int what = leg_failed_last ? (step == 0 ? 2 : (step <= 2 ? step - 1 : step)) : step;
+                    if (what == 0) {
+                        // eliminateFarAndColliding (several_leg.cu:504-559): no map point inside the
+                        // body cylinder (r = dim.body, z in (-110, 250)) ...
+                        pass = !walk_filtered(
+                            P.map, bx, by, O.r_hit, lane,
+                            [&](float x, float y, float z, float rc) {
+                                const float3 T = rotate(O.R, x, y, z);
+                                const float dz = T.z - B.z;
+                                const float dx = T.x - B.x, dy = T.y - B.y, rr = O.radius_out + rc;
+                                return fmaf(dx, dx, dy * dy) < rr * rr && dz < 250.f + rc && dz > -110.f - rc;
+                            },
+                            [&](float4 t, bool ok) {
+                                const float3 T = rotate(O.R, t.x, t.y, t.z);
+                                const float dz = T.z - B.z;
+                                const float dx = T.x - B.x, dy = T.y - B.y;
+                                const bool in_body = fmaf(dx, dx, dy * dy) < O.radius_out * O.radius_out &&
+                                                     dz < 250.f && dz > -110.f;
+                                return __any_sync(0xffffffffu, ok && t.w != 0.f && in_body) != 0;
+                            });
+                        if (!pass) leg_failed_last = false;
+                    } else if (what == 1) {
+                        // ... and at least one inside the reach cylinder
+                        pass = walk_filtered(
+                            P.map, bx, by, O.r_near, lane,
+                            [&](float x, float y, float z, float rc) {
+                                const float3 T = rotate(O.R, x, y, z);
+                                const float dz = T.z - B.z;
+                                const float dx = T.x - B.x, dy = T.y - B.y, rr = O.radius_in + rc;
+                                return fmaf(dx, dx, dy * dy) < rr * rr && dz < O.plus_in + rc && dz > O.minus_in - rc;
+                            },
+                            [&](float4 t, bool ok) {
+                                const float3 T = rotate(O.R, t.x, t.y, t.z);
+                                const float dz = T.z - B.z;
+                                const float dx = T.x - B.x, dy = T.y - B.y;
+                                const bool in_reach = fmaf(dx, dx, dy * dy) < O.radius_in * O.radius_in &&
+                                                      dz < O.plus_in && dz > O.minus_in;
+                                return __any_sync(0xffffffffu, ok && t.w != 0.f && in_reach) != 0;
+                            });
+                        if (!pass) leg_failed_last = false;
+                    } else {
+                        // eliminateUnreachable (:633-706): every leg needs one reachable map point
+                        const int ll = what - 2;  // 0: the leg that failed last
+                        const int l = first_leg + ll < P.nlegs ? first_leg + ll : first_leg + ll - P.nlegs;
+                        const ReachPlan& L = plans[o * P.nlegs + l];
+                        pass = walk_filtered(
+                            P.map, bx, by, P.r_leg, lane,
+                            [&](float x, float y, float z, float rc) {
+                                const float3 T = rotate(O.R, x, y, z);
+                                return reach_ball_possible(L, T.x - B.x, T.y - B.y, T.z - B.z, rc);
+                            },
+                            [&](float4 t, bool ok) {
+                                // reachable_rotate_leg (several_leg.cu:48-67): offset in the
+                                // orientation frame, gravity-side test, leg frame, reachability_circles
+                                const float3 T = rotate(O.R, t.x, t.y, t.z);
+                                const GravCtx gc{&O.grav, bx, by, bz, t.x, t.y, t.z};
+                                const bool r = ok && t.w != 0.f && reach_offset(L, T.x - B.x, T.y - B.y, T.z - B.z, &gc);
+                                return __any_sync(0xffffffffu, r) != 0;
+                            });
+                        if (!pass) first_leg = l, leg_failed_last = true;
+                    }
                 }
-                if (all) result = (uint8_t)(o + 1);
+                if (pass) result = (uint8_t)(o + 1);
             }
         }
         if (lane == 0) P.standable[b] = result;
