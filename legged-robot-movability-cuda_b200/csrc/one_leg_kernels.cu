@@ -966,8 +966,10 @@ cudaError_t launch_tier_impl(const LegPlan& plan, const FastTables& ft, const At
     // chunks of up to 8 consecutive tiles per CTA, fewer on small sweeps (keep >= 16 chunks per CTA)
     int kshift = 0;
     while (kshift < tier_chunk_shift_max() && (tiles >> (kshift + 1)) >= grid * 16) kshift++;
+#ifdef LRM_ENABLE_SKELETON  // measurement builds only (LRM_NVCC_EXTRA=-DLRM_ENABLE_SKELETON): results are garbage
     if (const char* sk = getenv("LRM_TIER_SKELETON"))
         if (sk[0] == '1') kshift |= 0x100;
+#endif
     const RedoIo io{ix, iy, iz, ox, oy, oz, flag};
     kernel<<<(unsigned)grid, kTT, smem, stream>>>(plan, ft, atlas, vol, io, n, kshift, gate, gate_want);
     return cudaGetLastError();
