@@ -168,6 +168,25 @@ LRM_API int lrm_recurs(const float* xyz, size_t n, const lrm_leg_t* leg, const f
 LRM_API int lrm_oct(const float* footholds, size_t nt, const lrm_leg_t* leg, int max_depth, float* out_xyz,
             size_t cap, size_t* count, int on_device, void* stream, float* kernel_ms);
 
+/* lrm_oct for ONE shard of the tree: the subtrees under the root's eight children never interact
+ * (branchKernel descends child by child, several_leg_octree.cu:296-313), so shard `shard` of
+ * `nshards` refines only the top-level children c with c % nshards == shard — one process per GPU,
+ * footholds replicated, no collective.  child_counts[c] (8 entries, may be NULL) receives the number
+ * of centres written for top-level child c; out_xyz holds them grouped by ascending c, so the
+ * full result in the reference's traversal order is, for c = 0..7, shard (c % nshards)'s group c. */
+LRM_API int lrm_oct_sharded(const float* footholds, size_t nt, const lrm_leg_t* leg, int max_depth, int shard,
+                    int nshards, float* out_xyz, size_t cap, size_t* count, size_t child_counts[8],
+                    int on_device, void* stream, float* kernel_ms);
+
+/* Replaces ONE launch of validity_child (several_leg_octree.cu:19-151) together with the child
+ * initialisation branchKernel does before it (:315-352): the eight children of the body box
+ * parent_box6 = {centre xyz, half extents xyz} (parent_validity = the parent's validity flag, which
+ * the predicate inherits, :71) are created with CreateChildBox's rules and evaluated against all
+ * footholds.  out_flags: 8 x {validity, leaf, raw, onEdge} bytes; out_boxes: 8 x 6 floats (both
+ * host).  Sequential semantics, like lrm_oct. */
+LRM_API int lrm_oct_children(const float* footholds, size_t nt, const lrm_leg_t* leg, const float parent_box6[6],
+                     int parent_validity, uint8_t* out_flags, float* out_boxes, int on_device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

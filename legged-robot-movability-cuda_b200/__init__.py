@@ -83,6 +83,9 @@ def lib():
                                           ctypes.POINTER(PositOpts), vp, ci, vp, fp]
         L.lrm_recurs.argtypes = [vp, sz, legp, vp, ci, vp, ci, vp, fp]
         L.lrm_oct.argtypes = [vp, sz, legp, ci, vp, sz, ctypes.POINTER(ctypes.c_size_t), ci, vp, fp]
+        L.lrm_oct_sharded.argtypes = [vp, sz, legp, ci, ci, ci, vp, sz, ctypes.POINTER(ctypes.c_size_t), vp,
+                                      ci, vp, fp]
+        L.lrm_oct_children.argtypes = [vp, sz, legp, vp, ci, vp, vp, ci, vp]
         _lib = L
     return _lib
 
@@ -131,9 +134,32 @@ def _stream_ptr(stream):
     return ctypes.c_void_p(int(stream))
 
 
-def _torch_stream():
+def _stream_for(stream, tensor):
+    """An explicitly passed stream is used as given (the default stream, 0, included); otherwise the
+    current torch stream of the TENSOR's device."""
+    if stream is not None:
+        return _stream_ptr(stream)
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(tensor.device).cuda_stream)
+
+
+class _device_of:
+    """Make the device of `tensor` current for the duration of a device-pointer call (scratch
+    buffers, cached tables and the launch itself belong to the current device) and check that every
+    other tensor argument lives there too."""
+
+    def __init__(self, tensor, *others):
+        import torch
+        for t in others:
+            if t is not None and _is_torch(t):
+                assert t.device == tensor.device, f"tensors on different devices: {t.device} vs {tensor.device}"
+        self.guard = torch.cuda.device(tensor.device)
+
+    def __enter__(self):
+        return self.guard.__enter__()
+
+    def __exit__(self, *a):
+        return self.guard.__exit__(*a)
 
 
 def _prep_points(points):
@@ -163,8 +189,9 @@ def reachability(points, leg, quat=None, out=None, stream=None, timing=False):
     if dev:
         import torch
         out = torch.empty(n, dtype=torch.uint8, device=points.device) if out is None else out
-        st = _stream_ptr(stream) or _torch_stream()
-        _check(lib().lrm_reach(ptr, n, ctypes.byref(leg), qp, out.data_ptr(), 1, st, msp))
+        st = _stream_for(stream, points)
+        with _device_of(points, out):
+            _check(lib().lrm_reach(ptr, n, ctypes.byref(leg), qp, out.data_ptr(), 1, st, msp))
     else:
         out = np.empty(n, dtype=np.uint8) if out is None else out
         _check(lib().lrm_reach(ptr, n, ctypes.byref(leg), qp, out.ctypes.data, 0, None, msp))
@@ -180,9 +207,10 @@ def distance(points, leg, quat=None, out=None, flags=True, stream=None, timing=F
         import torch
         out = torch.empty((n, 3), dtype=torch.float32, device=points.device) if out is None else out
         fl = torch.empty(n, dtype=torch.uint8, device=points.device) if flags else None
-        st = _stream_ptr(stream) or _torch_stream()
-        _check(lib().lrm_dist(ptr, n, ctypes.byref(leg), qp, out.data_ptr(),
-                              fl.data_ptr() if flags else None, 1, st, msp))
+        st = _stream_for(stream, points)
+        with _device_of(points, out, fl):
+            _check(lib().lrm_dist(ptr, n, ctypes.byref(leg), qp, out.data_ptr(),
+                                  fl.data_ptr() if flags else None, 1, st, msp))
     else:
         out = np.empty((n, 3), dtype=np.float32) if out is None else out
         fl = np.empty(n, dtype=np.uint8) if flags else None
@@ -201,9 +229,10 @@ def reach_dist(points, leg, quat=None, out_flags=None, out_vec=None, stream=None
         import torch
         fl = torch.empty(n, dtype=torch.uint8, device=points.device) if out_flags is None else out_flags
         vec = torch.empty((n, 3), dtype=torch.float32, device=points.device) if out_vec is None else out_vec
-        st = _stream_ptr(stream) or _torch_stream()
-        _check(lib().lrm_reach_dist(ptr, n, ctypes.byref(leg), qp, fl.data_ptr(), vec.data_ptr(), 1,
-                                    st, msp))
+        st = _stream_for(stream, points)
+        with _device_of(points, fl, vec):
+            _check(lib().lrm_reach_dist(ptr, n, ctypes.byref(leg), qp, fl.data_ptr(), vec.data_ptr(), 1,
+                                        st, msp))
     else:
         fl = np.empty(n, dtype=np.uint8) if out_flags is None else out_flags
         vec = np.empty((n, 3), dtype=np.float32) if out_vec is None else out_vec
@@ -220,10 +249,11 @@ def reach_dist_soa(x, y, z, leg, quat=None, want_vec=True, stream=None, timing=F
     ms, msp = _timing(timing)
     fl = torch.empty(n, dtype=torch.uint8, device=x.device)
     d = [torch.empty(n, dtype=torch.float32, device=x.device) for _ in range(3)] if want_vec else [None] * 3
-    st = _stream_ptr(stream) or _torch_stream()
-    _check(lib().lrm_reach_dist_soa(x.data_ptr(), y.data_ptr(), z.data_ptr(), n, ctypes.byref(leg), qp,
-                                    fl.data_ptr(), *[t.data_ptr() if t is not None else None for t in d],
-                                    st, msp))
+    st = _stream_for(stream, x)
+    with _device_of(x, y, z):
+        _check(lib().lrm_reach_dist_soa(x.data_ptr(), y.data_ptr(), z.data_ptr(), n, ctypes.byref(leg), qp,
+                                        fl.data_ptr(), *[t.data_ptr() if t is not None else None for t in d],
+                                        st, msp))
     res = (fl, d[0], d[1], d[2])
     return res + (ms.value,) if timing else res
 
@@ -234,8 +264,9 @@ def forward_kinematics(angles, leg, stream=None):
     if dev:
         import torch
         out = torch.empty((n, 3), dtype=torch.float32, device=angles.device)
-        st = _stream_ptr(stream) or _torch_stream()
-        _check(lib().lrm_forward_kine(ptr, n, ctypes.byref(leg), out.data_ptr(), 1, st, None))
+        st = _stream_for(stream, angles)
+        with _device_of(angles):
+            _check(lib().lrm_forward_kine(ptr, n, ctypes.byref(leg), out.data_ptr(), 1, st, None))
     else:
         out = np.empty((n, 3), dtype=np.float32)
         _check(lib().lrm_forward_kine(ptr, n, ctypes.byref(leg), out.ctypes.data, 0, None, None))
@@ -258,9 +289,10 @@ def make_lattice(out, lo, step, dims, first=0, count=None, stream=None):
     step = np.ascontiguousarray(step, dtype=np.float32)
     dims = np.ascontiguousarray(dims, dtype=np.uint32)
     count = out.shape[0] if count is None else count
-    st = _stream_ptr(stream) or _torch_stream()
-    _check(lib().lrm_make_lattice(out.data_ptr(), lo.ctypes.data, step.ctypes.data, dims.ctypes.data,
-                                  int(first), int(count), st))
+    st = _stream_for(stream, out)
+    with _device_of(out):
+        _check(lib().lrm_make_lattice(out.data_ptr(), lo.ctypes.data, step.ctypes.data, dims.ctypes.data,
+                                      int(first), int(count), st))
     return out
 
 
@@ -318,9 +350,10 @@ def positionability(bodies, map_points, legs, quats=None, pre_cull=False, stream
     if devb:
         import torch
         out = torch.empty(nb, dtype=torch.uint8, device=bodies.device)
-        st = _stream_ptr(stream) or _torch_stream()
-        _check(lib().lrm_positionability(pb, nb, pm, nt, leg_arr, len(legs), quats.ctypes.data,
-                                         quats.shape[0], ctypes.byref(opts), out.data_ptr(), 1, st, msp))
+        st = _stream_for(stream, bodies)
+        with _device_of(bodies, map_points):
+            _check(lib().lrm_positionability(pb, nb, pm, nt, leg_arr, len(legs), quats.ctypes.data,
+                                             quats.shape[0], ctypes.byref(opts), out.data_ptr(), 1, st, msp))
     else:
         out = np.empty(nb, dtype=np.uint8)
         _check(lib().lrm_positionability(pb, nb, pm, nt, leg_arr, len(legs), quats.ctypes.data,
@@ -337,8 +370,9 @@ def apply_recurs(points, leg, max_depth=1, quat=None, fill=-1.0, stream=None):
         import torch
         out = torch.zeros((n, 3), dtype=torch.float32, device=points.device)
         out[:, 0] = fill
-        st = _stream_ptr(stream) or _torch_stream()
-        _check(lib().lrm_recurs(ptr, n, ctypes.byref(leg), qp, int(max_depth), out.data_ptr(), 1, st, None))
+        st = _stream_for(stream, points)
+        with _device_of(points):
+            _check(lib().lrm_recurs(ptr, n, ctypes.byref(leg), qp, int(max_depth), out.data_ptr(), 1, st, None))
     else:
         out = np.zeros((n, 3), dtype=np.float32)
         out[:, 0] = fill
@@ -346,21 +380,64 @@ def apply_recurs(points, leg, max_depth=1, quat=None, fill=-1.0, stream=None):
     return out
 
 
-def apply_oct(footholds, leg, max_depth=1, cap=1 << 16, stream=None, timing=False):
+class _maybe_device:
+    def __init__(self, dev, tensor):
+        self.ctx = _device_of(tensor) if dev else None
+
+    def __enter__(self):
+        return self.ctx.__enter__() if self.ctx else None
+
+    def __exit__(self, *a):
+        return self.ctx.__exit__(*a) if self.ctx else False
+
+
+def apply_oct(footholds, leg, max_depth=1, cap=1 << 16, stream=None, timing=False, shard=0, nshards=1,
+              child_counts=False):
     """Body-space octree positionability (apply_oct, several_leg_octree.cu:391-488): centres of the
-    valid leaf / raw nodes after `max_depth` refinement passes, (n, 3) float32 numpy array."""
+    valid leaf / raw nodes after `max_depth` refinement passes, (n, 3) float32 numpy array.
+    shard / nshards: refine only the root's children c with c % nshards == shard (lrm_oct_sharded);
+    child_counts=True also returns the number of centres under each of the 8 top-level children."""
     dev, ptr, nt, keep = _prep_points(footholds)
     ms, msp = _timing(timing)
+    counts = (ctypes.c_size_t * 8)()
     while True:
         out = np.empty((cap, 3), dtype=np.float32)
         count = ctypes.c_size_t(0)
-        st = (_stream_ptr(stream) or _torch_stream()) if dev else None
-        _check(lib().lrm_oct(ptr, nt, ctypes.byref(leg), int(max_depth), out.ctypes.data, cap,
-                             ctypes.byref(count), dev, st, msp))
+        st = _stream_for(stream, footholds) if dev else None
+        with _maybe_device(dev, footholds):
+            _check(lib().lrm_oct_sharded(ptr, nt, ctypes.byref(leg), int(max_depth), int(shard), int(nshards),
+                                         out.ctypes.data, cap, ctypes.byref(count), counts, dev, st, msp))
         if count.value <= cap:
-            res = out[:count.value].copy()
-            return (res, ms.value) if timing else res
+            res = (out[:count.value].copy(),)
+            if child_counts:
+                res += (np.array(list(counts), dtype=np.int64),)
+            if timing:
+                res += (ms.value,)
+            return res if len(res) > 1 else res[0]
         cap = count.value
+
+
+def merge_oct_shards(parts):
+    """parts[r] = (centres, child_counts) of shard r of len(parts): the full list in the reference's
+    traversal order (top-level child c comes from shard c % nshards)."""
+    n = len(parts)
+    offs = [np.concatenate([[0], np.cumsum(c)]) for _, c in parts]
+    out = [parts[c % n][0][offs[c % n][c]:offs[c % n][c + 1]] for c in range(8)]
+    return np.concatenate(out) if out else np.zeros((0, 3), np.float32)
+
+
+def oct_children(footholds, leg, parent_box6, parent_validity=False, stream=None):
+    """One launch of validity_child (several_leg_octree.cu:19-151) on the 8 children of a body box:
+    (flags 8 x [validity, leaf, raw, onEdge] uint8, boxes 8 x 6 float32)."""
+    dev, ptr, nt, keep = _prep_points(footholds)
+    box = np.ascontiguousarray(parent_box6, dtype=np.float32).reshape(6)
+    flags = np.zeros((8, 4), np.uint8)
+    boxes = np.zeros((8, 6), np.float32)
+    st = _stream_for(stream, footholds) if dev else None
+    with _maybe_device(dev, footholds):
+        _check(lib().lrm_oct_children(ptr, nt, ctypes.byref(leg), box.ctypes.data, int(bool(parent_validity)),
+                                      flags.ctypes.data, boxes.ctypes.data, dev, st))
+    return flags, boxes
 
 
 def robot_full_struct(body_map, target_map, legs):

@@ -65,7 +65,14 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
 
 // Body-space octree (octree.cu).  d_footholds: device, nt x 3.  centres: xyz triples of the valid
 // leaf / raw nodes in the reference's traversal order.
+// shard / nshards: only the root's children c with c % nshards == shard are refined (the subtrees
+// are independent); child_counts (8, may be nullptr): centres found under each top-level child.
 cudaError_t run_octree(const float* d_footholds, size_t nt, const lrm_leg_t& leg, int max_depth,
-                       std::vector<float>* centres, cudaStream_t stream, float* kernel_ms);
+                       std::vector<float>* centres, cudaStream_t stream, float* kernel_ms, int shard = 0,
+                       int nshards = 1, size_t* child_counts = nullptr);
+// One pass of validity_child over the 8 children of one parent box: flags32 = 8 x {validity, leaf,
+// raw, onEdge}, boxes48 = 8 x {centre, half extents} (host).
+cudaError_t run_octree_children(const float* d_footholds, size_t nt, const lrm_leg_t& leg, const float* parent_box6,
+                                int parent_validity, uint8_t* flags32, float* boxes48, cudaStream_t stream);
 
 }  // namespace lrm

@@ -494,12 +494,14 @@ int lrm_positionability(const float* bodies, size_t nb, const float* map, size_t
     return LRM_OK;
 }
 
-int lrm_oct(const float* footholds, size_t nt, const lrm_leg_t* leg, int max_depth, float* out_xyz,
-            size_t cap, size_t* count, int on_device, void* stream_v, float* kernel_ms) {
+int lrm_oct_sharded(const float* footholds, size_t nt, const lrm_leg_t* leg, int max_depth, int shard, int nshards,
+                    float* out_xyz, size_t cap, size_t* count, size_t child_counts[8], int on_device,
+                    void* stream_v, float* kernel_ms) {
     if (!leg || !count) return fail(LRM_ERR_INVALID, "leg / count is NULL");
     if (nt && !footholds) return fail(LRM_ERR_INVALID, "footholds is NULL");
     if (cap && !out_xyz) return fail(LRM_ERR_INVALID, "out_xyz is NULL");
     if (max_depth < 0 || max_depth > 16) return fail(LRM_ERR_INVALID, "max_depth must be 0..16");
+    if (nshards < 1 || shard < 0 || shard >= nshards) return fail(LRM_ERR_INVALID, "shard must be in [0, nshards)");
     *count = 0;
     if (kernel_ms) *kernel_ms = 0.f;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -517,10 +519,40 @@ int lrm_oct(const float* footholds, size_t nt, const lrm_leg_t* leg, int max_dep
         d_foot = tmp;
     }
     std::vector<float> centres;
-    LRM_CUDA(lrm::run_octree(d_foot, nt, *leg, max_depth, &centres, stream, kernel_ms), "octree");
+    LRM_CUDA(lrm::run_octree(d_foot, nt, *leg, max_depth, &centres, stream, kernel_ms, shard, nshards, child_counts),
+             "octree");
     *count = centres.size() / 3;
     const size_t n = *count < cap ? *count : cap;
     if (n) std::memcpy(out_xyz, centres.data(), n * 12);
+    return LRM_OK;
+}
+
+int lrm_oct(const float* footholds, size_t nt, const lrm_leg_t* leg, int max_depth, float* out_xyz,
+            size_t cap, size_t* count, int on_device, void* stream_v, float* kernel_ms) {
+    return lrm_oct_sharded(footholds, nt, leg, max_depth, 0, 1, out_xyz, cap, count, nullptr, on_device, stream_v,
+                           kernel_ms);
+}
+
+int lrm_oct_children(const float* footholds, size_t nt, const lrm_leg_t* leg, const float parent_box6[6],
+                     int parent_validity, uint8_t* out_flags, float* out_boxes, int on_device, void* stream_v) {
+    if (!leg || !parent_box6 || !out_flags || !out_boxes) return fail(LRM_ERR_INVALID, "NULL argument");
+    if (nt && !footholds) return fail(LRM_ERR_INVALID, "footholds is NULL");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return cuda_fail(ce != cudaSuccess ? ce : cudaErrorNoDevice,
+                         "no CUDA device (this library has no CPU path)");
+    DeviceScratch scratch;
+    const float* d_foot = footholds;
+    if (!on_device) {
+        float* tmp = nullptr;
+        LRM_CUDA(scratch.alloc((void**)&tmp, nt * 12), "cudaMalloc footholds");
+        LRM_CUDA(cudaMemcpyAsync(tmp, footholds, nt * 12, cudaMemcpyHostToDevice, stream), "H2D footholds");
+        d_foot = tmp;
+    }
+    LRM_CUDA(lrm::run_octree_children(d_foot, nt, *leg, parent_box6, parent_validity, out_flags, out_boxes, stream),
+             "octree children");
     return LRM_OK;
 }
 

@@ -178,26 +178,11 @@ __global__ void __launch_bounds__(256) oct_validity_kernel(const ChildTask* __re
     if (lane == 0 && mine) atomicOr(&flags[blockIdx.y], mine);
 }
 
-#define OCT_CHECK(call)                    \
-    do {                                   \
-        cudaError_t e_ = (call);           \
-        if (e_ != cudaSuccess) return e_;  \
-    } while (0)
-
-}  // namespace
-
-cudaError_t run_octree(const float* d_footholds, size_t nt, const lrm_leg_t& leg, int max_depth,
-                       std::vector<float>* centres, cudaStream_t stream, float* kernel_ms) {
-    centres->clear();
-    if (kernel_ms) *kernel_ms = 0.f;
-    if (nt > 0x7fffffffull) return cudaErrorInvalidValue;
-    DevBuf mem;
-    CellGrid grid;
-    OCT_CHECK(build_grid(mem, d_footholds, nt, nullptr, 0.f, stream, &grid));
-
-    // plans for the 27 orientation samples x 4 leg mounts (octree_util.cu.h:184-198, settings.h:41)
+// plans for the 27 orientation samples x 4 leg mounts (octree_util.cu.h:184-198, settings.h:41)
+void build_oct_plans(const lrm_leg_t& leg, std::vector<LegPlan>* out) {
     const float pi = 3.14159265358979323846264338327950288419716939937510582097f;
-    std::vector<LegPlan> plans((size_t)kSamples * kLegs);
+    std::vector<LegPlan>& plans = *out;
+    plans.assign((size_t)kSamples * kLegs, LegPlan{});
     for (int a = 0; a < kSamples; a++) {
         // QuaternionFromAngleIndex: (ind + ind/2) % 3 maps 2 -> 0, so only {min, mid} are sampled
         const float lim[6] = {-pi / 4, pi / 4, -pi / 8, pi / 8, -pi / 8, pi / 8};
@@ -223,11 +208,104 @@ cudaError_t run_octree(const float* d_footholds, size_t nt, const lrm_leg_t& leg
             build_leg_plan(l, qy, &plans[(size_t)a * kLegs + k]);
         }
     }
+}
+
+// The 8 children of `parent` as branchKernel initialises them (several_leg_octree.cu:315-352),
+// with the work descriptor validity_child needs for each.
+void init_children(const HostNode& parent, const lrm_leg_t& leg, HostNode* children, std::vector<ChildTask>* tasks) {
+    const float reach = leg.body + leg.coxa_length + leg.femur_length + leg.tibia_length;
+    const bool rot = parent.box.h[0] < kRotBelow;
+    for (unsigned i = 0; i < 8; i++) {
+        HostNode& ch = children[i];
+        Box nb;
+        const int missing = child_box(parent.box, i, &nb);
+        ChildTask t{};
+        if (missing == kDeadQuadrant) {  // :331-339
+            ch.leaf = true, ch.raw = false, ch.validity = true, ch.on_edge = true;
+            ch.box = Box{{0, 0, 0}, {0, 0, 0}};
+            t.skip = 1;
+        } else {
+            ch.on_edge = false, ch.validity = false, ch.box = nb;
+            ch.leaf = (3 - missing) <= 0;
+            ch.raw = !ch.leaf;
+        }
+        t.box = ch.box;
+        for (int q = 0; q < 3; q++) t.elong[q] = parent.box.h[q] + reach;
+        t.margin = rot ? 0.f : kRotBelow / 3;
+        t.n_samples = rot ? kSamples : 1;
+        t.parent_valid = parent.validity ? 1 : 0;
+        t.wedge = (leg.max_angle_coxa >= leg.min_angle_coxa && leg.max_angle_coxa - leg.min_angle_coxa < 3.0f) ? 1 : 0;
+        tasks->push_back(t);
+    }
+}
+
+// validity_child's write-back (:134-150) from the OR-ed flags of a pass
+void apply_flags(unsigned f, HostNode* ch) {
+    if (f & 2u) ch->validity = true;
+    if (f & 4u) ch->leaf = true;
+    if ((f & 1u) && !(f & 4u)) ch->on_edge = true;
+}
+
+// One kernel pass over `tasks`; flags come back on the host.
+cudaError_t evaluate_tasks(const std::vector<ChildTask>& tasks, const CellGrid& grid, const LegPlan* d_plans,
+                           cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1, std::vector<unsigned>* flags) {
+    ChildTask* d_tasks = nullptr;
+    unsigned* d_flags = nullptr;
+    flags->assign(tasks.size(), 0u);
+    cudaError_t status = cudaMalloc((void**)&d_tasks, tasks.size() * sizeof(ChildTask));
+    if (status != cudaSuccess) return status;
+    status = cudaMalloc((void**)&d_flags, tasks.size() * sizeof(unsigned));
+    if (status == cudaSuccess) {
+        cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(ChildTask), cudaMemcpyHostToDevice, stream);
+        cudaMemsetAsync(d_flags, 0, tasks.size() * sizeof(unsigned), stream);
+        // enough slices that a pass with few children (the first ones) still fills the GPU
+        int slices = (int)(148 * 4 / tasks.size()) + 1;
+        if (slices > 64) slices = 64;
+        if (ev0) cudaEventRecord(ev0, stream);
+        for (size_t off = 0; off < tasks.size(); off += 32768) {
+            const unsigned cnt = (unsigned)std::min<size_t>(32768, tasks.size() - off);
+            oct_validity_kernel<<<dim3((unsigned)slices, cnt), 256, 0, stream>>>(d_tasks + off, grid, d_plans,
+                                                                                d_flags + off, slices);
+        }
+        status = cudaGetLastError();
+        if (ev1) cudaEventRecord(ev1, stream);
+        if (status == cudaSuccess)
+            status = cudaMemcpyAsync(flags->data(), d_flags, flags->size() * sizeof(unsigned), cudaMemcpyDeviceToHost,
+                                     stream);
+        if (status == cudaSuccess) status = cudaStreamSynchronize(stream);
+    }
+    cudaFree(d_tasks);
+    cudaFree(d_flags);
+    return status;
+}
+
+#define OCT_CHECK(call)                    \
+    do {                                   \
+        cudaError_t e_ = (call);           \
+        if (e_ != cudaSuccess) return e_;  \
+    } while (0)
+
+}  // namespace
+
+cudaError_t run_octree(const float* d_footholds, size_t nt, const lrm_leg_t& leg, int max_depth,
+                       std::vector<float>* centres, cudaStream_t stream, float* kernel_ms, int shard, int nshards,
+                       size_t* child_counts) {
+    centres->clear();
+    if (child_counts)
+        for (int i = 0; i < 8; i++) child_counts[i] = 0;
+    if (nshards < 1 || shard < 0 || shard >= nshards) return cudaErrorInvalidValue;
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (nt > 0x7fffffffull) return cudaErrorInvalidValue;
+    DevBuf mem;
+    CellGrid grid;
+    OCT_CHECK(build_grid(mem, d_footholds, nt, nullptr, 0.f, stream, &grid));
+
+    std::vector<LegPlan> plans;
+    build_oct_plans(leg, &plans);
     LegPlan* d_plans;
     OCT_CHECK(mem.alloc(&d_plans, plans.size()));
     OCT_CHECK(cudaMemcpyAsync(d_plans, plans.data(), plans.size() * sizeof(LegPlan), cudaMemcpyHostToDevice, stream));
 
-    const float reach = leg.body + leg.coxa_length + leg.femur_length + leg.tibia_length;
     std::vector<HostNode> nodes(1);
     nodes[0].box = Box{{0.f, 0.f, 0.f}, {kRootHalf, kRootHalf, kRootHalf}};
     nodes[0].raw = true;
@@ -261,76 +339,32 @@ cudaError_t run_octree(const float* d_footholds, size_t nt, const lrm_leg_t& leg
         for (int n : expand) {
             const int first = (int)nodes.size();
             nodes.resize(nodes.size() + 8);
-            HostNode& parent = nodes[n];
-            parent.children = first;
-            const bool rot = parent.box.h[0] < kRotBelow;
-            for (unsigned i = 0; i < 8; i++) {
-                HostNode& ch = nodes[first + i];
-                Box nb;
-                const int missing = child_box(parent.box, i, &nb);
-                ChildTask t{};
-                if (missing == kDeadQuadrant) {  // :331-339
-                    ch.leaf = true, ch.raw = false, ch.validity = true, ch.on_edge = true;
-                    ch.box = Box{{0, 0, 0}, {0, 0, 0}};
-                    t.skip = 1;
-                } else {
-                    ch.on_edge = false, ch.validity = false, ch.box = nb;
-                    ch.leaf = (3 - missing) <= 0;
-                    ch.raw = !ch.leaf;
-                }
-                t.box = ch.box;
-                for (int q = 0; q < 3; q++) t.elong[q] = parent.box.h[q] + reach;
-                t.margin = rot ? 0.f : kRotBelow / 3;
-                t.n_samples = rot ? kSamples : 1;
-                t.parent_valid = parent.validity ? 1 : 0;
-                t.wedge = (leg.max_angle_coxa >= leg.min_angle_coxa && leg.max_angle_coxa - leg.min_angle_coxa < 3.0f) ? 1 : 0;
-                tasks.push_back(t);
-            }
-            parent.raw = false;
-        }
-        ChildTask* d_tasks = nullptr;
-        unsigned* d_flags = nullptr;
-        status = cudaMalloc((void**)&d_tasks, tasks.size() * sizeof(ChildTask));
-        if (status != cudaSuccess) break;
-        status = cudaMalloc((void**)&d_flags, tasks.size() * sizeof(unsigned));
-        if (status == cudaSuccess) {
-            cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(ChildTask), cudaMemcpyHostToDevice, stream);
-            cudaMemsetAsync(d_flags, 0, tasks.size() * sizeof(unsigned), stream);
-            // enough slices that a pass with few children (the first ones) still fills the GPU
-            int slices = (int)(148 * 4 / tasks.size()) + 1;
-            if (slices > 64) slices = 64;
-            if (ev0) cudaEventRecord(ev0, stream);
-            for (size_t off = 0; off < tasks.size(); off += 32768) {
-                const unsigned cnt = (unsigned)std::min<size_t>(32768, tasks.size() - off);
-                oct_validity_kernel<<<dim3((unsigned)slices, cnt), 256, 0, stream>>>(d_tasks + off, grid, d_plans,
-                                                                                    d_flags + off, slices);
-            }
-            status = cudaGetLastError();
-            if (ev1) cudaEventRecord(ev1, stream);
-            std::vector<unsigned> flags(tasks.size());
-            if (status == cudaSuccess)
-                status = cudaMemcpyAsync(flags.data(), d_flags, flags.size() * sizeof(unsigned), cudaMemcpyDeviceToHost,
-                                         stream);
-            if (status == cudaSuccess) status = cudaStreamSynchronize(stream);
-            if (status == cudaSuccess && kernel_ms) {
-                float ms = 0.f;
-                if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) *kernel_ms += ms;
-            }
-            if (status == cudaSuccess) {
-                size_t t = 0;
-                for (int n : expand)
-                    for (int i = 0; i < 8; i++, t++) {  // :134-150
-                        HostNode& ch = nodes[nodes[n].children + i];
-                        if (tasks[t].skip) continue;
-                        const unsigned f = flags[t];
-                        if (f & 2u) ch.validity = true;
-                        if (f & 4u) ch.leaf = true;
-                        if ((f & 1u) && !(f & 4u)) ch.on_edge = true;
+            nodes[n].children = first;
+            init_children(nodes[n], leg, &nodes[first], &tasks);
+            nodes[n].raw = false;
+            if (n == 0 && nshards > 1) {
+                // sharding by top-level children (dealt round-robin): the subtrees under the root's
+                // children never interact, so a shard simply never looks at the other shards' children
+                for (int i = 0; i < 8; i++)
+                    if (i % nshards != shard) {
+                        HostNode& ch = nodes[first + i];
+                        tasks[tasks.size() - 8 + i].skip = 1;
+                        ch.leaf = true, ch.raw = false, ch.validity = false, ch.on_edge = false;
                     }
             }
         }
-        cudaFree(d_tasks);
-        cudaFree(d_flags);
+        std::vector<unsigned> flags;
+        status = evaluate_tasks(tasks, grid, d_plans, stream, ev0, ev1, &flags);
+        if (status == cudaSuccess && kernel_ms) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) *kernel_ms += ms;
+        }
+        if (status == cudaSuccess) {
+            size_t t = 0;
+            for (int n : expand)
+                for (int i = 0; i < 8; i++, t++)
+                    if (!tasks[t].skip) apply_flags(flags[t], &nodes[nodes[n].children + i]);
+        }
     }
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -352,11 +386,42 @@ cudaError_t run_octree(const float* d_footholds, size_t nt, const lrm_leg_t& leg
             if (endpoint && ch.children >= 0) {
                 stack.push_back({(int)(&ch - nodes.data()), 0});
             } else if (valid) {
+                if (child_counts) child_counts[stack.size() == 1 ? top.second - 1 : stack[1].first - nodes[0].children]++;
                 centres->push_back(ch.box.c[0]);
                 centres->push_back(ch.box.c[1]);
                 centres->push_back(ch.box.c[2]);
             }
         }
+    }
+    return cudaSuccess;
+}
+
+// validity_child on the 8 children of one parent box (lrm_oct_children).
+cudaError_t run_octree_children(const float* d_footholds, size_t nt, const lrm_leg_t& leg, const float* parent_box6,
+                                int parent_validity, uint8_t* flags32, float* boxes48, cudaStream_t stream) {
+    if (nt > 0x7fffffffull) return cudaErrorInvalidValue;
+    DevBuf mem;
+    CellGrid grid;
+    OCT_CHECK(build_grid(mem, d_footholds, nt, nullptr, 0.f, stream, &grid));
+    std::vector<LegPlan> plans;
+    build_oct_plans(leg, &plans);
+    LegPlan* d_plans;
+    OCT_CHECK(mem.alloc(&d_plans, plans.size()));
+    OCT_CHECK(cudaMemcpyAsync(d_plans, plans.data(), plans.size() * sizeof(LegPlan), cudaMemcpyHostToDevice, stream));
+    HostNode parent;
+    std::memcpy(&parent.box, parent_box6, sizeof(Box));
+    parent.validity = parent_validity != 0;
+    parent.raw = true;
+    HostNode children[8];
+    std::vector<ChildTask> tasks;
+    init_children(parent, leg, children, &tasks);
+    std::vector<unsigned> flags;
+    OCT_CHECK(evaluate_tasks(tasks, grid, d_plans, stream, nullptr, nullptr, &flags));
+    for (int i = 0; i < 8; i++) {
+        if (!tasks[i].skip) apply_flags(flags[i], &children[i]);
+        flags32[4 * i + 0] = children[i].validity, flags32[4 * i + 1] = children[i].leaf;
+        flags32[4 * i + 2] = children[i].raw, flags32[4 * i + 3] = children[i].on_edge;
+        std::memcpy(boxes48 + 6 * i, &children[i].box, sizeof(Box));
     }
     return cudaSuccess;
 }

@@ -87,6 +87,7 @@ class PortOracle(_Oracle):
         L.op_apply_recurs.argtypes = [_vp, _sz, _vp, _vp, _ci, _vp]
         L.op_apply_oct.argtypes = [_vp, _sz, _vp, _ci, _vp, _sz]
         L.op_apply_oct.restype = _sz
+        L.op_validity_children.argtypes = [_vp, _ci, _vp, _sz, _vp, _vp, _vp]
         L.op_create_child_box.argtypes = [_vp, ctypes.c_uint, _vp, _vp, _vp]
         L.op_create_child_box.restype = ctypes.c_uint
 
@@ -168,6 +169,18 @@ class PortOracle(_Oracle):
                                1 if pre_cull else 0, out.ctypes.data, threads)
         return out
 
+
+    def validity_children(self, parent_box6, parent_validity, footholds, leg):
+        """validity_child (several_leg_octree.cu:19-151) on the 8 children of one parent box:
+        (flags 8 x [validity, leaf, raw, onEdge], boxes 8 x 6)."""
+        f = _as_f32(footholds, 3)
+        leg = leg_array(leg)
+        box = _as_f32(parent_box6)
+        flags = np.zeros((8, 4), np.uint8)
+        boxes = np.zeros((8, 6), np.float32)
+        self.L.op_validity_children(box.ctypes.data, int(parent_validity), f.ctypes.data, len(f), leg.ctypes.data,
+                                    flags.ctypes.data, boxes.ctypes.data)
+        return flags, boxes
 
     def apply_oct(self, footholds, leg, max_depth=1, cap=1 << 20):
         """Sequential restatement of apply_oct (several_leg_octree.cu:391-488): centres of the

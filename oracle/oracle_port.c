@@ -933,6 +933,27 @@ static void op_branch(op_node* parent, const op_f3* foot, size_t nt, const op_le
         if (!node->leaf) op_branch(node, foot, nt, leg);
     }
 }
+/* One refinement pass on a hand-built parent: the children as branchKernel initialises them
+ * (several_leg_octree.cu:315-352), then validity_child (:19-151).  flags: 8 x {validity, leaf, raw,
+ * onEdge}; boxes: 8 x {center, topOffset} — the layout oracle/ref_gpu_shim.cu::refgpu_validity_child
+ * reports for the reference's own kernel. */
+void op_validity_children(const float* parent_box6, int parent_validity, const float* footholds, size_t nt,
+                          const op_leg_t* leg, uint8_t* flags, float* boxes) {
+    op_node parent;
+    memset(&parent, 0, sizeof parent);
+    memcpy(&parent.box, parent_box6, sizeof parent.box);
+    parent.validity = parent_validity != 0;
+    parent.raw = 1;
+    op_branch(&parent, (const op_f3*)footholds, nt, leg);
+    for (int c = 0; c < 8; c++) {
+        const op_node* n = &parent.children[c];
+        flags[4 * c + 0] = (uint8_t)n->validity, flags[4 * c + 1] = (uint8_t)n->leaf;
+        flags[4 * c + 2] = (uint8_t)n->raw, flags[4 * c + 3] = (uint8_t)n->on_edge;
+        memcpy(boxes + 6 * c, &n->box, sizeof n->box);
+    }
+    free(parent.children);
+}
+
 /* fill_recus, octree_util.cu:123-147 */
 static size_t op_collect(const op_node* node, float* out, size_t n, size_t cap) {
     for (int i = 0; i < 8; i++) {

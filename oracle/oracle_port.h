@@ -83,6 +83,12 @@ int op_is_in_box(const float* v3, const float* box6);
 size_t op_apply_oct(const float* footholds, size_t nt, const op_leg_t* leg, int max_depth,
                     float* out_xyz, size_t cap);
 
+/* One pass of validity_child (several_leg_octree.cu:19-151) over the 8 children of one parent box
+ * (children initialised as in branchKernel :315-352).  flags: 8 x {validity, leaf, raw, onEdge},
+ * boxes: 8 x {center xyz, topOffset xyz}. */
+void op_validity_children(const float* parent_box6, int parent_validity, const float* footholds, size_t nt,
+                          const op_leg_t* leg, uint8_t* flags, float* boxes);
+
 /* apply_recurs (cross_compiled.cu:82-139): octree of the single-leg distance field painted on the
  * query points, out = (leaf depth, 0, 0); points outside the +-5000 mm root box are left untouched. */
 void op_apply_recurs(const float* xyz, size_t n, const op_leg_t* leg, const float* quat4, int max_depth,

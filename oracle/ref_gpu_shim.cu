@@ -13,9 +13,14 @@
 #include "cross_compiled.cuh"
 #include "one_leg.cu.h"
 #include "several_leg_octree.cu.h"
+#include "octree_util.cu.h"
+#include "settings.h"
 
 #include <cstdint>
 #include <cstring>
+
+// defined in several_leg_octree.cu:19 (no header declares it)
+__global__ void validity_child(Node parent, const Array<float3> input, const LegDimensions leg);
 
 namespace {
 inline LegDimensions leg_from(const float* l) {
@@ -61,6 +66,68 @@ float refgpu_oct(const float* footholds, size_t nt, const float* leg14, float* o
     if (m) std::memcpy(out_xyz, o.elements, m * sizeof(float3));
     delete[] o.elements;
     return ms;
+}
+
+// validity_child (several_leg_octree.cu:19-151) on a hand-built one-level tree: the per-child
+// predicate of apply_oct WITHOUT the recursion, the device heap and the dynamic parallelism that
+// keep apply_oct itself from terminating on sm_100.  The eight children are initialised the way
+// branchKernel / branchCpu do it (several_leg_octree.cu:168-199,315-352) with the reference's own
+// CreateChildBox; then the reference's kernel runs on them, unmodified.
+//   threads > 0 : ONE block of `threads` threads.  With one warp the kernel is deterministic: all
+//                 lanes finish the flag-clearing loop (:30-34) before any enters the main loop, and
+//                 there is no other block whose write-back (:134-150) races with the early-out on
+//                 node.validity (:58).
+//   threads == 0: the reference's own launch shape (one block per 256 work items, :213-221).
+// out_flags: 8 x {validity, leaf, raw, onEdge}; out_boxes: 8 x {center xyz, topOffset xyz}.
+int refgpu_validity_child(const float* parent_box6, int parent_validity, const float* footholds,
+                          size_t nt, const float* leg14, int threads, uint8_t* out_flags,
+                          float* out_boxes) {
+    Node parent;
+    std::memcpy(&parent.box, parent_box6, sizeof(Box));
+    parent.validity = parent_validity != 0;
+    parent.leaf = false, parent.raw = true, parent.onEdge = false;
+    parent.childrenCount = MaxChildQuad;
+    if (cudaMallocManaged(&parent.childrenArr, MaxChildQuad * sizeof(Node)) != cudaSuccess) return -1;
+    const bool small[3] = {0, 0, 0};
+    for (uint c = 0; c < MaxChildQuad; c++) {
+        Node& node = parent.childrenArr[c];
+        node = Node();
+        Box nb;
+        uchar missing;
+        CreateChildBox(parent.box, nb, 3, c, small, missing);
+        node.childrenCount = MaxChildQuad;
+        node.childrenArr = nullptr;
+        if (missing == DEADQUADRAN) {
+            node.leaf = true, node.raw = false, node.validity = true, node.onEdge = true;
+            node.box = NullBox;
+            continue;
+        }
+        node.onEdge = false, node.validity = false, node.box = nb;
+        node.leaf = (3 - missing) <= 0;
+        node.raw = !node.leaf;
+    }
+    Array<float3> in{nt, nullptr};
+    if (cudaMalloc(&in.elements, (nt ? nt : 1) * sizeof(float3)) != cudaSuccess) return -2;
+    cudaMemcpy(in.elements, footholds, nt * sizeof(float3), cudaMemcpyHostToDevice);
+    constexpr size_t samples = AngleSample[0] * AngleSample[1] * AngleSample[2];
+    const size_t work = (size_t)MaxChildQuad * nt * samples;
+    int block = threads, grid = 1;
+    if (threads <= 0) {
+        block = (int)(work < 256 ? (work ? work : 1) : 256);
+        grid = (int)((work + block - 1) / block);
+        if (grid < 1) grid = 1;
+    }
+    validity_child<<<grid, block>>>(parent, in, leg_from(leg14));
+    const cudaError_t e = cudaDeviceSynchronize();
+    for (uint c = 0; c < MaxChildQuad; c++) {
+        const Node& node = parent.childrenArr[c];
+        out_flags[4 * c + 0] = node.validity, out_flags[4 * c + 1] = node.leaf;
+        out_flags[4 * c + 2] = node.raw, out_flags[4 * c + 3] = node.onEdge;
+        std::memcpy(out_boxes + 6 * c, &node.box, sizeof(Box));
+    }
+    cudaFree(in.elements);
+    cudaFree(parent.childrenArr);
+    return e == cudaSuccess ? 0 : -3;
 }
 
 }  // extern "C"
