@@ -72,6 +72,21 @@ LRM_API const char* lrm_last_error(void);
  * yaw sectors; same results).  Default 4 Mi points — building the 16 MiB atlas of
  * a new (leg, orientation) costs about 0.3 ms.  Returns the previous value. */
 LRM_API size_t lrm_set_fast_path_min_points(size_t n);
+/* Tuning / measurement knobs, process-wide, none of which can change a result (every sweep returns
+ * the same bits).  *previous (may be NULL) receives the old value.
+ *   "fast_path_min_points"  see lrm_set_fast_path_min_points
+ *   "sweep"                 which sweep large distance calls take: 0 two-tier (certified tables +
+ *                           full evaluation), 1 tiered (choice volume), 2 (default) chosen per launch
+ *                           on the device by a coherence probe of the input
+ *   "tier_chunk_shift"      log2 of the consecutive tiles a CTA of the tiered sweep takes (default 3)
+ *   "volume_cell_mm", "volume_dim"   cube size and cubes per side of choice volumes built from now
+ *                           on (default 3 mm x 512: 268 MB per cached plan)
+ *   "staging_chunk_points"  points per chunk of the host-pointer pipeline (default 2 Mi)
+ *   "skeleton"              measurement builds only (LRM_ERR_UNSUPPORTED otherwise) */
+LRM_API int lrm_set_option(const char* name, double value, double* previous);
+/* Counters: "table_builds" (plane-atlas builds since the library was loaded: a cached plan builds
+ * nothing), "volume_cell_mm", "volume_dim". */
+LRM_API int lrm_get_stat(const char* name, double* value);
 LRM_API int lrm_device_count(void);
 LRM_API int lrm_set_device(int device);
 
@@ -143,6 +158,17 @@ LRM_API int lrm_positionability(const float* bodies, size_t nb, const float* map
                         const lrm_leg_t* legs, int nlegs, const float* quats, int nq,
                         const lrm_posit_opts_t* opts, uint8_t* standable, int on_device,
                         void* stream, float* kernel_ms);
+
+/* The same search with its work counted (an instrumented instantiation of the kernel: not for
+ * timing).  counts[0] = leg predicates executed (reachable_rotate_leg, several_leg.cu:48-67, on one
+ * map point), counts[1] = cull-cylinder predicates executed (several_leg.cu:504-559), counts[2] =
+ * the ALGORITHMIC leg-predicate count of these poses: for every orientation, every map
+ * point inside the reach cylinder, once per leg — what reach_mem_kernel (several_leg.cu:92-129)
+ * evaluates without pruning or early exit.  standable is filled as by lrm_positionability. */
+LRM_API int lrm_positionability_counts(const float* bodies, size_t nb, const float* map, size_t nt,
+                               const lrm_leg_t* legs, int nlegs, const float* quats, int nq,
+                               const lrm_posit_opts_t* opts, uint8_t* standable, double counts[3],
+                               int on_device, void* stream);
 
 /* Replaces apply_recurs<float3,LegDimensions,float3> (cross_compiled.cuh:9-10, cross_compiled.cu:82-139;
  * recursive_kernel one_leg_global.cu:168-251, fillOutKernel octree_util.cu:9-26): adaptive octree of

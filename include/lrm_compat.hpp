@@ -5,13 +5,14 @@
 //     apply_kernel(points, dim, reachability_global_kernel, out)      -> float ms
 //     apply_kernel(points, dim, distance_global_kernel,     out)      -> float ms
 // with Array<float3> / Array<bool> / LegDimensions.  Including THIS header instead (and linking
-// liblrm_b200.so) keeps those call sites compiling unchanged: the kernel "handles" are tag objects,
-// dispatch is by overload instead of by function pointer, layouts and ownership are the reference's
-// (caller owns host arrays; the call stages through device memory and returns kernel-only
-// milliseconds; errors print and exit(EXIT_FAILURE) like CUDA_CHECK_ERROR, cross_compiled.cu:12-20).
+// liblrm_b200.so) keeps those call sites compiling unchanged: the kernel handles are host functions
+// with the reference's own signatures, apply_kernel is the reference's template (dispatching on the
+// handle's address), layouts and ownership are the reference's (caller owns host arrays; the call
+// stages through device memory and returns kernel-only milliseconds; errors print and
+// exit(EXIT_FAILURE) like CUDA_CHECK_ERROR, cross_compiled.cu:12-20).
 //
-// The CPU twins apply_reach_cpu / apply_dist_cpu (cross_compiled.cuh:12-15) are deliberately NOT
-// provided: the product has no CPU path.  They stay with the reference (or with oracle/ in tests).
+// The CPU twins apply_reach_cpu / apply_dist_cpu (cross_compiled.cuh:12-15) are declared but
+// deliberately NOT defined: the product has no CPU path.
 #pragma once
 #include <cstddef>
 #include <cstdio>
@@ -35,44 +36,138 @@ struct Array {  // HeaderCUDA.h:38-66
 };
 
 namespace lrm_compat {
-struct ReachKernelTag {};
-struct DistKernelTag {};
-struct ForwardKineTag {};
 inline void die(const char* where, int rc) {
     std::fprintf(stderr, "CUDA error in %s: %s (lrm status %d)\n", where, lrm_last_error(), rc);
     std::exit(EXIT_FAILURE);
 }
-}  // namespace lrm_compat
-
-// kernel handles, one_leg.cu.h:18-40
-static const lrm_compat::ReachKernelTag reachability_global_kernel{}, reachability_circles_kernel{};
-static const lrm_compat::DistKernelTag distance_global_kernel{}, distance_circles_kernel{};
-static const lrm_compat::ForwardKineTag forward_kine_kernel{};
-
-// cross_compiled.cuh:4-7
-inline float apply_kernel(const Array<float3> input, const LegDimensions dim,
-                          lrm_compat::ReachKernelTag, Array<bool> const output) {
+inline float run_reach(const Array<float3> input, const LegDimensions dim, Array<bool> const output) {
     static_assert(sizeof(bool) == 1, "Array<bool> is one byte per flag");
     float ms = 0.f;
     int rc = lrm_reach(&input.elements->x, input.length, &dim, nullptr,
                        reinterpret_cast<uint8_t*>(output.elements), 0, nullptr, &ms);
-    if (rc != LRM_OK) lrm_compat::die("reachability kernel", rc);
+    if (rc != LRM_OK) die("reachability kernel", rc);
     return ms;
 }
-inline float apply_kernel(const Array<float3> input, const LegDimensions dim,
-                          lrm_compat::DistKernelTag, Array<float3> const output) {
+inline float run_dist(const Array<float3> input, const LegDimensions dim, Array<float3> const output) {
     float ms = 0.f;
     int rc = lrm_dist(&input.elements->x, input.length, &dim, nullptr, &output.elements->x, nullptr,
                       0, nullptr, &ms);
-    if (rc != LRM_OK) lrm_compat::die("distance kernel", rc);
+    if (rc != LRM_OK) die("distance kernel", rc);
     return ms;
 }
-inline float apply_kernel(const Array<float3> input, const LegDimensions dim,
-                          lrm_compat::ForwardKineTag, Array<float3> const output) {
+inline float run_forward_kine(const Array<float3> input, const LegDimensions dim, Array<float3> const output) {
     float ms = 0.f;
     int rc = lrm_forward_kine(&input.elements->x, input.length, &dim, &output.elements->x, 0,
                               nullptr, &ms);
-    if (rc != LRM_OK) lrm_compat::die("forward_kine kernel", rc);
+    if (rc != LRM_OK) die("forward_kine kernel", rc);
+    return ms;
+}
+}  // namespace lrm_compat
+
+// Kernel handles with the reference's own names AND signatures (one_leg.cu.h:18-40): host symbols,
+// so that `apply_kernel(points, dim, reachability_global_kernel, out)`, the explicit form
+// `apply_kernel<float3, LegDimensions, bool>(...)` and call sites that keep the kernel in a
+// function-pointer variable all compile and link unchanged.  apply_kernel dispatches on pointer
+// identity (inline functions have one address per program).  Calling a handle directly runs the
+// sweep with the same host-array contract.  The *_circles_* kernels are the identity-orientation
+// forms (one_leg.cu:343-375): same result as the global ones with quatTest = {1,0,0,0}.
+inline void reachability_global_kernel(const Array<float3> input, const LegDimensions dim, Array<bool> output) {
+    lrm_compat::run_reach(input, dim, output);
+}
+inline void reachability_circles_kernel(const Array<float3> input, const LegDimensions dim, Array<bool> const output) {
+    lrm_compat::run_reach(input, dim, output);
+}
+inline void distance_global_kernel(const Array<float3> input, const LegDimensions dim, Array<float3> output) {
+    lrm_compat::run_dist(input, dim, output);
+}
+inline void distance_circles_kernel(const Array<float3> input, const LegDimensions dim, Array<float3> const output) {
+    lrm_compat::run_dist(input, dim, output);
+}
+inline void forward_kine_kernel(const Array<float3> input, const LegDimensions dim, Array<float3> const output) {
+    lrm_compat::run_forward_kine(input, dim, output);
+}
+
+// cross_compiled.cuh:4-7 — the reference's template, with the two instantiations it ships
+// (cross_compiled.cu:141-151).  Returns the kernel-only milliseconds.
+template <typename T_in, typename param, typename T_out>
+float apply_kernel(const Array<T_in> input, const param dim,
+                   void (*kernel)(const Array<T_in>, const param, Array<T_out> const),
+                   Array<T_out> const output);
+template <>
+inline float apply_kernel<float3, LegDimensions, bool>(const Array<float3> input, const LegDimensions dim,
+                                                       void (*kernel)(const Array<float3>, const LegDimensions,
+                                                                      Array<bool> const),
+                                                       Array<bool> const output) {
+    if (kernel == &reachability_global_kernel || kernel == &reachability_circles_kernel)
+        return lrm_compat::run_reach(input, dim, output);
+    std::fprintf(stderr, "apply_kernel: unknown Array<bool> kernel\n");
+    std::exit(EXIT_FAILURE);
+}
+template <>
+inline float apply_kernel<float3, LegDimensions, float3>(const Array<float3> input, const LegDimensions dim,
+                                                         void (*kernel)(const Array<float3>, const LegDimensions,
+                                                                        Array<float3> const),
+                                                         Array<float3> const output) {
+    if (kernel == &distance_global_kernel || kernel == &distance_circles_kernel)
+        return lrm_compat::run_dist(input, dim, output);
+    if (kernel == &forward_kine_kernel) return lrm_compat::run_forward_kine(input, dim, output);
+    std::fprintf(stderr, "apply_kernel: unknown Array<float3> kernel\n");
+    std::exit(EXIT_FAILURE);
+}
+
+// The CPU twins (cross_compiled.cuh:12-15) are DECLARED, so that call sites which pick the compute
+// mode at compile time (`if constexpr (ComputeMode == GPUMode) ... else apply_reach_cpu(...)`,
+// several_leg.cpp:143-148) keep compiling, and deliberately NOT defined: the product has no CPU
+// path, selecting one is a link error.
+double apply_reach_cpu(const Array<float3> input, const LegDimensions dim, Array<bool> const output);
+double apply_dist_cpu(const Array<float3> input, const LegDimensions dim, Array<float3> const output);
+
+// HeaderCPP.h:54-76 — LegCompact, the reference's unfinished precomputed form of a leg
+// (apply_kernel<float3, LegCompact, ...> is instantiated but no kernel takes it, cross_compiled.cu:
+// 153-161).  Here it is the public handle of what the library precomputes per (leg, orientation):
+// build it once with LegCompacter, pass it to the LegCompact overloads of apply_kernel, and the
+// library finds the cached certified tables without rebuilding the plan.
+struct LegCompact {
+    LegDimensions dim;   // the leg it was built from
+    float quat[4];       // body orientation folded into the plan (quatTest = {1,0,0,0} in the reference)
+};
+inline LegCompact LegCompacter(const LegDimensions dim) {
+    LegCompact c;
+    c.dim = dim;
+    c.quat[0] = 1.f, c.quat[1] = c.quat[2] = c.quat[3] = 0.f;
+    return c;
+}
+inline void reachability_global_kernel(const Array<float3> input, const LegCompact leg, Array<bool> output) {
+    float ms = 0.f;
+    int rc = lrm_reach(&input.elements->x, input.length, &leg.dim, leg.quat,
+                       reinterpret_cast<uint8_t*>(output.elements), 0, nullptr, &ms);
+    if (rc != LRM_OK) lrm_compat::die("reachability kernel (LegCompact)", rc);
+}
+inline void distance_global_kernel(const Array<float3> input, const LegCompact leg, Array<float3> output) {
+    float ms = 0.f;
+    int rc = lrm_dist(&input.elements->x, input.length, &leg.dim, leg.quat, &output.elements->x, nullptr, 0,
+                      nullptr, &ms);
+    if (rc != LRM_OK) lrm_compat::die("distance kernel (LegCompact)", rc);
+}
+template <>
+inline float apply_kernel<float3, LegCompact, bool>(const Array<float3> input, const LegCompact leg,
+                                                    void (*)(const Array<float3>, const LegCompact, Array<bool> const),
+                                                    Array<bool> const output) {
+    float ms = 0.f;
+    int rc = lrm_reach(&input.elements->x, input.length, &leg.dim, leg.quat,
+                       reinterpret_cast<uint8_t*>(output.elements), 0, nullptr, &ms);
+    if (rc != LRM_OK) lrm_compat::die("reachability kernel (LegCompact)", rc);
+    return ms;
+}
+template <>
+inline float apply_kernel<float3, LegCompact, float3>(const Array<float3> input, const LegCompact leg,
+                                                      void (*)(const Array<float3>, const LegCompact,
+                                                               Array<float3> const),
+                                                      Array<float3> const output) {
+    float ms = 0.f;
+    int rc = lrm_dist(&input.elements->x, input.length, &leg.dim, leg.quat, &output.elements->x, nullptr, 0,
+                      nullptr, &ms);
+    if (rc != LRM_OK) lrm_compat::die("distance kernel (LegCompact)", rc);
     return ms;
 }
 

@@ -70,6 +70,8 @@ def lib():
         L.lrm_set_fast_path_min_points.restype = sz
         L.lrm_set_fast_path_min_points.argtypes = [sz]
         L.lrm_set_device.argtypes = [ci]
+        L.lrm_set_option.argtypes = [ctypes.c_char_p, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+        L.lrm_get_stat.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
         L.lrm_default_leg.argtypes = [ci, ctypes.c_float, legp]
         L.lrm_reach.argtypes = [vp, sz, legp, vp, vp, ci, vp, fp]
         L.lrm_dist.argtypes = [vp, sz, legp, vp, vp, vp, ci, vp, fp]
@@ -81,6 +83,8 @@ def lib():
         L.lrm_rpy_to_quat.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_float, vp]
         L.lrm_positionability.argtypes = [vp, sz, vp, sz, legp, ci, vp, ci,
                                           ctypes.POINTER(PositOpts), vp, ci, vp, fp]
+        L.lrm_positionability_counts.argtypes = [vp, sz, vp, sz, legp, ci, vp, ci, ctypes.POINTER(PositOpts), vp,
+                                                 ctypes.POINTER(ctypes.c_double), ci, vp]
         L.lrm_recurs.argtypes = [vp, sz, legp, vp, ci, vp, ci, vp, fp]
         L.lrm_oct.argtypes = [vp, sz, legp, ci, vp, sz, ctypes.POINTER(ctypes.c_size_t), ci, vp, fp]
         L.lrm_oct_sharded.argtypes = [vp, sz, legp, ci, ci, ci, vp, sz, ctypes.POINTER(ctypes.c_size_t), vp,
@@ -98,6 +102,19 @@ def _check(rc):
 def set_fast_path_min_points(n):
     """One-leg sweeps of >= n points use the certified tables (default 4 Mi); returns the old value."""
     return int(lib().lrm_set_fast_path_min_points(int(n)))
+
+
+def set_option(name, value):
+    """lrm_set_option: tuning / measurement knobs (none changes a result); returns the old value."""
+    prev = ctypes.c_double(0.0)
+    _check(lib().lrm_set_option(name.encode(), float(value), ctypes.byref(prev)))
+    return prev.value
+
+
+def get_stat(name):
+    v = ctypes.c_double(0.0)
+    _check(lib().lrm_get_stat(name.encode(), ctypes.byref(v)))
+    return v.value
 
 
 def get_leg(robot, azimuth=0.0):
@@ -359,6 +376,27 @@ def positionability(bodies, map_points, legs, quats=None, pre_cull=False, stream
         _check(lib().lrm_positionability(pb, nb, pm, nt, leg_arr, len(legs), quats.ctypes.data,
                                          quats.shape[0], ctypes.byref(opts), out.ctypes.data, 0, None, msp))
     return (out, ms.value) if timing else out
+
+
+def positionability_counts(bodies, map_points, legs, quats=None, pre_cull=False, stream=None):
+    """lrm_positionability_counts on device tensors: (standable, {"leg_predicates_executed",
+    "cylinder_predicates_executed", "leg_predicates_algorithmic"})."""
+    import torch
+    devb, pb, nb, kb = _prep_points(bodies)
+    devm, pm, nt, km = _prep_points(map_points)
+    assert devb == 1 and devm == 1, "device tensors only"
+    quats = full_struct_orientations() if quats is None else np.ascontiguousarray(quats, np.float32)
+    quats = quats.reshape(-1, 4)
+    leg_arr = (LegDimensions * len(legs))(*legs)
+    opts = PositOpts(1 if pre_cull else 0, 0)
+    out = torch.empty(nb, dtype=torch.uint8, device=bodies.device)
+    counts = (ctypes.c_double * 3)()
+    st = _stream_for(stream, bodies)
+    with _device_of(bodies, map_points):
+        _check(lib().lrm_positionability_counts(pb, nb, pm, nt, leg_arr, len(legs), quats.ctypes.data, quats.shape[0],
+                                                ctypes.byref(opts), out.data_ptr(), counts, 1, st))
+    return out, {"leg_predicates_executed": counts[0], "cylinder_predicates_executed": counts[1],
+                 "leg_predicates_algorithmic": counts[2]}
 
 
 def apply_recurs(points, leg, max_depth=1, quat=None, fill=-1.0, stream=None):

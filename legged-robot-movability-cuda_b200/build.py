@@ -20,6 +20,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-std=c++17", "-O3", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    # host-built constants (leg plans, yaw tables, gravity knife-edge coefficients) must round like
+    # the reference's host pass and the oracle: never contract a*b+c (GCC does by default on aarch64)
+    "-Xcompiler", "-ffp-contract=off",
     "--expt-relaxed-constexpr",
     "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
 ]

@@ -22,6 +22,12 @@ cudaError_t launch_one_leg_aos(int mode, const LegPlan& plan, const float* xyz, 
 // Sweeps (calls) of at least this many points use the certified tables (default 4 Mi: building the
 // atlas costs ~0.3 ms per new plan); returns the previous value.
 size_t set_fast_path_min_points(size_t n);
+// lrm_set_option: 0 = two-tier sweep, 1 = tiered sweep, 2 = chosen per launch by the coherence probe;
+// log2 of the tiles per chunk of the tiered sweep; the staging skeleton (measurement builds only, else -1).
+// Each returns the previous value.
+int set_sweep_mode(int mode);
+int set_tier_chunk_shift(int shift);
+int set_skeleton(int on);
 // SoA planes; dx == nullptr selects reach-only.
 cudaError_t launch_one_leg_soa(const LegPlan& plan, const float* x, const float* y, const float* z,
                                float* dx, float* dy, float* dz, uint8_t* flag, size_t n,
@@ -37,16 +43,27 @@ cudaError_t launch_lattice(float* out, const float lo[3], const float step[3],
                            cudaStream_t stream);
 
 // Certified tables of a plan's distance fast path (plane_atlas.cu): the plane atlas (device) and
-// the yaw-sector table (host, passed as a kernel parameter); built on first use, cached per device.
+// the yaw-sector table (host, passed as a kernel parameter); built on first use, cached per device
+// (8 plans each).  acquire_tables PINS the entry: it cannot be evicted or rebuilt until
+// release_tables, which must follow the caller's last launch that reads the views (it records that
+// use on `stream`, so that a later rebuild is ordered after it on the device).  No host wait.
 struct AtlasView;
-cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView* view,
-                            FastTables* tables);
+struct TableLease {
+    void* entry = nullptr;
+};
+cudaError_t acquire_tables(const LegPlan& plan, cudaStream_t stream, AtlasView* view, FastTables* tables,
+                           TableLease* lease);
+void release_tables(TableLease* lease, cudaStream_t stream);
 
-// Choice volume of a plan whose atlas is cached (get_plane_atlas first): 3-D texture of the winning
-// coxa solution per cube (plane_atlas.cu).  Built in the background on first request: until it is
-// there the call returns cudaErrorNotReady (wait = false) or blocks (wait = true).
+// Choice volume of a leased plan: 3-D texture of 16-bit texels (winning coxa solution + plane label
+// per cube, plane_atlas.cu).  Built in the background on first request: until it is there the call
+// returns cudaErrorNotReady (wait = false) or blocks (wait = true).
 struct VolumeView;
-cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeView* view, bool wait);
+cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, VolumeView* view, bool wait);
+// cube size (mm) and cubes per side (multiple of 4) of volumes built from now on; -1 if out of range
+int set_choice_volume_shape(float cell_mm, int dim);
+void get_choice_volume_shape(float* cell_mm, int* dim);
+unsigned long long table_builds();  // atlas builds since load (diagnostics)
 
 // Multi-leg positionability (positionability.cu).  All pointers are device pointers.
 struct PositParams {
@@ -60,6 +77,7 @@ struct PositParams {
     int nq;
     int pre_cull;
     uint8_t* standable;    // nb
+    double* stats = nullptr;  // host, 3 entries, or nullptr: see lrm_positionability_counts
 };
 cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float* kernel_ms);
 

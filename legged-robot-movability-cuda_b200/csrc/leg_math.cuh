@@ -1040,6 +1040,82 @@ LRM_HD unsigned choice_cell_byte(const LegPlan& L, const SectorTable& tab, const
     return byte | reach;
 }
 
+// ---- plane label of a cube: tier 0 of the distance sweep ----------------------------------------
+// dist_choice still needs the plane-atlas cell of the chosen solution's plane point: a second
+// fetch that DEPENDS on the first.  The plane point (X, z) of a solution is a 1-Lipschitz image of
+// the point (X = +-rho - coxa for an unsaturated / mega yaw, a fixed direction's abscissa at a coxa
+// limit), so over a cube it stays inside a small rectangle of the plane: where the whole
+// rectangle carries ONE certified atlas label, that label is a property of the cube and travels in
+// the high byte of the cube's texel — one fetch per point, no dependent one.
+// texel (16 bit): low byte = cube byte as above; high byte = 0, or the atlas cell byte (bit 7 set,
+// bit 6 valid, bits 4-5 sector, bits 0-3 winner) shared by every plane point of the cube.
+//
+// Plane abscissa of one solution of p, exactly as dist_coxa_frame builds it (branch_prep).
+LRM_HD float solution_plane_x(const LegPlan& L, const CoxaPoint p, bool flipped) {
+    const float rho2 = fmaf(p.x, p.x, p.y * p.y);
+    const float inv_rho = rho2 > 0.f ? fast_rsqrt(rho2) : 0.f;
+    const float ux = rho2 > 0.f ? p.x * inv_rho : 1.f;
+    const float uy = rho2 > 0.f ? p.y * inv_rho : 0.f;
+    YawFlags fa, fb;
+    yaw_tests_both(L, p.x, p.y, fa, fb);
+    return flipped ? branch_prep(L, p, fb, -ux, -uy).X : branch_prep(L, p, fa, ux, uy).X;
+}
+// slack on the rectangle: float rounding of the plane point in the sweep vs here (< 1e-3 mm)
+constexpr float kPlaneRectSlack = 0.02f;
+// (a) by the instrumented evaluation at the centre: every decision keeps its sign within the
+//     cube's half diagonal.  Used on blocks of cubes (one probe settles 64 cubes of the far field).
+LRM_HD unsigned cube_plane_probe(const LegPlan& L, const SectorTable& tab, float Xc, float zc, float side) {
+    const PlaneProbe pr = plane_probe(L, tab, Xc, zc);
+    return pr.safety > 0.8660255f * side + kPlaneRectSlack ? (kAtlasPure | (unsigned)pr.label) : 0u;
+}
+// (b) by the atlas itself: every cell meeting the rectangle [Xc +- d_xy] x [zc +- side / 2] is
+//     certified with the same label (d_xy = half diagonal of the xy footprint: |dX| <= |d(x, y)|).
+//     Each certified cell vouches for all of its points, so the union vouches for the cube.
+LRM_HD unsigned cube_plane_scan(const AtlasView& A, float Xc, float zc, float side) {
+    const float dx = 0.70710678f * side + kPlaneRectSlack, dz = 0.5f * side + kPlaneRectSlack;
+    const int ix0 = (int)floorf(fmaf(Xc - dx, A.inv_cell, A.ox)), ix1 = (int)floorf(fmaf(Xc + dx, A.inv_cell, A.ox));
+    const int iy0 = (int)floorf(fmaf(zc - dz, A.inv_cell, A.oy)), iy1 = (int)floorf(fmaf(zc + dz, A.inv_cell, A.oy));
+    if (ix0 < 0 || iy0 < 0 || ix1 >= A.w || iy1 >= A.h) return 0u;
+    const unsigned ref = A.cells[atlas_index(A.w, ix0, iy0)];
+    if (!(ref & kAtlasPure)) return 0u;
+    for (int iy = iy0; iy <= iy1; iy++)
+        for (int ix = ix0; ix <= ix1; ix++)
+            if (A.cells[atlas_index(A.w, ix, iy)] != ref) return 0u;
+    return ref;
+}
+// Centre of the padded cube and its side, as choice_cell_first sees them.
+LRM_HD CoxaPoint cube_centre(float x0, float y0, float z0, float h, float* side) {
+    const float pad = vol_pad(h);
+    *side = h + 2.f * pad;
+    CoxaPoint c;
+    c.x = x0 - pad + 0.5f * *side, c.y = y0 - pad + 0.5f * *side, c.z = z0 - pad + 0.5f * *side;
+    return c;
+}
+// Texel shared by a whole block of cubes (the coarse pass of the volume build), or 0 when the block
+// is not settled as a whole: the centre must decide the choice, the reach bits AND the plane label
+// without any refinement.
+LRM_HD unsigned coarse_block_word(const LegPlan& L, const SectorTable& tab, const FastTables& FT, float x0, float y0,
+                                  float z0, float h) {
+    const CellFirst f = choice_cell_first(L, tab, FT, x0, y0, z0, h);
+    if (f.byte == 0u || f.refine || f.reach == 0u || f.reach_refine) return 0u;
+    float side;
+    const CoxaPoint c = cube_centre(x0, y0, z0, h, &side);
+    const unsigned hi = cube_plane_probe(L, tab, solution_plane_x(L, c, (f.byte & 1u) != 0u), c.z, side);
+    return hi ? (f.byte | f.reach | (hi << 8)) : 0u;
+}
+// Whole texel of one cube, serially (host emulation; the device build splits the work):
+// probe = true certifies the plane label as the coarse pass does, false as the fine pass does.
+LRM_HD unsigned choice_cell_word(const LegPlan& L, const SectorTable& tab, const FastTables& FT, const AtlasView& A,
+                                 float x0, float y0, float z0, float h, bool probe) {
+    const unsigned lo = choice_cell_byte(L, tab, FT, x0, y0, z0, h);
+    if (!(lo & kVolPure)) return lo;
+    float side;
+    const CoxaPoint c = cube_centre(x0, y0, z0, h, &side);
+    const float Xc = solution_plane_x(L, c, (lo & 1u) != 0u);
+    const unsigned hi = probe ? cube_plane_probe(L, tab, Xc, c.z, side) : cube_plane_scan(A, Xc, c.z, side);
+    return lo | (hi << 8);
+}
+
 // One point of a certified cube: the chosen solution only.  Same arithmetic as dist_fast for that
 // solution.  Straight-line; returns 0 = done, 1 = cube uncertified (dist_fast can still decide the
 // point), 2 = the chosen solution's plane cell is uncertified (full evaluation).
@@ -1088,6 +1164,28 @@ LRM_HD int dist_choice_back(const LegPlan& L, const YawSol* sols, unsigned cube,
     out->dz = fmaf(L.Mo[6], vx, fmaf(L.Mo[7], vy, L.Mo[8] * vz));
     return (cube & kVolPure) ? ((f.la & kAtlasPure) ? 0 : 2) : 1;
 }
+// Tier 0: one point whose cube texel carries both the chosen solution and its plane label.  The
+// very operations of dist_choice_back on the label, without any plane-atlas fetch.  Returns 0 =
+// done, 1 = cube uncertified (-> dist_fast), 3 = solution certified but the cube has no plane
+// label (-> dist_choice through the plane atlas).  `word` is the 16-bit texel.
+template <bool RULE>
+LRM_HD int dist_choice_label(const LegPlan& L, const YawSol* sols, unsigned word, const WinnerTable& W,
+                             const CoxaPoint p, DistResult* out) {
+    const unsigned cube = word & 0xffu, la = word >> 8;
+    const YawSol& s = sols[cube & 31u];
+    const float rho2 = fmaf(p.x, p.x, p.y * p.y);
+    // no guard against rho2 = 0: certified cubes stay clear of the coxa axis (where the guard of
+    // dist_choice is the identity), and an uncertified point's result is discarded
+    const float inv_rho = fast_rsqrt(rho2);
+    const float ux = p.x * inv_rho, uy = p.y * inv_rho;
+    ChoiceFront f;
+    f.cs = fmaf(s.k, ux, s.c_cs), f.ss = fmaf(s.k, uy, s.c_ss);
+    f.X = fmaf(p.x, f.cs, p.y * f.ss) - L.coxa_length;
+    f.la = la;
+    dist_choice_back<RULE>(L, sols, cube, f, W, p, out);
+    return (cube & kVolPure) ? ((la & kAtlasPure) ? 0 : 3) : 1;
+}
+
 template <bool TEX>
 LRM_HD int dist_choice(const LegPlan& L, const YawSol* sols, unsigned cube, const AtlasView& A,
                        const WinnerTable& W, const CoxaPoint p, DistResult* out) {

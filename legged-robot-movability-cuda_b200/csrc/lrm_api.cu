@@ -7,8 +7,8 @@
 // the CUDA kernels or fails with LRM_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -81,20 +81,14 @@ struct EventPair {
 // Chunk size: small enough that filling and draining the pipeline (one chunk up before the first
 // kernel, one chunk down after the last) is a small share of a call, large enough that each copy
 // runs at the link rate (>= 24 MiB on this box's PCIe 5 x16, tools/pcie_probe.py).
-// LRM_STAGING_CHUNK (points) overrides it for measurements.
+// lrm_set_option("staging_chunk_points") overrides it for measurements.
 constexpr size_t kDefaultChunkPoints = size_t(1) << 21;  // 2 Mi points: 24 MiB up, 26 MiB down
 constexpr int kSlots = 4;
-size_t chunk_points() {
-    static size_t v = 0;
-    if (v == 0) {
-        const char* e = getenv("LRM_STAGING_CHUNK");
-        const long long want = e ? atoll(e) : 0;
-        v = want >= 4096 ? ((size_t)want & ~size_t(15)) : kDefaultChunkPoints;
-    }
-    return v;
-}
+std::atomic<size_t> g_chunk_points{kDefaultChunkPoints};
+size_t chunk_points() { return g_chunk_points.load(std::memory_order_relaxed); }
 
 struct Staging {
+    size_t chunk_points = 0;
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
     cudaEvent_t uploaded[kSlots] = {}, computed[kSlots] = {}, drained[kSlots] = {};
     cudaEvent_t k0[kSlots] = {}, k1[kSlots] = {};
@@ -103,6 +97,7 @@ struct Staging {
     uint8_t* d_flag[kSlots] = {};
     cudaError_t init(size_t chunk, int nslots, bool want_vec, bool want_flag) {
         cudaError_t e;
+        chunk_points = chunk;
         if ((e = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking)) != cudaSuccess) return e;
         if ((e = cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking)) != cudaSuccess) return e;
         if ((e = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking)) != cudaSuccess) return e;
@@ -155,6 +150,10 @@ int staged_one_leg(int mode, const lrm::LegPlan& plan, const float* xyz, size_t 
         int dev = 0;
         cudaGetDevice(&dev);
         Staging*& slot = pool[dev & 63];
+        if (slot && slot->chunk_points != kChunkPoints) {  // the option changed: calls are synchronous, the set is idle
+            delete slot;
+            slot = nullptr;
+        }
         if (!slot) {
             slot = new Staging();
             cudaError_t e = slot->init(kChunkPoints, kSlots, true, true);
@@ -269,6 +268,57 @@ int lrm_abi_version(void) { return LRM_ABI_VERSION; }
 const char* lrm_last_error(void) { return g_error.c_str(); }
 
 size_t lrm_set_fast_path_min_points(size_t n) { return lrm::set_fast_path_min_points(n); }
+
+int lrm_set_option(const char* name, double value, double* previous) {
+    if (!name) return fail(LRM_ERR_INVALID, "name is NULL");
+    const std::string k(name);
+    double prev = 0.0;
+    if (k == "fast_path_min_points") {
+        if (!(value >= 0)) return fail(LRM_ERR_INVALID, "fast_path_min_points must be >= 0");
+        prev = (double)lrm::set_fast_path_min_points((size_t)value);
+    } else if (k == "sweep") {
+        if (value != 0 && value != 1 && value != 2) return fail(LRM_ERR_INVALID, "sweep must be 0, 1 or 2");
+        prev = lrm::set_sweep_mode((int)value);
+    } else if (k == "tier_chunk_shift") {
+        if (!(value >= 0 && value <= 8)) return fail(LRM_ERR_INVALID, "tier_chunk_shift must be 0..8");
+        prev = lrm::set_tier_chunk_shift((int)value);
+    } else if (k == "volume_cell_mm" || k == "volume_dim") {
+        float cell;
+        int dim;
+        lrm::get_choice_volume_shape(&cell, &dim);
+        prev = k == "volume_dim" ? (double)dim : (double)cell;
+        if (lrm::set_choice_volume_shape(k == "volume_dim" ? cell : (float)value, k == "volume_dim" ? (int)value : dim) != 0)
+            return fail(LRM_ERR_INVALID, "volume_cell_mm must be 0.5..64, volume_dim a multiple of 4 in 16..1024");
+    } else if (k == "staging_chunk_points") {
+        if (!(value >= 4096 && value <= (double)(size_t(1) << 30)))
+            return fail(LRM_ERR_INVALID, "staging_chunk_points must be 4096..2^30");
+        prev = (double)g_chunk_points.exchange((size_t)value & ~size_t(15));
+    } else if (k == "skeleton") {
+        const int r = lrm::set_skeleton(value != 0 ? 1 : 0);
+        if (r < 0) return fail(LRM_ERR_UNSUPPORTED, "skeleton needs a measurement build (-DLRM_ENABLE_SKELETON)");
+        prev = r;
+    } else {
+        return fail(LRM_ERR_INVALID, "unknown option: " + k);
+    }
+    if (previous) *previous = prev;
+    return LRM_OK;
+}
+
+int lrm_get_stat(const char* name, double* value) {
+    if (!name || !value) return fail(LRM_ERR_INVALID, "NULL argument");
+    const std::string k(name);
+    if (k == "table_builds") {
+        *value = (double)lrm::table_builds();
+    } else if (k == "volume_cell_mm" || k == "volume_dim") {
+        float cell;
+        int dim;
+        lrm::get_choice_volume_shape(&cell, &dim);
+        *value = k == "volume_dim" ? (double)dim : (double)cell;
+    } else {
+        return fail(LRM_ERR_INVALID, "unknown statistic: " + k);
+    }
+    return LRM_OK;
+}
 
 int lrm_device_count(void) {
     int n = 0;
@@ -452,10 +502,10 @@ int lrm_rpy_to_quat(float roll, float pitch, float yaw, float out[4]) {
     return LRM_OK;
 }
 
-int lrm_positionability(const float* bodies, size_t nb, const float* map, size_t nt,
-                        const lrm_leg_t* legs, int nlegs, const float* quats, int nq,
-                        const lrm_posit_opts_t* opts, uint8_t* standable, int on_device,
-                        void* stream_v, float* kernel_ms) {
+static int positionability_call(const float* bodies, size_t nb, const float* map, size_t nt,
+                                const lrm_leg_t* legs, int nlegs, const float* quats, int nq,
+                                const lrm_posit_opts_t* opts, uint8_t* standable, int on_device,
+                                void* stream_v, float* kernel_ms, double* stats) {
     if (!legs || nlegs <= 0 || nlegs > 8) return fail(LRM_ERR_INVALID, "1..8 legs required");
     if (!quats || nq <= 0 || nq > 254) return fail(LRM_ERR_INVALID, "1..254 orientations required");
     if (nb && (!bodies || !standable)) return fail(LRM_ERR_INVALID, "NULL body buffer");
@@ -467,6 +517,7 @@ int lrm_positionability(const float* bodies, size_t nb, const float* map, size_t
     lrm::PositParams p;
     p.nb = nb, p.nt = nt, p.legs = legs, p.nlegs = nlegs, p.quats = quats, p.nq = nq;
     p.pre_cull = opts ? opts->pre_cull : 0;
+    p.stats = stats;
     DeviceScratch scratch;
     if (on_device) {
         p.bodies = bodies, p.map = map, p.standable = standable;
@@ -492,6 +543,24 @@ int lrm_positionability(const float* bodies, size_t nb, const float* map, size_t
         LRM_CUDA(cudaStreamSynchronize(stream), "stream synchronize");
     }
     return LRM_OK;
+}
+
+int lrm_positionability(const float* bodies, size_t nb, const float* map, size_t nt,
+                        const lrm_leg_t* legs, int nlegs, const float* quats, int nq,
+                        const lrm_posit_opts_t* opts, uint8_t* standable, int on_device,
+                        void* stream_v, float* kernel_ms) {
+    return positionability_call(bodies, nb, map, nt, legs, nlegs, quats, nq, opts, standable, on_device, stream_v,
+                                kernel_ms, nullptr);
+}
+
+int lrm_positionability_counts(const float* bodies, size_t nb, const float* map, size_t nt,
+                               const lrm_leg_t* legs, int nlegs, const float* quats, int nq,
+                               const lrm_posit_opts_t* opts, uint8_t* standable, double counts[3],
+                               int on_device, void* stream_v) {
+    if (!counts) return fail(LRM_ERR_INVALID, "counts is NULL");
+    counts[0] = counts[1] = counts[2] = 0.0;
+    return positionability_call(bodies, nb, map, nt, legs, nlegs, quats, nq, opts, standable, on_device, stream_v,
+                                nullptr, counts);
 }
 
 int lrm_oct_sharded(const float* footholds, size_t nt, const lrm_leg_t* leg, int max_depth, int shard, int nshards,

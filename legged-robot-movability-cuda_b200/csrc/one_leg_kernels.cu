@@ -255,8 +255,8 @@ __global__ void __launch_bounds__(kThreads)
                         x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
                     }
                     p[k] = to_coxa_frame(L, x, y, z);
-                    c[k] = tex3D<unsigned char>(vol.tex, fmaf(p[k].x, vol.inv_cell, vol.o),
-                                                fmaf(p[k].y, vol.inv_cell, vol.oy), fmaf(p[k].z, vol.inv_cell, vol.o));
+                    c[k] = tex3D<unsigned short>(vol.tex, fmaf(p[k].x, vol.inv_cell, vol.o),
+                                                 fmaf(p[k].y, vol.inv_cell, vol.oy), fmaf(p[k].z, vol.inv_cell, vol.o));
                 }
 #pragma unroll
                 for (int k = 0; k < kPer; k++) {
@@ -395,18 +395,24 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ---- tiered distance sweep ----------------------------------------------------------------------
-// Tier 1 (every point): the choice volume names the winning coxa solution of the point's cube;
-// that ONE solution is evaluated through the plane atlas (dist_choice).  What tier 1 cannot
-// decide is parked in one of three per-CTA rings and redone later, 256 entries at a time by all
-// threads of the CTA (dense warps, every lane on the same path), from / to global memory, and only
-// after the bulk store of the entry's tile has completed (see one_leg_stream_kernel):
-//   ring A: the cube is certified but the chosen solution's plane cell is not -> the same ONE
-//           solution with the explicit plane evaluation (dist_choice_clamp); cannot fail;
+// Tier 0 (every point): ONE fetch from the choice volume returns a 16-bit texel — the winning coxa
+// solution of the point's cube and, where the cube's whole plane rectangle carries one certified
+// plane-atlas label, that label.  The point is then finished with one projection on the labelled
+// circle / corner (dist_choice_label): no dependent second fetch, no round trip through shared
+// memory.  All four texel fetches of a thread are in flight together.  What tier 0 cannot decide is
+// parked in one of four per-CTA rings and redone later, 256 entries at a time by all threads of
+// the CTA (dense warps, every lane on the same path), from / to global memory, and only after the
+// bulk store of the entry's tile has completed (see one_leg_stream_kernel):
+//   ring P: solution certified, no plane label for the cube -> the same ONE solution through the
+//           plane atlas (dist_choice); hands on to ring A if the point's atlas cell is uncertified;
+//   ring A: -> the same ONE solution with the explicit plane evaluation (dist_choice_clamp); cannot fail;
 //   ring B: the cube is uncertified -> both solutions through the tables (dist_fast);
 //   ring C: what ring B's redo cannot decide -> the full evaluation.
-// A ring that is full refuses the push; the point then moves to the next ring or is evaluated on
-// the spot (correct, just divergent).  Every path applies the same operations to the winning
-// candidate, so the output does not depend on which one ran.
+// A ring that is full refuses the push; the point then moves to ring C or is evaluated on the spot
+// (correct, just divergent).  Every path applies the same operations to the winning candidate, so
+// the output does not depend on which one ran.  A parked point's slot keeps the INPUT point, which
+// the tile's store writes to the output and the redo later replaces: a call whose output buffer is
+// its input buffer stays correct (the redo re-reads an unchanged input).
 // CTA shape of the tiered sweep (its own: the other sweeps keep kThreads / kTile)
 #ifndef LRM_TIER_THREADS
 #define LRM_TIER_THREADS 256
@@ -417,15 +423,20 @@ __global__ void __launch_bounds__(kThreads)
 #ifndef LRM_TIER_CTAS
 #define LRM_TIER_CTAS 4
 #endif
+#ifndef LRM_T0_GROUP
+#define LRM_T0_GROUP 4  // points of a thread that share one "any valid plane point in the warp" vote
+#endif
 constexpr int kTT = LRM_TIER_THREADS;  // threads per CTA
 constexpr int kTL = LRM_TIER_TILE;     // points per tile
-static_assert(kTL % kTT == 0 && kTL % 16 == 0 && kTL <= 1024 && kTL / kTT == 4, "tier tile shape");
+constexpr int kPer = kTL / kTT;        // points per thread and tile
+static_assert(kTL % kTT == 0 && kTL % 16 == 0 && kTL <= 1024 && kPer % LRM_T0_GROUP == 0, "tier tile shape");
 #ifndef LRM_RING_A
+#define LRM_RING_P 512
 #define LRM_RING_A 512
 #define LRM_RING_B 512
 #define LRM_RING_C 512
 #endif
-constexpr int kRingA = LRM_RING_A, kRingB = LRM_RING_B, kRingC = LRM_RING_C;  // entries (powers of two)
+constexpr int kRingP = LRM_RING_P, kRingA = LRM_RING_A, kRingB = LRM_RING_B, kRingC = LRM_RING_C;  // entries (powers of two)
 // ring entry: iteration (17 bits) | cube byte bits 0-4 | index in tile (10 bits)
 constexpr int kEntryIterBits = 17;
 
@@ -435,8 +446,8 @@ struct alignas(128) TierSmem {
     alignas(16) SectorTable table;
     alignas(16) WinnerTable winners;
     alignas(16) YawPair ypair[kYawPairs];
-    uint32_t ring_a[kRingA], ring_b[kRingB], ring_c[kRingC];
-    unsigned cnt[3][3];  // [ring][it % 3]: pushes attempted in that iteration
+    uint32_t ring_p[kRingP], ring_a[kRingA], ring_b[kRingB], ring_c[kRingC];
+    unsigned cnt[4][3];  // [ring P, A, B, C][it % 3]: pushes attempted in that iteration
     alignas(8) uint64_t full[3];
 };
 
@@ -491,7 +502,17 @@ __device__ __forceinline__ void redo_store(const RedoIo& io, size_t g, const Dis
     if (io.out_flag) io.out_flag[g] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
 }
 // The redo paths are deliberately NOT inlined (see redo_point).
-// ring A: the chosen solution (cube bits carried by the entry) with the explicit plane evaluation
+// ring P: the chosen solution (cube bits carried by the entry) through the plane atlas; false
+// (nothing written) if the point's atlas cell is uncertified
+template <int MODE, bool SOA>
+__device__ __noinline__ bool redo_atlas(const LegPlan& L, const YawSol* sols, unsigned cube, const AtlasView& A,
+                                        const WinnerTable& W, const RedoIo& io, size_t g) {
+    DistResult r;
+    if (dist_choice<true>(L, sols, cube | kVolPure, A, W, redo_load<SOA>(L, io, g), &r) != 0) return false;
+    redo_store<MODE, SOA>(io, g, r);
+    return true;
+}
+// ring A: the chosen solution with the explicit plane evaluation
 template <int MODE, bool SOA>
 __device__ __noinline__ void redo_choice(const LegPlan& L, const SectorTable& tab, const YawSol* sols,
                                          unsigned cube, const RedoIo& io, size_t g) {
@@ -515,17 +536,17 @@ __device__ __noinline__ void redo_full(const LegPlan& L, const SectorTable& tab,
 }
 
 // full evaluation of one point of the tile in shared memory, in place (ring overflow only); the
-// slot already holds the point in the coxa frame
+// slot still holds the input point
 template <int MODE, bool SOA>
 __device__ __noinline__ void tile_point_full(const LegPlan& L, const SectorTable& tab, float* tile,
                                              uint8_t* flag, int i) {
-    CoxaPoint p;
+    float x, y, z;
     if (SOA) {
-        p.x = tile[i], p.y = tile[kTL + i], p.z = tile[2 * kTL + i];
+        x = tile[i], y = tile[kTL + i], z = tile[2 * kTL + i];
     } else {
-        p.x = tile[3 * i], p.y = tile[3 * i + 1], p.z = tile[3 * i + 2];
+        x = tile[3 * i], y = tile[3 * i + 1], z = tile[3 * i + 2];
     }
-    const DistResult r = dist_coxa_frame<false>(L, tab, p);
+    const DistResult r = dist_coxa_frame<false>(L, tab, to_coxa_frame(L, x, y, z));
     if (SOA) {
         tile[i] = r.dx, tile[kTL + i] = r.dy, tile[2 * kTL + i] = r.dz;
     } else {
@@ -540,10 +561,14 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
                         const AtlasView atlas, const VolumeView vol, const __grid_constant__ RedoIo io,
                         size_t n, int kshift_arg, const int* __restrict__ gate, int gate_want) {
     if (gate != nullptr && *gate != gate_want) return;  // the coherence probe chose the other sweep
-    // bit 8 of the argument (LRM_TIER_SKELETON=1, measurements only): move the tiles but skip the
-    // arithmetic — the ceiling of the staging pipeline itself
     const int kshift = kshift_arg & 0xff;
+#ifdef LRM_ENABLE_SKELETON
+    // measurement builds only: move the tiles but skip the arithmetic — the ceiling of the staging
+    // pipeline itself (results are garbage)
     const bool skeleton = (kshift_arg & 0x100) != 0;
+#else
+    constexpr bool skeleton = false;
+#endif
     extern __shared__ __align__(128) unsigned char smem_raw[];
     auto& S = *reinterpret_cast<TierSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -556,7 +581,7 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
     for (int i = tid; i < kYawPairs * (int)(sizeof(YawPair) / 4); i += kTT)
         reinterpret_cast<float*>(S.ypair)[i] = reinterpret_cast<const float*>(FT.pair)[i];
     if (tid == 0) {
-        for (int k = 0; k < 9; k++) (&S.cnt[0][0])[k] = 0;
+        for (int k = 0; k < 12; k++) (&S.cnt[0][0])[k] = 0;
         for (int s = 0; s < kStages; s++) bulk::mbar_init(&S.full[s], 1);
         bulk::fence_barrier_init();
     }
@@ -579,8 +604,8 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
         }
     };
     // Tiles are dealt to the CTAs in chunks of 2^kshift consecutive tiles: neighbouring tiles of a
-    // lattice sweep are neighbouring columns, whose points fall into the same cubes and plane
-    // cells, so a CTA's texture fetches keep hitting lines it has just brought in.
+    // lattice sweep are neighbouring columns, whose points fall into the same cubes, so a CTA's
+    // texture fetches keep hitting lines it has just brought in.
     auto tile_of = [&](uint32_t iter) -> uint32_t {
         return (((iter >> kshift) * gridDim.x + blockIdx.x) << kshift) + (iter & ((1u << kshift) - 1u));
     };
@@ -595,6 +620,7 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
     const FastView fview{S.ypair, FT.code, FT.combo, FT.ncombo};
     const YawSol* sols = reinterpret_cast<const YawSol*>(S.ypair);
     uint32_t it = 0;
+    Ring<kRingP> rp;
     Ring<kRingA> ra;
     Ring<kRingB> rb;
     Ring<kRingC> rc;
@@ -609,10 +635,14 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
     auto do_c = [&](uint32_t entry) { redo_full<MODE, SOA>(L, S.table, io, global_index(entry)); };
     auto do_b = [&](uint32_t entry) {
         if (!redo_fast<MODE, SOA>(L, fview, atlas, S.winners, io, global_index(entry)))
-            if (!rc.push(S.ring_c, &S.cnt[2][rot], entry)) do_c(entry);
+            if (!rc.push(S.ring_c, &S.cnt[3][rot], entry)) do_c(entry);
     };
     auto do_a = [&](uint32_t entry) {
         redo_choice<MODE, SOA>(L, S.table, sols, (entry >> 10) & 31u, io, global_index(entry));
+    };
+    auto do_p = [&](uint32_t entry) {
+        if (!redo_atlas<MODE, SOA>(L, sols, (entry >> 10) & 31u, atlas, S.winners, io, global_index(entry)))
+            if (!ra.push(S.ring_a, &S.cnt[1][rot], entry)) do_a(entry);
     };
 
     for (uint32_t tile = tile_of(0); tile < n_tiles; tile = tile_of(++it)) {
@@ -623,9 +653,10 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
 
         // counters of the previous iteration are final since its tile barrier
         const int rot_prev = rot == 0 ? 2 : rot - 1;
-        ra.advance(S.cnt[0][rot_prev]);
-        rb.advance(S.cnt[1][rot_prev]);
-        rc.advance(S.cnt[2][rot_prev]);
+        rp.advance(S.cnt[0][rot_prev]);
+        ra.advance(S.cnt[1][rot_prev]);
+        rb.advance(S.cnt[2][rot_prev]);
+        rc.advance(S.cnt[3][rot_prev]);
 #pragma unroll 1
         while (rc.elig - rc.head >= (uint32_t)kTT) {
             do_c(S.ring_c[(rc.head + tid) & (kRingC - 1)]);
@@ -641,6 +672,11 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
             do_a(S.ring_a[(ra.head + tid) & (kRingA - 1)]);
             ra.head += kTT;
         }
+#pragma unroll 1
+        while (rp.elig - rp.head >= (uint32_t)kTT) {
+            do_p(S.ring_p[(rp.head + tid) & (kRingP - 1)]);
+            rp.head += kTT;
+        }
 
         auto load_pt = [&](int i, float& x, float& y, float& z) {
             if (SOA) {
@@ -649,90 +685,83 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
                 x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
             }
         };
-        auto store3 = [&](int i, float x, float y, float z) {
-            if (SOA) {
-                in[i] = x, in[kTL + i] = y, in[2 * kTL + i] = z;
-            } else {
-                in[3 * i] = x, in[3 * i + 1] = y, in[3 * i + 2] = z;
-            }
-        };
-        // Phase 1: every point of the thread goes to the coxa frame (kept in the point's own slot)
-        // and its cube byte is requested; the bytes are parked in the flag slots.  All of a
-        // thread's volume fetches are in flight together, off the critical path of phase 2.
-        if (!skeleton) {
-            constexpr int kPer = kTL / kTT;
-            unsigned cube[kPer];
-            if (cnt == (uint32_t)kTL) {
-#pragma unroll
-                for (int k = 0; k < kPer; k++) {
-                    const int i = tid + k * kTT;
-                    float x, y, z;
-                    load_pt(i, x, y, z);
-                    const CoxaPoint p = to_coxa_frame(L, x, y, z);
-                    cube[k] = tex3D<unsigned char>(vol.tex, fmaf(p.x, vol.inv_cell, vol.o),
-                                                   fmaf(p.y, vol.inv_cell, vol.oy), fmaf(p.z, vol.inv_cell, vol.o));
-                    store3(i, p.x, p.y, p.z);
-                }
-#pragma unroll
-                for (int k = 0; k < kPer; k++) flag[tid + k * kTT] = (uint8_t)cube[k];
-            } else {
-#pragma unroll 1
-                for (int i = tid; i < (int)cnt; i += kTT) {
-                    float x, y, z;
-                    load_pt(i, x, y, z);
-                    const CoxaPoint p = to_coxa_frame(L, x, y, z);
-                    flag[i] = (uint8_t)tex3D<unsigned char>(vol.tex, fmaf(p.x, vol.inv_cell, vol.o),
-                                                            fmaf(p.y, vol.inv_cell, vol.oy), fmaf(p.z, vol.inv_cell, vol.o));
-                    store3(i, p.x, p.y, p.z);
-                }
-            }
-        }
-        // Phase 2: the chosen solution of each point, two points per trip (their plane-atlas
-        // fetches overlap).  A parked point leaves its slot alone: the redo rewrites it in global
-        // memory after the tile's store.
+        // a parked point leaves its slot alone (the input point): the redo rewrites it in global
+        // memory after the tile's store
         auto store_pt = [&](int i, const DistResult& r) {
-            store3(i, r.dx, r.dy, r.dz);
+            if (SOA) {
+                in[i] = r.dx, in[kTL + i] = r.dy, in[2 * kTL + i] = r.dz;
+            } else {
+                in[3 * i] = r.dx, in[3 * i + 1] = r.dy, in[3 * i + 2] = r.dz;
+            }
             flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
         };
-        auto park = [&](int i, int why, unsigned cube) {
-            const uint32_t entry = (it << 15) | ((cube & 31u) << 10) | (uint32_t)i;
-            if (why == 2 && ra.push(S.ring_a, &S.cnt[0][rot], entry)) return;
-            if (why == 1 && rb.push(S.ring_b, &S.cnt[1][rot], entry)) return;
-            if (rc.push(S.ring_c, &S.cnt[2][rot], entry)) return;
+        auto park = [&](int i, int why, unsigned word) {
+            const uint32_t entry = (it << 15) | ((word & 31u) << 10) | (uint32_t)i;
+            if (why == 3 && rp.push(S.ring_p, &S.cnt[0][rot], entry)) return;
+            if (why == 1 && rb.push(S.ring_b, &S.cnt[2][rot], entry)) return;
+            if (rc.push(S.ring_c, &S.cnt[3][rot], entry)) return;
             tile_point_full<MODE, SOA>(L, S.table, in, flag, i);
         };
-#pragma unroll 1
-        for (int i = tid; i < (skeleton ? 0 : (int)cnt); i += 2 * kTT) {
-            const bool has_j = i + kTT < (int)cnt;
-            const int j = has_j ? i + kTT : i;
-            CoxaPoint pi, pj;
-            load_pt(i, pi.x, pi.y, pi.z);
-            load_pt(j, pj.x, pj.y, pj.z);  // both loads before any store: the tile is updated in place
-            const unsigned ci = flag[i], cj = flag[j];
-            DistResult ri, rj;
-            const ChoiceFront fi = dist_choice_front<true>(L, sols, ci, atlas, pi);
-            const ChoiceFront fj = dist_choice_front<true>(L, sols, cj, atlas, pj);
-            // the limit-plane rule needs a valid plane point: skipped when no lane of the warp has
-            // one in this trip (full tiles: the warp is converged here)
-            int si, sj;
-            if (cnt != (uint32_t)kTL || __any_sync(0xffffffffu, ((fi.la | fj.la) & 0x40u) != 0u)) {
-                si = dist_choice_back<true>(L, sols, ci, fi, S.winners, pi, &ri);
-                sj = dist_choice_back<true>(L, sols, cj, fj, S.winners, pj, &rj);
-            } else {
-                si = dist_choice_back<false>(L, sols, ci, fi, S.winners, pi, &ri);
-                sj = dist_choice_back<false>(L, sols, cj, fj, S.winners, pj, &rj);
+        auto fetch = [&](const CoxaPoint& p) -> unsigned {
+            return tex3D<unsigned short>(vol.tex, fmaf(p.x, vol.inv_cell, vol.o), fmaf(p.y, vol.inv_cell, vol.oy),
+                                         fmaf(p.z, vol.inv_cell, vol.o));
+        };
+        if (skeleton) {
+        } else if (cnt == (uint32_t)kTL) {
+            // every texel of the thread is requested before the first one is consumed
+            CoxaPoint p[kPer];
+            unsigned w[kPer];
+#pragma unroll
+            for (int k = 0; k < kPer; k++) {
+                float x, y, z;
+                load_pt(tid + k * kTT, x, y, z);
+                p[k] = to_coxa_frame(L, x, y, z);
+                w[k] = fetch(p[k]);
             }
-            if (si == 0) store_pt(i, ri);
-            if ((sj == 0) & has_j) store_pt(j, rj);
-            if (si != 0) park(i, si, ci);
-            if ((sj != 0) & has_j) park(j, sj, cj);
+#pragma unroll
+            for (int g = 0; g < kPer; g += LRM_T0_GROUP) {
+                // the limit-plane rule needs a valid plane point (bit 6 of the label): skipped when
+                // no lane of the warp has one in this group (full tiles: the warp is converged here)
+                unsigned any = 0u;
+#pragma unroll
+                for (int k = g; k < g + LRM_T0_GROUP; k++) any |= w[k];
+                DistResult r[LRM_T0_GROUP];
+                int st[LRM_T0_GROUP];
+                if (__any_sync(0xffffffffu, (any & 0x4000u) != 0u)) {
+#pragma unroll
+                    for (int k = 0; k < LRM_T0_GROUP; k++)
+                        st[k] = dist_choice_label<true>(L, sols, w[g + k], S.winners, p[g + k], &r[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < LRM_T0_GROUP; k++)
+                        st[k] = dist_choice_label<false>(L, sols, w[g + k], S.winners, p[g + k], &r[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < LRM_T0_GROUP; k++)
+                    if (st[k] == 0) store_pt(tid + (g + k) * kTT, r[k]);
+#pragma unroll
+                for (int k = 0; k < LRM_T0_GROUP; k++)
+                    if (st[k] != 0) park(tid + (g + k) * kTT, st[k], w[g + k]);
+            }
+        } else {
+#pragma unroll 1
+            for (int i = tid; i < (int)cnt; i += kTT) {
+                float x, y, z;
+                load_pt(i, x, y, z);
+                const CoxaPoint p = to_coxa_frame(L, x, y, z);
+                const unsigned w = fetch(p);
+                DistResult r;
+                const int st = dist_choice_label<true>(L, sols, w, S.winners, p, &r);
+                if (st == 0) store_pt(i, r);
+                else park(i, st, w);
+            }
         }
 
         bulk::fence_proxy_async();
         if (tid == 0) {
             bulk::wait_group<0>();  // every committed store has COMPLETED: parked points of those tiles may be redone
             const int rot_next = rot == 2 ? 0 : rot + 1;
-            S.cnt[0][rot_next] = 0, S.cnt[1][rot_next] = 0, S.cnt[2][rot_next] = 0;
+            S.cnt[0][rot_next] = 0, S.cnt[1][rot_next] = 0, S.cnt[2][rot_next] = 0, S.cnt[3][rot_next] = 0;
         }
         __syncthreads();
         if (tid == 0) {
@@ -758,28 +787,44 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
     {
         const int rot_prev = rot == 0 ? 2 : rot - 1;
         if (it) {
-            ra.advance(S.cnt[0][rot_prev]);
-            rb.advance(S.cnt[1][rot_prev]);
-            rc.advance(S.cnt[2][rot_prev]);
+            rp.advance(S.cnt[0][rot_prev]);
+            ra.advance(S.cnt[1][rot_prev]);
+            rb.advance(S.cnt[2][rot_prev]);
+            rc.advance(S.cnt[3][rot_prev]);
         }
+        // rings A and C first: they are final.  Then P and B, whose hand-overs go to cnt[1][rot] /
+        // cnt[3][rot] (zero so far: nothing was pushed in an iteration that did not run)
 #pragma unroll 1
         for (; ra.head < ra.base; ra.head += kTT)
             if (ra.head + tid < ra.base) do_a(S.ring_a[(ra.head + tid) & (kRingA - 1)]);
 #pragma unroll 1
         for (; rc.head < rc.base; rc.head += kTT)
             if (rc.head + tid < rc.base) do_c(S.ring_c[(rc.head + tid) & (kRingC - 1)]);
-        // ring C is empty now; what ring B's drain cannot decide goes to cnt[2][rot] (zero so far)
+        ra.head = ra.base, ra.room = kRingA;
         rc.head = rc.base, rc.room = kRingC;
         __syncthreads();
+        // each drain round of P / B hands on at most kTT entries: rings A / C (>= 2 kTT) take them,
+        // and are emptied again before the next round
 #pragma unroll 1
-        for (; rb.head < rb.base; rb.head += kTT)
+        for (; rp.head < rp.base; rp.head += kTT) {
+            if (rp.head + tid < rp.base) do_p(S.ring_p[(rp.head + tid) & (kRingP - 1)]);
+            __syncthreads();
+            const unsigned late = S.cnt[1][rot];
+            __syncthreads();
+            if (tid == 0) S.cnt[1][rot] = 0;
+            if (tid < (int)late) do_a(S.ring_a[(ra.base + tid) & (kRingA - 1)]);
+            __syncthreads();
+        }
+#pragma unroll 1
+        for (; rb.head < rb.base; rb.head += kTT) {
             if (rb.head + tid < rb.base) do_b(S.ring_b[(rb.head + tid) & (kRingB - 1)]);
-        __syncthreads();
-        const unsigned late = S.cnt[2][rot];
-        rc.base += late < rc.room ? late : rc.room;
-#pragma unroll 1
-        for (; rc.head < rc.base; rc.head += kTT)
-            if (rc.head + tid < rc.base) do_c(S.ring_c[(rc.head + tid) & (kRingC - 1)]);
+            __syncthreads();
+            const unsigned late = S.cnt[3][rot];
+            __syncthreads();
+            if (tid == 0) S.cnt[3][rot] = 0;
+            if (tid < (int)late) do_c(S.ring_c[(rc.base + tid) & (kRingC - 1)]);
+            __syncthreads();
+        }
     }
 
     // the last n % 16 points bypass the bulk engine
@@ -933,12 +978,14 @@ cudaError_t launch_stream_impl(const LegPlan& plan, const FastTables& ft, const 
     return cudaGetLastError();
 }
 
-// LRM_TIER_CHUNK (log2 of the tiles per chunk, default 3): measurement knob
-int tier_chunk_shift_max() {
-    const char* e = getenv("LRM_TIER_CHUNK");
-    const int v = e ? atoi(e) : 3;
-    return v < 0 ? 0 : (v > 8 ? 8 : v);
-}
+// Options (lrm_set_option): log2 of the tiles per chunk of the tiered sweep, and which sweep large
+// distance calls take (0 = always the two-tier sweep, 1 = always the tiered sweep, 2 = decided per
+// launch by the coherence probe).
+std::atomic<int> g_tier_chunk_shift{3};
+std::atomic<int> g_sweep_mode{2};
+#ifdef LRM_ENABLE_SKELETON
+std::atomic<int> g_skeleton{0};
+#endif
 
 template <int MODE, bool SOA>
 cudaError_t launch_tier_impl(const LegPlan& plan, const FastTables& ft, const AtlasView& atlas,
@@ -965,18 +1012,18 @@ cudaError_t launch_tier_impl(const LegPlan& plan, const FastTables& ft, const At
     if (grid == 0) grid = 1;
     // chunks of up to 8 consecutive tiles per CTA, fewer on small sweeps (keep >= 16 chunks per CTA)
     int kshift = 0;
-    while (kshift < tier_chunk_shift_max() && (tiles >> (kshift + 1)) >= grid * 16) kshift++;
+    const int kshift_max = g_tier_chunk_shift.load(std::memory_order_relaxed);
+    while (kshift < kshift_max && (tiles >> (kshift + 1)) >= grid * 16) kshift++;
 #ifdef LRM_ENABLE_SKELETON  // measurement builds only (LRM_NVCC_EXTRA=-DLRM_ENABLE_SKELETON): results are garbage
-    if (const char* sk = getenv("LRM_TIER_SKELETON"))
-        if (sk[0] == '1') kshift |= 0x100;
+    if (g_skeleton.load()) kshift |= 0x100;
 #endif
     const RedoIo io{ix, iy, iz, ox, oy, oz, flag};
     kernel<<<(unsigned)grid, kTT, smem, stream>>>(plan, ft, atlas, vol, io, n, kshift, gate, gate_want);
     return cudaGetLastError();
 }
 
-// Which sweep suits the input?  The tiered sweep adds a fetch from the 3-D choice volume (tens of
-// MB): a win when neighbouring points of the array are neighbours in space (lattices, scan lines,
+// Which sweep suits the input?  The tiered sweep adds a fetch from the 3-D choice volume (hundreds
+// of MB): a win when neighbouring points of the array are neighbours in space (lattices, scan lines,
 // sorted clouds: the fetches of a warp share a few sectors), a loss on shuffled clouds, where every
 // fetch is its own DRAM sector.  256 pairs of consecutive points spread over the array vote; the
 // verdict goes to a device word that both sweeps read first — the one that is not chosen returns
@@ -1013,26 +1060,19 @@ int* next_verdict_word() {
     return p + (next.fetch_add(1u, std::memory_order_relaxed) % kWords);
 }
 
-// LRM_CHOICE_VOLUME: 0 = always the two-tier sweep (dist_fast + full evaluation), 1 = always the
-// tiered sweep, unset = decided per launch by the coherence probe.  Read per launch: tools switch
-// it inside one process.
-int choice_volume_mode() {
-    const char* e = getenv("LRM_CHOICE_VOLUME");
-    if (e && e[0] == '0') return 0;
-    if (e && e[0] == '1') return 1;
-    return 2;
-}
-
-// LRM_ATLAS_TEX=0 selects plain loads from the blocked copy of the atlas instead of the texture
-// unit (same cells, same results; kept for A/B measurements)
-bool atlas_through_texture() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("LRM_ATLAS_TEX");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v != 0;
-}
+// A leased set of certified tables, released (and its use recorded on the stream) when the
+// launcher returns — after its last launch.
+struct Tables {
+    TableLease lease;
+    cudaStream_t stream;
+    AtlasView atlas{};
+    FastTables ft{};
+    explicit Tables(cudaStream_t s) : stream(s) {}
+    cudaError_t acquire(const LegPlan& plan) { return acquire_tables(plan, stream, &atlas, &ft, &lease); }
+    ~Tables() { release_tables(&lease, stream); }
+    Tables(const Tables&) = delete;
+    Tables& operator=(const Tables&) = delete;
+};
 
 // reach-only never cross-validates, so only the distance modes have a generic instantiation
 template <int MODE, bool SOA>
@@ -1042,33 +1082,27 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
     AtlasView none{};
     static const FastTables no_tables{};
     const bool big = (n_call > n ? n_call : n) >= g_fast_min_points.load(std::memory_order_relaxed);
+    const int vmode = g_sweep_mode.load(std::memory_order_relaxed);
     if (MODE == kModeReach) {
         // large reach-only sweeps read the valid bit of the plane atlas instead of testing circles
         if (big && !plan.generic) {
-            AtlasView atlas;
-            cudaError_t e = get_plane_atlas(plan, stream, &atlas, nullptr);
+            Tables T(stream);
+            cudaError_t e = T.acquire(plan);
             if (e != cudaSuccess) return e;
-            if (atlas_through_texture()) {
-                // reach bits of the choice volume (built in the background on first request); as for
-                // the distance sweeps, only for inputs the coherence probe finds spatially ordered
-                FastTables ft;
-                const int vmode = choice_volume_mode();
-                VolumeView vol{};
-                if (vmode != 0 && get_plane_atlas(plan, stream, &atlas, &ft) == cudaSuccess &&
-                    get_choice_volume(plan, stream, &vol, /*wait=*/vmode == 1) == cudaSuccess) {
-                    int* verdict = vmode == 2 ? next_verdict_word() : nullptr;
-                    if (verdict != nullptr)
-                        coherence_probe_kernel<SOA><<<1, 256, 0, stream>>>(ix, iy, iz, n, 2.0f / vol.inv_cell, verdict);
-                    if (vmode == 1 || verdict != nullptr)
-                        return launch_stream_impl<MODE, SOA, false, MODE == kModeReach, true>(
-                            plan, no_tables, atlas, ix, iy, iz, ox, oy, oz, flag, n, stream, verdict, -1, &vol);
-                }
-                (void)cudaGetLastError();
-                return launch_stream_impl<MODE, SOA, false, MODE == kModeReach, true>(
-                    plan, no_tables, atlas, ix, iy, iz, ox, oy, oz, flag, n, stream);
+            // reach bits of the choice volume (built in the background on first request); as for
+            // the distance sweeps, only for inputs the coherence probe finds spatially ordered
+            VolumeView vol{};
+            if (vmode != 0 && get_choice_volume(T.lease, stream, &vol, /*wait=*/vmode == 1) == cudaSuccess) {
+                int* verdict = vmode == 2 ? next_verdict_word() : nullptr;
+                if (verdict != nullptr)
+                    coherence_probe_kernel<SOA><<<1, 256, 0, stream>>>(ix, iy, iz, n, 2.0f / vol.inv_cell, verdict);
+                if (vmode == 1 || verdict != nullptr)
+                    return launch_stream_impl<MODE, SOA, false, MODE == kModeReach, true>(
+                        plan, no_tables, T.atlas, ix, iy, iz, ox, oy, oz, flag, n, stream, verdict, -1, &vol);
             }
-            return launch_stream_impl<MODE, SOA, false, MODE == kModeReach, false>(
-                plan, no_tables, atlas, ix, iy, iz, ox, oy, oz, flag, n, stream);
+            (void)cudaGetLastError();
+            return launch_stream_impl<MODE, SOA, false, MODE == kModeReach, true>(
+                plan, no_tables, T.atlas, ix, iy, iz, ox, oy, oz, flag, n, stream);
         }
         return launch_stream_impl<MODE, SOA, false, false, false>(plan, no_tables, none, ix, iy, iz, ox, oy,
                                                                   oz, flag, n, stream);
@@ -1080,38 +1114,33 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
     // the atlas pays for itself (16 Mi probes) only on large sweeps, or once it is cached; ring
     // entries hold a 22-bit per-CTA iteration count (n / (kTile * grid) is far below that)
     if (big && n / kTile / (size_t)sm_count() < (size_t(1) << 21)) {
-        AtlasView atlas;
-        FastTables ft;
-        cudaError_t e = get_plane_atlas(plan, stream, &atlas, &ft);
+        Tables T(stream);
+        cudaError_t e = T.acquire(plan);
         if (e != cudaSuccess) return e;
         if constexpr (kDist) {
             // ring entries of the tiered sweep hold a 17-bit per-CTA iteration count
-            const int vmode = choice_volume_mode();
-            if (atlas_through_texture() && vmode != 0 && ft.both_unsat == 0 &&
+            if (vmode != 0 && T.ft.both_unsat == 0 &&
                 n / kTL / (size_t)sm_count() < (size_t(1) << (kEntryIterBits - 1)) && n < (size_t(1) << 40)) {
                 VolumeView vol;
-                e = get_choice_volume(plan, stream, &vol, /*wait=*/vmode == 1);
+                e = get_choice_volume(T.lease, stream, &vol, /*wait=*/vmode == 1);
                 int* verdict = (e == cudaSuccess && vmode == 2) ? next_verdict_word() : nullptr;
                 if (e == cudaSuccess && vmode == 2 && verdict != nullptr) {
                     // "near" = within two cubes of the volume
                     coherence_probe_kernel<SOA><<<1, 256, 0, stream>>>(ix, iy, iz, n, 2.0f / vol.inv_cell, verdict);
-                    e = launch_tier_impl<MODE, SOA>(plan, ft, atlas, vol, ix, iy, iz, ox, oy, oz, flag, n, stream,
+                    e = launch_tier_impl<MODE, SOA>(plan, T.ft, T.atlas, vol, ix, iy, iz, ox, oy, oz, flag, n, stream,
                                                     verdict, 1);
                     if (e != cudaSuccess) return e;
-                    return launch_stream_impl<MODE, SOA, false, kDist, kDist>(plan, ft, atlas, ix, iy, iz, ox, oy,
+                    return launch_stream_impl<MODE, SOA, false, kDist, kDist>(plan, T.ft, T.atlas, ix, iy, iz, ox, oy,
                                                                               oz, flag, n, stream, verdict, 0);
                 }
                 if (e == cudaSuccess)
-                    return launch_tier_impl<MODE, SOA>(plan, ft, atlas, vol, ix, iy, iz, ox, oy, oz, flag, n, stream,
-                                                       nullptr, 0);
+                    return launch_tier_impl<MODE, SOA>(plan, T.ft, T.atlas, vol, ix, iy, iz, ox, oy, oz, flag, n,
+                                                       stream, nullptr, 0);
                 (void)cudaGetLastError();  // volume still being built, or no memory for it: the two-tier sweep gives the same bits
             }
         }
-        if (atlas_through_texture())
-            return launch_stream_impl<MODE, SOA, false, kDist, kDist>(plan, ft, atlas, ix, iy, iz, ox, oy, oz,
-                                                                      flag, n, stream);
-        return launch_stream_impl<MODE, SOA, false, kDist, false>(plan, ft, atlas, ix, iy, iz, ox, oy, oz, flag,
-                                                                  n, stream);
+        return launch_stream_impl<MODE, SOA, false, kDist, kDist>(plan, T.ft, T.atlas, ix, iy, iz, ox, oy, oz,
+                                                                  flag, n, stream);
     }
     return launch_stream_impl<MODE, SOA, false, false, false>(plan, no_tables, none, ix, iy, iz, ox, oy, oz,
                                                               flag, n, stream);
@@ -1138,6 +1167,16 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 }  // namespace
 
 size_t set_fast_path_min_points(size_t n) { return g_fast_min_points.exchange(n); }
+int set_sweep_mode(int mode) { return g_sweep_mode.exchange(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); }
+int set_tier_chunk_shift(int shift) { return g_tier_chunk_shift.exchange(shift < 0 ? 0 : (shift > 8 ? 8 : shift)); }
+int set_skeleton(int on) {
+#ifdef LRM_ENABLE_SKELETON
+    return g_skeleton.exchange(on);
+#else
+    (void)on;
+    return -1;
+#endif
+}
 
 cudaError_t launch_one_leg_aos(int mode, const LegPlan& plan, const float* xyz, float* out_vec,
                                uint8_t* flag, size_t n, cudaStream_t stream, size_t n_call) {

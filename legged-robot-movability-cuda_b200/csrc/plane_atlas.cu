@@ -8,9 +8,10 @@
 // cannot certify.  16 MiB per (leg, orientation); a small per-device LRU keeps the last few.
 #include <cuda_runtime.h>
 
-#include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "kernels.h"
 #include "leg_math.cuh"
@@ -49,7 +50,7 @@ __global__ void atlas_build_kernel(const __grid_constant__ LegPlan L, unsigned c
 // cubes of the other blocks — the shells around the decision surfaces.
 __global__ void __launch_bounds__(128)
     volume_coarse_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
-                         unsigned char* __restrict__ linear, unsigned char* __restrict__ block_done, int dim,
+                         unsigned short* __restrict__ linear, unsigned char* __restrict__ block_done, int dim,
                          float cell) {
     __shared__ SectorTable table;
     fill_sector_table(L, &table, threadIdx.x, blockDim.x);
@@ -61,16 +62,14 @@ __global__ void __launch_bounds__(128)
         const int bx = (int)(i % bd), by = (int)((i / bd) % bd), bz = (int)(i / ((size_t)bd * bd));
         const float x0 = ((float)(4 * bx) - half) * cell, y0 = ((float)(4 * by) - half - kVolShiftY) * cell,
                     z0 = ((float)(4 * bz) - half) * cell;
-        const CellFirst f = choice_cell_first(L, table, FT, x0, y0, z0, 4.f * cell);
-        const bool done = f.byte != 0u && !f.refine && f.reach != 0u && !f.reach_refine;
-        block_done[i] = done ? 1 : 0;
-        if (done) {
-            const unsigned b = f.byte | f.reach;
-            const uint32_t four = b * 0x01010101u;  // four cubes along x, 4-byte aligned (dim % 4 == 0)
+        const unsigned w = coarse_block_word(L, table, FT, x0, y0, z0, 4.f * cell);
+        block_done[i] = w != 0u ? 1 : 0;
+        if (w != 0u) {
+            const unsigned long long four = (unsigned long long)w * 0x0001000100010001ull;  // four texels along x (dim % 4 == 0)
             for (int dz = 0; dz < 4; dz++)
                 for (int dy = 0; dy < 4; dy++)
-                    *reinterpret_cast<uint32_t*>(linear + ((size_t)(4 * bz + dz) * dim + (size_t)(4 * by + dy)) * dim +
-                                                 4 * bx) = four;
+                    *reinterpret_cast<unsigned long long*>(
+                        linear + ((size_t)(4 * bz + dz) * dim + (size_t)(4 * by + dy)) * dim + 4 * bx) = four;
         }
     }
 }
@@ -80,8 +79,8 @@ __global__ void __launch_bounds__(128)
 // per warp), so the warp refines them one after the other with all 32 lanes, two sub-cubes each,
 // instead of leaving 29 lanes idle while three of them run 64 probes.
 __global__ void __launch_bounds__(128)
-    volume_build_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
-                        unsigned char* __restrict__ linear, const unsigned char* __restrict__ block_done, int dim,
+    volume_build_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT, const AtlasView atlas,
+                        unsigned short* __restrict__ linear, const unsigned char* __restrict__ block_done, int dim,
                         float cell) {
     __shared__ SectorTable table;
     fill_sector_table(L, &table, threadIdx.x, blockDim.x);
@@ -127,13 +126,37 @@ __global__ void __launch_bounds__(128)
             const bool all = __all_sync(0xffffffffu, ok);
             if (lane == src && !all) f.reach = 0u;
         }
-        if (live) linear[i] = (unsigned char)(f.byte | f.reach);
+        if (live) {
+            // plane label of the chosen solution (tier 0 of the sweep): the atlas cells under the
+            // cube's plane rectangle all carry one certified label
+            unsigned hi = 0u;
+            if (f.byte & kVolPure) {
+                float side;
+                const CoxaPoint c = cube_centre(x0, y0, z0, cell, &side);
+                hi = cube_plane_scan(atlas, solution_plane_x(L, c, (f.byte & 1u) != 0u), c.z, side);
+            }
+            linear[i] = (unsigned short)(f.byte | f.reach | (hi << 8));
+        }
     }
 }
 
+// ---- cache ---------------------------------------------------------------------------------------
+// Per device, a small LRU of (plan -> atlas, yaw tables, choice volume).  Nothing here makes a
+// device-pointer call synchronous once a plan's tables exist, and a rebuild is ordered by events:
+//   * a caller LEASES an entry (acquire_tables): the entry is pinned until release_tables, which
+//     records an event on the caller's stream after its launches — eviction never touches a pinned
+//     entry, so a second host thread cannot rebuild the tables between a lookup and the launch
+//     that uses them;
+//   * an entry's buffers are rewritten (eviction) only after the rebuilding stream has been made to
+//     wait for every recorded use (cudaStreamWaitEvent; a device-wide wait only if more streams than
+//     kUseSlots used the entry);
+//   * a freshly built atlas is published by a `ready` event that other streams wait for on the
+//     device; the host does not wait.
+constexpr int kUseSlots = 4;
 struct Entry {
     bool used = false;
     int device = -1;
+    int pins = 0;
     unsigned long long stamp = 0;
     LegPlan plan;
     unsigned char* cells = nullptr;   // 8 x 4 blocked
@@ -141,6 +164,12 @@ struct Entry {
     cudaArray_t array = nullptr;
     cudaTextureObject_t tex = 0;
     FastTables tables;  // yaw-sector table of the same plan (host-built, ~0.5 ms: cached with the atlas)
+    cudaEvent_t ready = nullptr;      // atlas build complete
+    cudaStream_t ready_stream = nullptr;
+    cudaStream_t use_stream[kUseSlots] = {};
+    cudaEvent_t use_done[kUseSlots] = {};
+    bool use_valid[kUseSlots] = {};
+    bool use_overflow = false;        // more distinct streams than slots since the last rebuild
     // choice volume (built on first request, see get_choice_volume)
     cudaArray_t vol_array = nullptr;
     cudaTextureObject_t vol_tex = 0;
@@ -151,7 +180,8 @@ struct Entry {
     bool vol_building = false;
     cudaStream_t vol_stream = nullptr;
     cudaEvent_t vol_done = nullptr;
-    unsigned char* vol_linear = nullptr;  // staging copy, freed once the build has finished
+    unsigned short* vol_linear = nullptr;  // staging copy, freed once the build has finished
+    float vol_build_ms = 0.f;              // wall time of the last build (host clock around the wait), diagnostics
 };
 // a build in flight must finish before its buffers or its plan's atlas go away
 void settle_volume(Entry* c) {
@@ -168,13 +198,21 @@ void release_volume(Entry* c) {
     if (c->vol_array) cudaFreeArray(c->vol_array);
     c->vol_tex = 0, c->vol_array = nullptr, c->vol_ready = false, c->vol_dim = 0;
 }
-void release(Entry* c) {
-    release_volume(c);
-    if (c->tex) cudaDestroyTextureObject(c->tex);
-    if (c->array) cudaFreeArray(c->array);
-    if (c->cells) cudaFree(c->cells);
-    if (c->linear) cudaFree(c->linear);
-    c->tex = 0, c->array = nullptr, c->cells = nullptr, c->linear = nullptr;
+// every stream that used the entry must have finished with it before its buffers are rewritten:
+// ordered on the device where the uses are known, device-wide otherwise
+cudaError_t order_after_uses(Entry* c, cudaStream_t stream) {
+    if (c->use_overflow) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return e;
+    }
+    for (int k = 0; k < kUseSlots; k++)
+        if (c->use_valid[k]) {
+            cudaError_t e = cudaStreamWaitEvent(stream, c->use_done[k], 0);
+            if (e != cudaSuccess) return e;
+            c->use_valid[k] = false;
+        }
+    c->use_overflow = false;
+    return cudaSuccess;
 }
 cudaError_t allocate(Entry* c) {
     const size_t bytes = (size_t)kAtlasDim * kAtlasDim;
@@ -195,42 +233,94 @@ cudaError_t allocate(Entry* c) {
     td.filterMode = cudaFilterModePoint;
     td.readMode = cudaReadModeElementType;
     td.normalizedCoords = 0;
-    return cudaCreateTextureObject(&c->tex, &res, &td, nullptr);
+    e = cudaCreateTextureObject(&c->tex, &res, &td, nullptr);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    for (int k = 0; k < kUseSlots; k++) {
+        e = cudaEventCreateWithFlags(&c->use_done[k], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
-constexpr int kCacheEntries = 4;
-Entry g_cache[kCacheEntries];
+void release(Entry* c) {
+    release_volume(c);
+    if (c->vol_stream) cudaStreamDestroy(c->vol_stream);
+    if (c->vol_done) cudaEventDestroy(c->vol_done);
+    c->vol_stream = nullptr, c->vol_done = nullptr;
+    if (c->tex) cudaDestroyTextureObject(c->tex);
+    if (c->array) cudaFreeArray(c->array);
+    if (c->cells) cudaFree(c->cells);
+    if (c->linear) cudaFree(c->linear);
+    if (c->ready) cudaEventDestroy(c->ready);
+    for (int k = 0; k < kUseSlots; k++) {
+        if (c->use_done[k]) cudaEventDestroy(c->use_done[k]);
+        c->use_done[k] = nullptr, c->use_valid[k] = false;
+    }
+    c->tex = 0, c->array = nullptr, c->cells = nullptr, c->linear = nullptr, c->ready = nullptr;
+}
+
+// Entries never move (leases hold pointers) and belong to ONE device for life: kCacheEntries per
+// device (a hexapod sweeping its six legs in turn keeps all six), plus spill-over entries when
+// every entry of a device is pinned at once.
+constexpr int kCacheEntries = 8;
+constexpr int kMaxDevices = 64;
+std::vector<Entry*> g_cache[kMaxDevices];
 unsigned long long g_clock = 0;
 std::mutex g_mutex;
+std::atomic<int> g_vol_dim{512};
+std::atomic<float> g_vol_cell{3.0f};
+std::atomic<unsigned long long> g_builds{0};  // atlas builds since the library was loaded (diagnostics / tests)
+
+void fill_view(const Entry* hit, AtlasView* view) {
+    view->cells = hit->cells;
+    view->tex = hit->tex;
+    view->inv_cell = 1.0f / kAtlasCell;
+    view->ox = view->oy = -kAtlasOrigin / kAtlasCell;
+    view->w = kAtlasDim, view->h = kAtlasDim;
+}
 
 }  // namespace
 
-cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView* view, FastTables* tables) {
+// 3 mm cubes over +-768 mm: 268 MB per cached plan (16-bit texels).  Measured on the bench lattice
+// with 8-bit texels: 4 mm / 384 is 2 % slower, 2.5 mm / 640 1 % faster.
+int set_choice_volume_shape(float cell_mm, int dim) {
+    if (!(cell_mm >= 0.5f && cell_mm <= 64.f) || dim < 16 || dim > 1024 || dim % 4 != 0) return -1;
+    g_vol_cell.store(cell_mm), g_vol_dim.store(dim);
+    return 0;
+}
+void get_choice_volume_shape(float* cell_mm, int* dim) { *cell_mm = g_vol_cell.load(), *dim = g_vol_dim.load(); }
+unsigned long long table_builds() { return g_builds.load(); }
+
+cudaError_t acquire_tables(const LegPlan& plan, cudaStream_t stream, AtlasView* view, FastTables* tables,
+                           TableLease* lease) {
+    lease->entry = nullptr;
     std::lock_guard<std::mutex> lock(g_mutex);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    std::vector<Entry*>& cache = g_cache[dev];
     Entry* hit = nullptr;
-    Entry* victim = &g_cache[0];
-    for (Entry& c : g_cache) {
-        if (c.used && c.device == dev && std::memcmp(&c.plan, &plan, sizeof(LegPlan)) == 0) hit = &c;
-        if (!c.used || c.stamp < victim->stamp || (victim->used && !c.used)) victim = &c;
-    }
+    for (Entry* c : cache)
+        if (c->used && std::memcmp(&c->plan, &plan, sizeof(LegPlan)) == 0) hit = c;
     if (!hit) {
-        for (Entry& c : g_cache)
-            if (!c.used) {
-                victim = &c;
-                break;
-            }
-        if (victim->used && victim->device != dev) {
-            // evicting another device's atlas: free it on that device
-            int cur = dev;
-            cudaSetDevice(victim->device);
-            release(victim);
-            cudaSetDevice(cur);
-        } else if (victim->used) {
-            // reuse the buffers: earlier kernels on other streams may still read them
-            e = cudaDeviceSynchronize();
-            if (e != cudaSuccess) return e;
+        // victim: an unused entry, else the least recently used unpinned one, else a new entry
+        Entry* victim = nullptr;
+        for (Entry* c : cache)
+            if (!c->used && c->pins == 0) victim = c;
+        if (!victim && (int)cache.size() < kCacheEntries) {
+            victim = new Entry();
+            victim->device = dev;
+            cache.push_back(victim);
+        }
+        if (!victim)
+            for (Entry* c : cache)
+                if (c->pins == 0 && (!victim || c->stamp < victim->stamp)) victim = c;
+        if (!victim) {  // everything pinned by concurrent callers: spill over
+            victim = new Entry();
+            victim->device = dev;
+            cache.push_back(victim);
         }
         victim->used = false;
         settle_volume(victim);
@@ -242,6 +332,8 @@ cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView*
                 return e;
             }
         }
+        e = order_after_uses(victim, stream);
+        if (e != cudaSuccess) return e;
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         atlas_build_kernel<<<sms * 8, 256, 0, stream>>>(plan, victim->cells, victim->linear, kAtlasDim,
@@ -251,61 +343,68 @@ cudaError_t get_plane_atlas(const LegPlan& plan, cudaStream_t stream, AtlasView*
         e = cudaMemcpy2DToArrayAsync(victim->array, 0, 0, victim->linear, kAtlasDim, kAtlasDim, kAtlasDim,
                                      cudaMemcpyDeviceToDevice, stream);
         if (e != cudaSuccess) return e;
-        // other streams may use this entry next: make the build visible device-wide
-        e = cudaStreamSynchronize(stream);
+        // other streams wait for this event on the device; the host does not wait
+        e = cudaEventRecord(victim->ready, stream);
         if (e != cudaSuccess) return e;
+        victim->ready_stream = stream;
         build_fast_tables(plan, &victim->tables);
         victim->used = true;
-        victim->device = dev;
         std::memcpy(&victim->plan, &plan, sizeof(LegPlan));
+        g_builds.fetch_add(1);
         hit = victim;
     }
+    if (hit->ready_stream != stream) {
+        e = cudaStreamWaitEvent(stream, hit->ready, 0);
+        if (e != cudaSuccess) return e;
+    }
     hit->stamp = ++g_clock;
+    hit->pins++;
+    lease->entry = hit;
     if (tables) *tables = hit->tables;
-    view->cells = hit->cells;
-    view->tex = hit->tex;
-    view->inv_cell = 1.0f / kAtlasCell;
-    view->ox = view->oy = -kAtlasOrigin / kAtlasCell;
-    view->w = kAtlasDim, view->h = kAtlasDim;
+    fill_view(hit, view);
     return cudaSuccess;
 }
 
-// LRM_VOL_CELL (mm, default 3) / LRM_VOL_DIM (cubes per side, default 512): measurement knobs.
-// 3 mm cubes over +-768 mm: 134 MB per cached plan; 4 mm / 384 (57 MB) is 2 % slower on the bench
-// lattice, 2.5 mm / 640 (262 MB) 1 % faster.
-void volume_shape(int* dim, float* cell) {
-    static int d = 0;
-    static float c = 0.f;
-    if (d == 0) {
-        const char* ec = getenv("LRM_VOL_CELL");
-        const char* ed = getenv("LRM_VOL_DIM");
-        c = ec ? (float)atof(ec) : 3.0f;
-        if (!(c >= 0.5f && c <= 64.f)) c = 3.0f;
-        d = ed ? atoi(ed) : 512;
-        if (d < 16 || d > 1024) d = 512;
+void release_tables(TableLease* lease, cudaStream_t stream) {
+    Entry* c = static_cast<Entry*>(lease->entry);
+    if (!c) return;
+    lease->entry = nullptr;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    // remember that `stream` used the entry up to here
+    int slot = -1;
+    for (int k = 0; k < kUseSlots; k++)
+        if (c->use_valid[k] && c->use_stream[k] == stream) slot = k;
+    if (slot < 0)
+        for (int k = 0; k < kUseSlots; k++)
+            if (!c->use_valid[k]) slot = k;
+    if (slot < 0 || cudaEventRecord(c->use_done[slot], stream) != cudaSuccess) {
+        c->use_overflow = true;
+        (void)cudaGetLastError();
+    } else {
+        c->use_stream[slot] = stream, c->use_valid[slot] = true;
     }
-    *dim = d, *cell = c;
+    c->pins--;
 }
 
 // wait = false: a volume that is not built yet is built in the BACKGROUND, on the entry's own
 // stream, and cudaErrorNotReady is returned — the caller runs the two-tier sweep meanwhile (same
-// results, bit for bit), so a one-off call never waits ~10 ms for a table it would use once;
-// calls that come after the build has finished get the volume.  wait = true blocks until it is there.
-cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeView* view, bool wait) {
-    (void)stream;
+// results, bit for bit), so a one-off call never waits for a table it would use once; calls that
+// come after the build has finished get the volume.  wait = true blocks until it is there.
+cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, VolumeView* view, bool wait) {
+    Entry* hit = static_cast<Entry*>(lease.entry);
+    if (!hit) return cudaErrorInvalidValue;  // acquire_tables first
     std::lock_guard<std::mutex> lock(g_mutex);
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    Entry* hit = nullptr;
-    for (Entry& c : g_cache)
-        if (c.used && c.device == dev && std::memcmp(&c.plan, &plan, sizeof(LegPlan)) == 0) hit = &c;
-    if (!hit) return cudaErrorInvalidValue;  // get_plane_atlas first
-    int dim;
-    float cell;
-    volume_shape(&dim, &cell);
+    cudaError_t e;
+    const int dim = g_vol_dim.load();
+    const float cell = g_vol_cell.load();
+    if (hit->vol_ready && (hit->vol_dim != dim || hit->vol_cell != cell)) hit->vol_ready = false;  // shape changed
     if (!hit->vol_ready && !hit->vol_building) {
-        if (hit->vol_array && hit->vol_dim != dim) release_volume(hit);
+        if (hit->vol_array && hit->vol_dim != dim) {
+            // the old array may still be read by sweeps in flight
+            e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) return e;
+            release_volume(hit);
+        }
         if (!hit->vol_stream) {
             e = cudaStreamCreateWithFlags(&hit->vol_stream, cudaStreamNonBlocking);
             if (e != cudaSuccess) return e;
@@ -313,7 +412,7 @@ cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeVi
             if (e != cudaSuccess) return e;
         }
         if (!hit->vol_array) {
-            const cudaChannelFormatDesc fmt = cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+            const cudaChannelFormatDesc fmt = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned);
             e = cudaMalloc3DArray(&hit->vol_array, &fmt, make_cudaExtent(dim, dim, dim));
             if (e != cudaSuccess) return e;
             cudaResourceDesc res;
@@ -332,32 +431,31 @@ cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeVi
                 return e;
             }
             hit->vol_dim = dim;
-        } else {
-            // a sweep of the evicted plan may still read the array that is about to be rewritten
-            e = cudaDeviceSynchronize();
-            if (e != cudaSuccess) return e;
         }
-        const size_t bytes = (size_t)dim * dim * dim;
-        e = cudaMalloc((void**)&hit->vol_linear, bytes + bytes / 64 + 64);
+        // a sweep of the evicted plan may still read the array that is about to be rewritten, and
+        // the build reads the atlas: order the build stream behind both
+        e = order_after_uses(hit, hit->vol_stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(hit->vol_stream, hit->ready, 0);
+        if (e != cudaSuccess) return e;
+        const size_t cubes = (size_t)dim * dim * dim;
+        e = cudaMalloc((void**)&hit->vol_linear, cubes * sizeof(unsigned short) + cubes / 64 + 64);
         if (e != cudaSuccess) return e;
         int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        // the atlas build (caller's stream) has been synchronised by get_plane_atlas; the volume
-        // build only needs the plan and the host-built yaw tables
-        unsigned char* block_done = nullptr;
-        if (dim % 4 == 0) {
-            // the block map lives behind the cube bytes in the same staging allocation
-            block_done = hit->vol_linear + bytes;
-            volume_coarse_kernel<<<sms * 8, 128, 0, hit->vol_stream>>>(plan, hit->tables, hit->vol_linear, block_done,
-                                                                      dim, cell);
-        }
-        volume_build_kernel<<<sms * 16, 128, 0, hit->vol_stream>>>(plan, hit->tables, hit->vol_linear, block_done, dim,
-                                                                   cell);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, hit->device);
+        // the block map lives behind the texels in the same staging allocation
+        unsigned char* block_done = reinterpret_cast<unsigned char*>(hit->vol_linear + cubes);
+        volume_coarse_kernel<<<sms * 8, 128, 0, hit->vol_stream>>>(hit->plan, hit->tables, hit->vol_linear, block_done,
+                                                                  dim, cell);
+        AtlasView atlas{};
+        fill_view(hit, &atlas);
+        volume_build_kernel<<<sms * 16, 128, 0, hit->vol_stream>>>(hit->plan, hit->tables, atlas, hit->vol_linear,
+                                                                   block_done, dim, cell);
         e = cudaGetLastError();
         if (e == cudaSuccess) {
             cudaMemcpy3DParms cp;
             std::memset(&cp, 0, sizeof cp);
-            cp.srcPtr = make_cudaPitchedPtr(hit->vol_linear, (size_t)dim, (size_t)dim, (size_t)dim);
+            cp.srcPtr = make_cudaPitchedPtr(hit->vol_linear, (size_t)dim * sizeof(unsigned short), (size_t)dim, (size_t)dim);
             cp.dstArray = hit->vol_array;
             cp.extent = make_cudaExtent(dim, dim, dim);
             cp.kind = cudaMemcpyDeviceToDevice;
@@ -385,6 +483,7 @@ cudaError_t get_choice_volume(const LegPlan& plan, cudaStream_t stream, VolumeVi
         cudaFree(hit->vol_linear);
         hit->vol_linear = nullptr;
     }
+    (void)stream;  // vol_done has completed on the host's clock: no device-side wait needed
     view->tex = hit->vol_tex;
     view->inv_cell = 1.0f / hit->vol_cell;
     view->o = 0.5f * (float)hit->vol_dim;

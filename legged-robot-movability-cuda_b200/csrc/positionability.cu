@@ -56,6 +56,10 @@ struct SearchParams {
     float r_collide_all, r_near_any;
     uint8_t* standable;
     unsigned long long* next;   // dynamic work counter
+    // STATS instantiation only: [0] leg predicates executed (reach_offset on a live map point),
+    // [1] cylinder predicates executed, [2] leg predicates of the algorithmic count (every map point
+    // inside the reach cylinder, for every leg and orientation, no early exit)
+    unsigned long long* stats;
 };
 
 __device__ __forceinline__ float3 rotate(const float* R, float x, float y, float z) {
@@ -178,6 +182,7 @@ __global__ void target_precull_kernel(CellGrid body_grid, const float* __restric
     }
 }
 
+template <bool STATS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(const SearchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ReachPlan* plans = P.plans;
@@ -191,11 +196,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
         plans = reinterpret_cast<const ReachPlan*>(smem_raw);
     }
     const int lane = threadIdx.x & 31;
+    unsigned long long n_leg = 0, n_cyl = 0, n_alg = 0;  // STATS: identical in every lane of the warp
     while (true) {
         unsigned long long b = 0;
         if (lane == 0) b = atomicAdd(P.next, 1ull);
         b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= P.nb) return;
+        if (b >= P.nb) {
+            if (STATS && lane == 0) {
+                atomicAdd(&P.stats[0], n_leg), atomicAdd(&P.stats[1], n_cyl), atomicAdd(&P.stats[2], n_alg);
+            }
+            return;
+        }
 
         uint8_t result = 0;
         if (P.alive == nullptr || P.alive[b]) {
@@ -254,6 +265,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
                                 const float dx = T.x - B.x, dy = T.y - B.y;
                                 const bool in_body = fmaf(dx, dx, dy * dy) < O.radius_out * O.radius_out &&
                                                      dz < 250.f && dz > -110.f;
+                                if (STATS) n_cyl += __popc(__ballot_sync(0xffffffffu, ok && t.w != 0.f));
                                 return __any_sync(0xffffffffu, ok && t.w != 0.f && in_body) != 0;
                             });
                         if (!pass) leg_failed_last = false;
@@ -273,6 +285,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
                                 const float dx = T.x - B.x, dy = T.y - B.y;
                                 const bool in_reach = fmaf(dx, dx, dy * dy) < O.radius_in * O.radius_in &&
                                                       dz < O.plus_in && dz > O.minus_in;
+                                if (STATS) n_cyl += __popc(__ballot_sync(0xffffffffu, ok && t.w != 0.f));
                                 return __any_sync(0xffffffffu, ok && t.w != 0.f && in_reach) != 0;
                             });
                         if (!pass) leg_failed_last = false;
@@ -293,12 +306,40 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(cons
                                 const float3 T = rotate(O.R, t.x, t.y, t.z);
                                 const GravCtx gc{&O.grav, bx, by, bz, t.x, t.y, t.z};
                                 const bool r = ok && t.w != 0.f && reach_offset(L, T.x - B.x, T.y - B.y, T.z - B.z, &gc);
+                                if (STATS) n_leg += __popc(__ballot_sync(0xffffffffu, ok && t.w != 0.f));
                                 return __any_sync(0xffffffffu, r) != 0;
                             });
                         if (!pass) first_leg = l, leg_failed_last = true;
                     }
                 }
                 if (pass) result = (uint8_t)(o + 1);
+            }
+            if (STATS) {
+                // the algorithmic count: what a search without pruning or early exit evaluates — for
+                // every orientation, every map point inside the reach cylinder, once per leg
+                for (int o = 0; o < P.nq; o++) {
+                    const OrientConsts& O = P.orient[o];
+                    const float3 B = rotate(O.R, bx, by, bz);
+                    unsigned long long inside = 0;
+                    walk_filtered(
+                        P.map, bx, by, O.r_near, lane,
+                        [&](float x, float y, float z, float rc) {
+                            const float3 T = rotate(O.R, x, y, z);
+                            const float dz = T.z - B.z;
+                            const float dx = T.x - B.x, dy = T.y - B.y, rr = O.radius_in + rc;
+                            return fmaf(dx, dx, dy * dy) < rr * rr && dz < O.plus_in + rc && dz > O.minus_in - rc;
+                        },
+                        [&](float4 t, bool ok) {
+                            const float3 T = rotate(O.R, t.x, t.y, t.z);
+                            const float dz = T.z - B.z;
+                            const float dx = T.x - B.x, dy = T.y - B.y;
+                            const bool in_reach = fmaf(dx, dx, dy * dy) < O.radius_in * O.radius_in &&
+                                                  dz < O.plus_in && dz > O.minus_in;
+                            inside += __popc(__ballot_sync(0xffffffffu, ok && t.w != 0.f && in_reach));
+                            return false;
+                        });
+                    n_alg += inside * (unsigned long long)P.nlegs;
+                }
             }
         }
         if (lane == 0) P.standable[b] = result;
@@ -425,6 +466,11 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
         S.r_near_any = r_far + 1.f;
     }
     S.standable = p.standable, S.next = d_next;
+    S.stats = nullptr;
+    if (p.stats) {
+        if ((e = mem.alloc(&S.stats, 3)) != cudaSuccess) return finish(e);
+        cudaMemsetAsync(S.stats, 0, 3 * sizeof(unsigned long long), stream);
+    }
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -432,18 +478,27 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
     const size_t plan_bytes = plans.size() * sizeof(ReachPlan);
     S.plans_in_smem = plan_bytes <= 100 * 1024 ? 1 : 0;
     const size_t smem = S.plans_in_smem ? plan_bytes : 0;
+    auto kernel = p.stats ? positionability_kernel<true> : positionability_kernel<false>;
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(positionability_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return finish(e);
     }
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, positionability_kernel, kWarpsPerCta * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kWarpsPerCta * 32, smem);
     if (occ < 1) occ = 1;
-    positionability_kernel<<<sms * occ, kWarpsPerCta * 32, smem, stream>>>(S);
+    kernel<<<sms * occ, kWarpsPerCta * 32, smem, stream>>>(S);
     e = cudaGetLastError();
     if (e != cudaSuccess) return finish(e);
     e = finish(cudaSuccess);
     if (e != cudaSuccess) return e;
+    if (p.stats) {
+        unsigned long long h[3] = {0, 0, 0};
+        e = cudaMemcpyAsync(h, S.stats, sizeof h, cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(stream);
+        for (int i = 0; i < 3; i++) p.stats[i] = (double)h[i];
+        return e;
+    }
     // scratch (grid, plans) is freed on return: make sure the kernels are done with it
     return cudaStreamSynchronize(stream);
 }

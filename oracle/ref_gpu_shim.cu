@@ -73,15 +73,16 @@ float refgpu_oct(const float* footholds, size_t nt, const float* leg14, float* o
 // keep apply_oct itself from terminating on sm_100.  The eight children are initialised the way
 // branchKernel / branchCpu do it (several_leg_octree.cu:168-199,315-352) with the reference's own
 // CreateChildBox; then the reference's kernel runs on them, unmodified.
-//   threads > 0 : ONE block of `threads` threads.  With one warp the kernel is deterministic: all
-//                 lanes finish the flag-clearing loop (:30-34) before any enters the main loop, and
-//                 there is no other block whose write-back (:134-150) races with the early-out on
-//                 node.validity (:58).
-//   threads == 0: the reference's own launch shape (one block per 256 work items, :213-221).
+// The kernel runs as ONE thread (<<<1, 1>>>).  That is the only launch shape in which it is
+// well defined: distance() -> distance_global (one_leg_global.cu:74-101) stages the oriented leg in
+// a __shared__ variable written by threadIdx.x == 0 and then calls __syncthreads() — inside
+// validity_child's divergent loop (`continue`s per work item, :52-60, :82), so with more than one
+// thread per block the barrier sits in divergent code (it deadlocked the B200 for 25 minutes;
+// this is also why apply_oct never terminates on sm_100) and every thread would use thread 0's
+// orientation sample.  One thread = the sequential semantics, deterministic.
 // out_flags: 8 x {validity, leaf, raw, onEdge}; out_boxes: 8 x {center xyz, topOffset xyz}.
 int refgpu_validity_child(const float* parent_box6, int parent_validity, const float* footholds,
-                          size_t nt, const float* leg14, int threads, uint8_t* out_flags,
-                          float* out_boxes) {
+                          size_t nt, const float* leg14, uint8_t* out_flags, float* out_boxes) {
     Node parent;
     std::memcpy(&parent.box, parent_box6, sizeof(Box));
     parent.validity = parent_validity != 0;
@@ -109,15 +110,7 @@ int refgpu_validity_child(const float* parent_box6, int parent_validity, const f
     Array<float3> in{nt, nullptr};
     if (cudaMalloc(&in.elements, (nt ? nt : 1) * sizeof(float3)) != cudaSuccess) return -2;
     cudaMemcpy(in.elements, footholds, nt * sizeof(float3), cudaMemcpyHostToDevice);
-    constexpr size_t samples = AngleSample[0] * AngleSample[1] * AngleSample[2];
-    const size_t work = (size_t)MaxChildQuad * nt * samples;
-    int block = threads, grid = 1;
-    if (threads <= 0) {
-        block = (int)(work < 256 ? (work ? work : 1) : 256);
-        grid = (int)((work + block - 1) / block);
-        if (grid < 1) grid = 1;
-    }
-    validity_child<<<grid, block>>>(parent, in, leg_from(leg14));
+    validity_child<<<1, 1>>>(parent, in, leg_from(leg14));
     const cudaError_t e = cudaDeviceSynchronize();
     for (uint c = 0; c < MaxChildQuad; c++) {
         const Node& node = parent.childrenArr[c];

@@ -202,6 +202,96 @@ void emu_dist_choice(const float* xyz, size_t n, const lrm_leg_t* leg, const flo
     }
 }
 
+// The tiered distance sweep WITH tier 0 (16-bit cube texels: chosen solution + plane label), as
+// one_leg_tier_kernel runs it: dist_choice_label -> dist_choice (plane atlas) -> dist_choice_clamp /
+// dist_fast -> full evaluation.  Texels are computed on demand the way the device build does it:
+// the block of 4^3 cubes first (probe at the block centre), the cube itself (atlas scan) if the
+// block is not settled as a whole.  tiers[0..4] = points decided by tier 0, the atlas tier, the
+// explicit plane evaluation, dist_fast, the full evaluation.
+void emu_dist_tier0(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, int dim, float cell,
+                    float vol_h, int vol_dim, float* out_vec, uint8_t* out_flag, uint8_t* out_reach,
+                    size_t* tiers, uint8_t* out_tier) {
+    lrm::LegPlan L;
+    lrm::build_leg_plan(*leg, quat, &L);
+    lrm::SectorTable tab;
+    host_table(L, &tab);
+    lrm::WinnerTable win;
+    lrm::fill_winner_table(L, &win, 0, 1);
+    lrm::FastTables ft;
+    lrm::build_fast_tables(L, &ft);
+    const float origin = -0.5f * dim * cell;
+    std::vector<unsigned char> cells((size_t)dim * dim);
+    const float need = lrm::kAtlasNeedFactor * cell + lrm::kAtlasNeedSlack;
+    for (int iy = 0; iy < dim; iy++)
+        for (int ix = 0; ix < dim; ix++) {
+            const float X = origin + ((float)ix + 0.5f) * cell, Y = origin + ((float)iy + 0.5f) * cell;
+            cells[lrm::atlas_index(dim, ix, iy)] = (unsigned char)lrm::atlas_cell_byte(lrm::plane_probe(L, tab, X, Y), need);
+        }
+    lrm::AtlasView A{cells.data(), 0, 1.0f / cell, -origin / cell, -origin / cell, dim, dim};
+    const lrm::FastView F{ft.pair, ft.code, ft.combo, ft.ncombo};
+    const lrm::YawSol* sols = reinterpret_cast<const lrm::YawSol*>(ft.pair);
+    std::unordered_map<uint64_t, unsigned> cubes, blocks;
+    const float vo = 0.5f * vol_dim, vinv = 1.0f / vol_h;
+    for (int k = 0; k < 5; k++) tiers[k] = 0;
+    for (size_t i = 0; i < n; i++) {
+        const lrm::CoxaPoint p = lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        const float fx = fmaf(p.x, vinv, vo), fy = fmaf(p.y, vinv, vo + lrm::kVolShiftY), fz = fmaf(p.z, vinv, vo);
+        unsigned word = 0;
+        if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)vol_dim && fy < (float)vol_dim && fz < (float)vol_dim) {
+            const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+            const uint64_t bkey = ((uint64_t)(iz >> 2) * vol_dim + (iy >> 2)) * vol_dim + (ix >> 2);
+            auto bt = blocks.find(bkey);
+            if (bt == blocks.end()) {
+                // volume_coarse_kernel: the block is settled only if nothing needs refinement
+                const float x0 = ((float)(ix & ~3) - vo) * vol_h, y0 = ((float)(iy & ~3) - vo - lrm::kVolShiftY) * vol_h,
+                            z0 = ((float)(iz & ~3) - vo) * vol_h;
+                unsigned w = lrm::coarse_block_word(L, tab, ft, x0, y0, z0, 4.f * vol_h);
+                bt = blocks.emplace(bkey, w).first;
+            }
+            word = bt->second;
+            if (word == 0u) {
+                const uint64_t key = ((uint64_t)iz * vol_dim + iy) * vol_dim + ix;
+                auto it = cubes.find(key);
+                if (it == cubes.end()) {
+                    const unsigned w = lrm::choice_cell_word(L, tab, ft, A, ((float)ix - vo) * vol_h,
+                                                             ((float)iy - vo - lrm::kVolShiftY) * vol_h,
+                                                             ((float)iz - vo) * vol_h, vol_h, false);
+                    it = cubes.emplace(key, w).first;
+                }
+                word = it->second;
+            }
+        }
+        lrm::DistResult r;
+        int tier = 0;
+        int st = lrm::dist_choice_label<true>(L, sols, word, win, p, &r);
+        if (st == 0 && !(word & 0x4000u)) {
+            // a warp without any valid plane point takes the version without the limit-plane rule
+            lrm::DistResult r2;
+            lrm::dist_choice_label<false>(L, sols, word, win, p, &r2);
+            if (std::memcmp(&r2.dx, &r.dx, 12) != 0 || r2.flag != r.flag || r2.reach != r.reach) tiers[0] = (size_t)-1 << 20;
+        }
+        if (st == 3) {  // ring A0: the plane atlas; its cell may be uncertified too (ring A)
+            tier = 1;
+            st = lrm::dist_choice<false>(L, sols, (word & 0xffu) | lrm::kVolPure, A, win, p, &r);
+            if (st == 2) {
+                lrm::dist_choice_clamp(L, tab, sols, word & 0xffu, p, &r);
+                tier = 2;
+            }
+        } else if (st == 1) {
+            tier = 3;
+            if (!lrm::dist_fast<false, false, true>(L, F, A, win, p, &r)) {
+                r = lrm::dist_coxa_frame<false>(L, tab, p);
+                tier = 4;
+            }
+        }
+        tiers[tier]++;
+        if (out_tier) out_tier[i] = (uint8_t)tier;
+        out_vec[3 * i] = r.dx, out_vec[3 * i + 1] = r.dy, out_vec[3 * i + 2] = r.dz;
+        if (out_flag) out_flag[i] = r.flag ? 1 : 0;
+        if (out_reach) out_reach[i] = r.reach ? 1 : 0;
+    }
+}
+
 // The positionability kernel's per-pose logic (positionability.cu) with brute-force target loops:
 // same orientation matrix, same cull cylinders, same leg predicate arithmetic.
 void emu_standability(const float* bodies, size_t nb, const float* map, size_t nt,
@@ -309,5 +399,18 @@ int emu_plan_is_generic(const lrm_leg_t* leg, const float* quat) {
 }
 
 int emu_sizeof_plan() { return (int)sizeof(lrm::LegPlan); }
+
+// the host-built plan and yaw tables, byte for byte (pinned by tests/golden/leg_plan_golden.npz)
+void emu_plan_bytes(const lrm_leg_t* leg, const float* quat, unsigned char* plan_out, unsigned char* tables_out) {
+    lrm::LegPlan L;
+    std::memset(&L, 0, sizeof L);
+    lrm::build_leg_plan(*leg, quat, &L);
+    std::memcpy(plan_out, &L, sizeof L);
+    lrm::FastTables ft;
+    std::memset(&ft, 0, sizeof ft);
+    lrm::build_fast_tables(L, &ft);
+    std::memcpy(tables_out, &ft, sizeof ft);
+}
+int emu_sizeof_tables() { return (int)sizeof(lrm::FastTables); }
 
 }  // extern "C"

@@ -3,6 +3,7 @@
 library), against the golden vectors and the oracle — the same bar as the GPU parity tests.  This
 keeps algorithmic regressions out of the GPU budget; the GPU tests remain the parity tests proper."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -209,6 +210,45 @@ def test_choice_volume_never_changes_a_result(emu, port):
         assert (tier[:120000] == 0).mean() > want_share, (robot, az, float((tier[:120000] == 0).mean()))
 
 
+def test_tier0_labels_never_change_a_result(emu, port):
+    """Tier 0 of the tiered sweep (16-bit cube texels: winning solution + plane label of the cube,
+    certified per block by plane_probe and per cube by the atlas cells under the cube's plane
+    rectangle — coarse_block_word / choice_cell_word, the functions of the device build) followed
+    by the plane-atlas tier, the explicit plane evaluation, dist_fast and the full evaluation: the
+    output equals the full evaluation's BIT FOR BIT whichever tier decides a point, the rule-free
+    variant equals the ruled one wherever the kernel may take it, and tier 0 alone decides most of
+    the bench lattice (the device runs 0.5 mm atlas cells and reaches 88 %; 1 mm cells here)."""
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    emu.emu_dist_tier0.argtypes = [vp, sz, vp, vp, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                   vp, vp, vp, vp, vp]
+    rng = np.random.default_rng(43)
+    idx = rng.integers(0, 1000, (100000, 3))
+    lo, hi = np.array([-100, -400, -500], np.float32), np.array([600, 400, 200], np.float32)
+    lattice = lo + idx.astype(np.float32) * ((hi - lo) / np.float32(999)).astype(np.float32)
+    cloud = np.concatenate([lattice, rng.uniform(-800, 800, (50000, 3))]).astype(np.float32)
+    cases = ((1, 0.0, [1, 0, 0, 0], 3.0, 0.80), (0, 0.7853982, port.quaternion_from_angle_index(0), 4.0, 0.65),
+             (1, 3.9269907, port.full_struct_orientations()[31], 2.0, 0.65))
+    for robot, az, q, cell, want_share in cases:
+        leg = port.get_leg(robot, az)
+        q = np.ascontiguousarray(q, np.float32)
+        pts = np.ascontiguousarray(cloud, np.float32)
+        r0, base, bf, br = run_emu(emu, pts, leg, q)
+        out = np.zeros_like(pts)
+        fl = np.zeros(len(pts), np.uint8)
+        rf = np.zeros(len(pts), np.uint8)
+        tier = np.zeros(len(pts), np.uint8)
+        tiers = (ctypes.c_size_t * 5)()
+        emu.emu_dist_tier0(pts.ctypes.data, len(pts), leg.ctypes.data, q.ctypes.data, 2048, 1.0, cell,
+                           int(1536 / cell) // 4 * 4, out.ctypes.data, fl.ctypes.data, rf.ctypes.data, tiers,
+                           tier.ctypes.data)
+        assert sum(tiers) == len(pts), (robot, az, list(tiers))     # the rule-free variant never differed
+        assert np.array_equal(fl, bf) and np.array_equal(rf, br), (robot, az)
+        assert np.array_equal(out, base), (robot, az, float(np.abs(out - base).max()))
+        share = float((tier[:100000] == 0).mean())
+        assert share > want_share, (robot, az, share, [t / len(pts) for t in tiers])
+        assert all(t > 0 for t in tiers), list(tiers)               # every tier was exercised
+
+
 def test_reach_plan_predicates(emu, port):
     """positionability.cu's per-foothold predicate on the compact ReachPlan equals the full-plan
     path, and the cell-level pruning test is conservative: whenever some point within rc of a
@@ -275,3 +315,21 @@ def test_octree_leg_pruning_is_conservative(emu, port):
                 step *= (rng.uniform(0, 1, (len(step), 1)) ** (1 / 3)) * rc / np.linalg.norm(step, axis=1, keepdims=True)
                 _, _, f2, _ = run_emu(emu, (centres[pruned] + step).astype(np.float32), leg, q)
                 assert not f2.any(), (rc, int(f2.sum()))
+
+
+def test_host_plan_bytes_match_the_golden_file(emu):
+    """The host-built constants (LegPlan: affine maps, angle tests, circle tables, valid arcs,
+    corners; FastTables: yaw-sector pairs and bin codes) byte for byte against
+    tests/golden/leg_plan_golden.npz (captured on x86-64 with -ffp-contract=off): a host compiler
+    that contracts a*b+c, or any edit of leg_plan.cpp / fast_tables.cpp that moves a rounding,
+    shows up here — the certified tables and the knife-edge rules assume these exact bits."""
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "leg_plan_golden.npz"))
+    keys = [k[len("plan_"):] for k in gold.files if k.startswith("plan_")]
+    assert len(keys) >= 4
+    for k in keys:
+        plan = np.zeros(emu.emu_sizeof_plan(), np.uint8)
+        tables = np.zeros(emu.emu_sizeof_tables(), np.uint8)
+        leg, q = np.ascontiguousarray(gold["leg_" + k]), np.ascontiguousarray(gold["quat_" + k])
+        emu.emu_plan_bytes(leg.ctypes.data, q.ctypes.data, plan.ctypes.data, tables.ctypes.data)
+        assert np.array_equal(plan, gold["plan_" + k]), k
+        assert np.array_equal(tables, gold["tables_" + k]), k

@@ -220,12 +220,13 @@ def test_kernel_ms_is_reported(lrm):
 
 
 @pytest.fixture(params=["two-tier", "tiered"])
-def sweep(request, monkeypatch):
-    """LRM_CHOICE_VOLUME (read per launch): 0 = the two-tier sweep (certified tables + full
-    evaluation), 1 = the tiered sweep through the choice volume, waiting for the volume instead of
-    letting it build in the background.  Unset, a coherence probe picks one per launch."""
-    monkeypatch.setenv("LRM_CHOICE_VOLUME", "0" if request.param == "two-tier" else "1")
-    return request.param
+def sweep(request, lrm):
+    """lrm_set_option("sweep"): 0 = the two-tier sweep (certified tables + full evaluation), 1 = the
+    tiered sweep through the choice volume, waiting for the volume instead of letting it build in
+    the background; 2 (the default), a coherence probe picks one per launch."""
+    old = lrm.set_option("sweep", 0 if request.param == "two-tier" else 1)
+    yield request.param
+    lrm.set_option("sweep", old)
 
 
 # ---- the fast path (certified tables + deferred redo) only runs on sweeps of >= 4 Mi points -------
@@ -315,7 +316,7 @@ def test_golden_vectors_through_the_fast_path(lrm, oracle, golden, sweep):
         lrm.set_fast_path_min_points(old)
 
 
-def test_every_sweep_returns_the_same_bits(lrm, monkeypatch):
+def test_every_sweep_returns_the_same_bits(lrm):
     """The two-tier sweep, the tiered sweep and the probe's own pick return identical bytes — on a
     lattice slab (coherent: the probe picks the tiered sweep), on a shuffled cloud reaching beyond
     the choice volume (the probe picks the two-tier sweep), and on points lying ON the reachability
@@ -327,40 +328,79 @@ def test_every_sweep_returns_the_same_bits(lrm, monkeypatch):
     lrm.make_lattice(lattice, lo, step, dims, 0, n)
     g = torch.Generator(device="cuda").manual_seed(12)
     cloud = torch.rand((n, 3), device="cuda", generator=g) * 2000.0 - 1000.0
-    monkeypatch.setenv("LRM_CHOICE_VOLUME", "0")
-    _, v = lrm.reach_dist(lattice, leg)
-    edge = (lattice - v).contiguous()
-    for name, pts in (("lattice", lattice), ("cloud", cloud), ("edge", edge)):
-        got = {}
-        for mode in ("0", "1", None):
-            if mode is None:
-                monkeypatch.delenv("LRM_CHOICE_VOLUME")
-            else:
-                monkeypatch.setenv("LRM_CHOICE_VOLUME", mode)
-            fr, vec = lrm.reach_dist(pts, leg)
-            d, f = lrm.distance(pts, leg)
-            got[mode] = (fr, vec, d, f)
-        for mode in ("1", None):
-            for a, b in zip(got["0"], got[mode]):
-                assert torch.equal(a, b), (name, mode)
+    old = lrm.set_option("sweep", 0)
+    try:
+        _, v = lrm.reach_dist(lattice, leg)
+        edge = (lattice - v).contiguous()
+        for name, pts in (("lattice", lattice), ("cloud", cloud), ("edge", edge)):
+            got = {}
+            for mode in (0, 1, 2):
+                lrm.set_option("sweep", mode)
+                fr, vec = lrm.reach_dist(pts, leg)
+                d, f = lrm.distance(pts, leg)
+                got[mode] = (fr, vec, d, f)
+            for mode in (1, 2):
+                for a, b in zip(got[0], got[mode]):
+                    assert torch.equal(a, b), (name, mode)
+        # a call whose output buffer IS its input buffer (lrm_c.h allows it): parked points are
+        # redone from an input the tile's store has not changed
+        lrm.set_option("sweep", 1)
+        want = lrm.distance(lattice, leg)[0]
+        buf = lattice.clone()
+        lrm.distance(buf, leg, out=buf)
+        assert torch.equal(buf, want)
+    finally:
+        lrm.set_option("sweep", old)
 
 
-def test_plan_cache_eviction_keeps_results(lrm, monkeypatch):
-    """More distinct (leg, orientation) plans than the table cache holds (4), swept back to back
-    with the choice volume forced on: every sweep must rebuild / reuse atlas and volume correctly
-    (eviction while earlier sweeps are still in flight, rebuild into the evicted entry's arrays)
-    and return the bytes of the two-tier sweep."""
+def test_plan_cache_eviction_keeps_results(lrm):
+    """More distinct (leg, orientation) plans than the per-device table cache holds (8), swept back
+    to back with the choice volume forced on: every sweep must rebuild / reuse atlas and volume
+    correctly (eviction while earlier sweeps are still in flight — ordered by events, no host wait —
+    and rebuild into the evicted entry's arrays) and return the bytes of the two-tier sweep."""
     n = 4 * (1 << 20) + 77
     lo, step, dims = lrm.lattice_spec((-100, -400, -500), (600, 400, 200), (5, 1000, 1000))
     pts = torch.empty((n, 3), dtype=torch.float32, device="cuda")
     lrm.make_lattice(pts, lo, step, dims, 0, n)
-    plans = [(robot, az) for robot in (1, 0) for az in (0.0, 0.7, 1.4)] + [(1, 0.0), (0, 0.7)]
+    first = [(robot, az) for robot in (1, 0) for az in (0.0, 0.7, 1.4, 2.1, 2.8)]     # 10 plans > 8 entries
+    plans = first + [(1, 0.0), (0, 0.7), (1, 2.8)]
     want = {}
-    monkeypatch.setenv("LRM_CHOICE_VOLUME", "0")
-    for robot, az in plans[:6]:
-        want[(robot, az)] = lrm.reach_dist(pts, lrm.get_leg(robot, az))
-    monkeypatch.setenv("LRM_CHOICE_VOLUME", "1")
-    got = [lrm.reach_dist(pts, lrm.get_leg(robot, az)) for robot, az in plans]   # no sync in between
-    torch.cuda.synchronize()
+    old = lrm.set_option("sweep", 0)
+    try:
+        for robot, az in first:
+            want[(robot, az)] = lrm.reach_dist(pts, lrm.get_leg(robot, az))
+        lrm.set_option("sweep", 1)
+        got = [lrm.reach_dist(pts, lrm.get_leg(robot, az)) for robot, az in plans]   # no sync in between
+        torch.cuda.synchronize()
+    finally:
+        lrm.set_option("sweep", old)
     for (robot, az), (fr, vec) in zip(plans, got):
         assert torch.equal(fr, want[(robot, az)][0]) and torch.equal(vec, want[(robot, az)][1]), (robot, az)
+
+
+def test_hexapod_legs_stay_cached(lrm):
+    """A hexapod sweeping its six legs in turn (BASELINE configs[4]'s mounts, k * pi / 3) builds each
+    leg's tables once: the second round over the legs builds nothing (lrm_get_stat table_builds)."""
+    n = 4 * (1 << 20)
+    pts = torch.rand((n, 3), device="cuda") * 900.0 - 300.0
+    legs = [lrm.get_M2_leg(float(np.float32(k) * np.float32(np.pi / 3))) for k in range(6)]
+    first = [lrm.distance(pts, leg)[0] for leg in legs]
+    torch.cuda.synchronize()
+    builds = lrm.get_stat("table_builds")
+    second = [lrm.distance(pts, leg)[0] for leg in legs]
+    torch.cuda.synchronize()
+    assert lrm.get_stat("table_builds") == builds
+    for a, b in zip(first, second):
+        assert torch.equal(a, b)
+
+
+def test_options_are_validated(lrm):
+    with pytest.raises(lrm.LrmError):
+        lrm.set_option("no_such_option", 1)
+    with pytest.raises(lrm.LrmError):
+        lrm.set_option("sweep", 7)
+    with pytest.raises(lrm.LrmError):
+        lrm.set_option("volume_dim", 510)       # not a multiple of 4
+    with pytest.raises(lrm.LrmError):
+        lrm.set_option("skeleton", 1)           # measurement builds only
+    assert lrm.set_option("tier_chunk_shift", 3) == 3

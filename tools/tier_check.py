@@ -1,7 +1,7 @@
-"""A/B of the three-tier distance sweep (choice volume) against the two-tier one (LRM_CHOICE_VOLUME=0)
+"""A/B of the tiered distance sweep (choice volume) against the two-tier one (lrm_set_option "sweep" 0)
 on the same resident lattice slab: results must be identical up to float rounding of the
 projection (flags exactly), and both are timed.  Also reports what the first call (volume build)
-costs.  Usage: python tools/tier_check.py [points] [random]"""
+costs.  Usage: python tools/tier_check.py [points] [random] [volume_cell_mm volume_dim]"""
 import json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,12 +18,13 @@ else:
     lo, step, dims = lrm.lattice_spec((-100, -400, -500), (600, 400, 200), (max(1, n // 1_000_000), 1000, 1000))
     lrm.make_lattice(pts, lo, step, dims, 0, n)
 out = {"points": n}
+if len(sys.argv) > 4:
+    lrm.set_option("volume_cell_mm", float(sys.argv[3]))
+    lrm.set_option("volume_dim", int(sys.argv[4]))
+    out["volume"] = [float(sys.argv[3]), int(sys.argv[4])]
 res = {}
-for name, env in (("two_tier", "0"), ("three_tier", "1"), ("auto", None)):
-    if env is None:
-        os.environ.pop("LRM_CHOICE_VOLUME", None)
-    else:
-        os.environ["LRM_CHOICE_VOLUME"] = env
+for name, mode in (("two_tier", 0), ("three_tier", 1), ("auto", 2)):
+    lrm.set_option("sweep", mode)
     flags = torch.empty(n, dtype=torch.uint8, device="cuda")
     vec = torch.empty((n, 3), dtype=torch.float32, device="cuda")
     torch.cuda.synchronize()
