@@ -27,6 +27,7 @@ size_t set_fast_path_min_points(size_t n);
 // Each returns the previous value.
 int set_sweep_mode(int mode);
 int set_tier_chunk_shift(int shift);
+int set_tier_kernel(int which);  // 0 = CTA-tiled tiered sweep, 1 = warp-autonomous tiered sweep
 int set_skeleton(int on);
 // SoA planes; dx == nullptr selects reach-only.
 cudaError_t launch_one_leg_soa(const LegPlan& plan, const float* x, const float* y, const float* z,
@@ -54,6 +55,8 @@ struct TableLease {
 cudaError_t acquire_tables(const LegPlan& plan, cudaStream_t stream, AtlasView* view, FastTables* tables,
                            TableLease* lease);
 void release_tables(TableLease* lease, cudaStream_t stream);
+// true if acquire_tables(plan) would build nothing on the current device
+bool tables_cached(const LegPlan& plan);
 
 // Choice volume of a leased plan: 3-D texture of 16-bit texels (winning coxa solution + plane label
 // per cube, plane_atlas.cu).  Built in the background on first request: until it is there the call

@@ -279,6 +279,9 @@ int lrm_set_option(const char* name, double value, double* previous) {
     } else if (k == "sweep") {
         if (value != 0 && value != 1 && value != 2) return fail(LRM_ERR_INVALID, "sweep must be 0, 1 or 2");
         prev = lrm::set_sweep_mode((int)value);
+    } else if (k == "tier_kernel") {
+        if (value != 0 && value != 1) return fail(LRM_ERR_INVALID, "tier_kernel must be 0 or 1");
+        prev = lrm::set_tier_kernel((int)value);
     } else if (k == "tier_chunk_shift") {
         if (!(value >= 0 && value <= 8)) return fail(LRM_ERR_INVALID, "tier_chunk_shift must be 0..8");
         prev = lrm::set_tier_chunk_shift((int)value);

@@ -35,6 +35,8 @@ constexpr bool kSkipB = LRM_SKIP_B != 0;  // skip the flipped solution by its lo
 // keeps the two points of a trip from interleaving (measured: 104 vs 111 Gpoints/s) -> off
 constexpr size_t kAtlasMinPoints = size_t(1) << 22;
 std::atomic<size_t> g_fast_min_points{kAtlasMinPoints};
+// ... but once a plan's tables are cached they cost nothing: sweeps from this size on use them
+constexpr size_t kCachedMinPoints = size_t(1) << 16;
 // deferred points of the fast path: entries of at most two tiles plus a partial flush block
 constexpr int kQueueCap = 2 * kTile + kThreads + 256;
 static_assert(kTile % kThreads == 0 && kTile % 16 == 0 && kTile <= 1024, "tile shape");
@@ -423,17 +425,20 @@ __global__ void __launch_bounds__(kThreads)
 #ifndef LRM_TIER_CTAS
 #define LRM_TIER_CTAS 4
 #endif
-#ifndef LRM_T0_GROUP
-#define LRM_T0_GROUP 4  // points of a thread that share one "any valid plane point in the warp" vote
-#endif
+// points of a thread that share one "any valid plane point in the warp" vote: all four (finer
+// groups measured no faster, and the one-point build faulted in its distance-only instantiation)
+#define LRM_T0_GROUP 4
 constexpr int kTT = LRM_TIER_THREADS;  // threads per CTA
 constexpr int kTL = LRM_TIER_TILE;     // points per tile
 constexpr int kPer = kTL / kTT;        // points per thread and tile
 static_assert(kTL % kTT == 0 && kTL % 16 == 0 && kTL <= 1024 && kPer % LRM_T0_GROUP == 0, "tier tile shape");
+// Parked points come in runs (a lattice column that grazes a decision surface parks hundreds of
+// consecutive points): rings P and B hold two such tiles.  Measured at 1e9 points: 512 / 512 entries
+// 119.0, 1024 / 512 123.0, 1024 / 1024 125.0 Gpoints/s (an overflowing push falls to a slower tier).
 #ifndef LRM_RING_A
-#define LRM_RING_P 512
+#define LRM_RING_P 1024
 #define LRM_RING_A 512
-#define LRM_RING_B 512
+#define LRM_RING_B 1024
 #define LRM_RING_C 512
 #endif
 constexpr int kRingP = LRM_RING_P, kRingA = LRM_RING_A, kRingB = LRM_RING_B, kRingC = LRM_RING_C;  // entries (powers of two)
@@ -698,6 +703,7 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
         auto park = [&](int i, int why, unsigned word) {
             const uint32_t entry = (it << 15) | ((word & 31u) << 10) | (uint32_t)i;
             if (why == 3 && rp.push(S.ring_p, &S.cnt[0][rot], entry)) return;
+            if (why == 3 && ra.push(S.ring_a, &S.cnt[1][rot], entry)) return;  // P full: the explicit plane evaluation
             if (why == 1 && rb.push(S.ring_b, &S.cnt[2][rot], entry)) return;
             if (rc.push(S.ring_c, &S.cnt[3][rot], entry)) return;
             tile_point_full<MODE, SOA>(L, S.table, in, flag, i);
@@ -830,6 +836,217 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
     // the last n % 16 points bypass the bulk engine
     if (blockIdx.x == 0) {
         const size_t i = n_bulk + tid;
+        if (i < n) redo_full<MODE, SOA>(L, S.table, io, i);
+    }
+}
+
+// ---- warp-autonomous tiered sweep ---------------------------------------------------------------
+// The same tiers as one_leg_tier_kernel, organised per WARP instead of per CTA: no shared-memory
+// tiles, no bulk copies, no CTA barrier, no wait for a store to complete.
+//   * a warp owns tiles of 128 consecutive points; a lane owns FOUR CONSECUTIVE points of the tile:
+//     48 contiguous bytes, read with three 16-byte loads and written back with three 16-byte
+//     stores (AoS; SoA: one 16-byte load / store per plane), flags as one 32-bit word — every
+//     sector of the streams is touched by exactly one warp, once;
+//   * tier 0 as above (one texel fetch per point, all four in flight);
+//   * what tier 0 cannot decide goes to warp-private rings in shared memory (index only); the
+//     lane writes the INPUT back for such a point, and once a ring holds a warp's worth of entries
+//     they are redone from / to global memory by the same warp, 32 at a time — after the
+//     tile's own stores in program order (__syncwarp orders the two writes), so there is nothing to
+//     wait for and a call whose output buffer is its input buffer stays correct;
+//   * rings: P (solution certified, cube without plane label -> plane atlas; hands on to A),
+//     A (-> explicit plane evaluation), B (cube uncertified -> dist_fast; hands on to C),
+//     C (-> full evaluation).
+#ifndef LRM_WARP_CTAS
+#define LRM_WARP_CTAS 4
+#endif
+constexpr int kWT = 128;     // points per warp-tile
+constexpr int kWW = 8;       // warps per CTA
+constexpr int kWCapBig = 256, kWCapSmall = 64;  // ring capacities (powers of two)
+struct WarpRings {
+    uint32_t p[kWCapBig], b[kWCapBig], a[kWCapSmall], c[kWCapSmall];
+};
+struct alignas(128) WarpSmem {
+    alignas(16) SectorTable table;
+    alignas(16) WinnerTable winners;
+    alignas(16) YawPair ypair[kYawPairs];
+    WarpRings ring[kWW];
+};
+// ring entry: warp iteration (20 bits) | cube byte bits 0-4 | point in tile (7 bits)
+struct WarpGeom {
+    uint32_t w, nw;  // this warp, all warps
+    int kshift;
+    __device__ __forceinline__ uint32_t tile_of(uint32_t iter) const {
+        return (((iter >> kshift) * nw + w) << kshift) + (iter & ((1u << kshift) - 1u));
+    }
+    __device__ __forceinline__ size_t global_index(uint32_t entry) const {
+        return (size_t)tile_of(entry >> 12) * kWT + (entry & 127u);
+    }
+};
+
+template <int MODE, bool SOA>
+__global__ void __launch_bounds__(kWW * 32, LRM_WARP_CTAS)
+    one_leg_warp_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
+                        const AtlasView atlas, const VolumeView vol, const __grid_constant__ RedoIo io,
+                        size_t n, int kshift, const int* __restrict__ gate, int gate_want) {
+    if (gate != nullptr && *gate != gate_want) return;  // the coherence probe chose the other sweep
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    auto& S = *reinterpret_cast<WarpSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    fill_sector_table(L, &S.table, tid, kWW * 32);
+    fill_winner_table(L, &S.winners, tid, kWW * 32);
+    for (int i = tid; i < kYawPairs * (int)(sizeof(YawPair) / 4); i += kWW * 32)
+        reinterpret_cast<float*>(S.ypair)[i] = reinterpret_cast<const float*>(FT.pair)[i];
+    __syncthreads();
+
+    const uint32_t n_tiles = (uint32_t)(n / kWT);  // full tiles; the launcher keeps n below 2^38
+    const WarpGeom G{(uint32_t)(blockIdx.x * kWW + warp), (uint32_t)(gridDim.x * kWW), kshift};
+    WarpRings& R = S.ring[warp];
+    const FastView fview{S.ypair, FT.code, FT.combo, FT.ncombo};
+    const YawSol* sols = reinterpret_cast<const YawSol*>(S.ypair);
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t hp = 0, tp = 0, ha = 0, ta = 0, hb = 0, tb = 0, hc = 0, tc = 0;  // ring heads / tails (warp-uniform)
+
+    // one batch of up to 32 entries of a ring; `cnt` lanes take part
+    auto batch_c = [&](uint32_t cnt) {
+        if ((uint32_t)lane < cnt) redo_full<MODE, SOA>(L, S.table, io, G.global_index(R.c[(hc + lane) & (kWCapSmall - 1)]));
+        hc += cnt;
+        __syncwarp();
+    };
+    auto batch_a = [&](uint32_t cnt) {
+        if ((uint32_t)lane < cnt) {
+            const uint32_t e = R.a[(ha + lane) & (kWCapSmall - 1)];
+            redo_choice<MODE, SOA>(L, S.table, sols, (e >> 7) & 31u, io, G.global_index(e));
+        }
+        ha += cnt;
+        __syncwarp();
+    };
+    auto batch_b = [&](uint32_t cnt) {
+        uint32_t e = 0;
+        bool fail = false;
+        if ((uint32_t)lane < cnt) {
+            e = R.b[(hb + lane) & (kWCapBig - 1)];
+            fail = !redo_fast<MODE, SOA>(L, fview, atlas, S.winners, io, G.global_index(e));
+        }
+        hb += cnt;
+        const unsigned m = __ballot_sync(0xffffffffu, fail);
+        if (m) {
+            if (tc - hc + __popc(m) > (uint32_t)kWCapSmall) batch_c(tc - hc < 32u ? tc - hc : 32u);
+            if (fail) R.c[(tc + __popc(m & lt)) & (kWCapSmall - 1)] = e;
+            tc += __popc(m);
+        }
+        __syncwarp();
+    };
+    auto batch_p = [&](uint32_t cnt) {
+        uint32_t e = 0;
+        bool fail = false;
+        if ((uint32_t)lane < cnt) {
+            e = R.p[(hp + lane) & (kWCapBig - 1)];
+            fail = !redo_atlas<MODE, SOA>(L, sols, (e >> 7) & 31u, atlas, S.winners, io, G.global_index(e));
+        }
+        hp += cnt;
+        const unsigned m = __ballot_sync(0xffffffffu, fail);
+        if (m) {
+            if (ta - ha + __popc(m) > (uint32_t)kWCapSmall) batch_a(ta - ha < 32u ? ta - ha : 32u);
+            if (fail) R.a[(ta + __popc(m & lt)) & (kWCapSmall - 1)] = e;
+            ta += __popc(m);
+        }
+        __syncwarp();
+    };
+
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t tile = G.tile_of(it);
+        if (tile >= n_tiles) break;
+        const size_t base = (size_t)tile * kWT;
+        // the lane's four consecutive points
+        float x[4], y[4], z[4];
+        if (SOA) {
+            const float4 vx = __ldcs(reinterpret_cast<const float4*>(io.in_x + base) + lane);
+            const float4 vy = __ldcs(reinterpret_cast<const float4*>(io.in_y + base) + lane);
+            const float4 vz = __ldcs(reinterpret_cast<const float4*>(io.in_z + base) + lane);
+            x[0] = vx.x, x[1] = vx.y, x[2] = vx.z, x[3] = vx.w;
+            y[0] = vy.x, y[1] = vy.y, y[2] = vy.z, y[3] = vy.w;
+            z[0] = vz.x, z[1] = vz.y, z[2] = vz.z, z[3] = vz.w;
+        } else {
+            const float4* src = reinterpret_cast<const float4*>(io.in_x + 3 * base) + 3 * lane;
+            const float4 v0 = __ldcs(src), v1 = __ldcs(src + 1), v2 = __ldcs(src + 2);
+            x[0] = v0.x, y[0] = v0.y, z[0] = v0.z, x[1] = v0.w, y[1] = v1.x, z[1] = v1.y;
+            x[2] = v1.z, y[2] = v1.w, z[2] = v2.x, x[3] = v2.y, y[3] = v2.z, z[3] = v2.w;
+        }
+        CoxaPoint p[4];
+        unsigned wd[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            p[k] = to_coxa_frame(L, x[k], y[k], z[k]);
+            wd[k] = tex3D<unsigned short>(vol.tex, fmaf(p[k].x, vol.inv_cell, vol.o), fmaf(p[k].y, vol.inv_cell, vol.oy),
+                                          fmaf(p[k].z, vol.inv_cell, vol.o));
+        }
+        DistResult r[4];
+        int st[4];
+        // the limit-plane rule needs a valid plane point (bit 6 of the label): skipped when no lane
+        // of the warp has one in this tile
+        if (__any_sync(0xffffffffu, ((wd[0] | wd[1] | wd[2] | wd[3]) & 0x4000u) != 0u)) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) st[k] = dist_choice_label<true>(L, sols, wd[k], S.winners, p[k], &r[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) st[k] = dist_choice_label<false>(L, sols, wd[k], S.winners, p[k], &r[k]);
+        }
+        // a parked point gets its input written back (the redo replaces it)
+        unsigned fl = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (st[k] == 0) {
+                x[k] = r[k].dx, y[k] = r[k].dy, z[k] = r[k].dz;
+                fl |= ((MODE == kModeBoth ? r[k].reach : r[k].flag) ? 1u : 0u) << (8 * k);
+            }
+        }
+        if (SOA) {
+            __stcs(reinterpret_cast<float4*>(io.out_x + base) + lane, make_float4(x[0], x[1], x[2], x[3]));
+            __stcs(reinterpret_cast<float4*>(io.out_y + base) + lane, make_float4(y[0], y[1], y[2], y[3]));
+            __stcs(reinterpret_cast<float4*>(io.out_z + base) + lane, make_float4(z[0], z[1], z[2], z[3]));
+        } else {
+            float4* dst = reinterpret_cast<float4*>(io.out_x + 3 * base) + 3 * lane;
+            __stcs(dst, make_float4(x[0], y[0], z[0], x[1]));
+            __stcs(dst + 1, make_float4(y[1], z[1], x[2], y[2]));
+            __stcs(dst + 2, make_float4(z[2], x[3], y[3], z[3]));
+        }
+        if (io.out_flag) __stcs(reinterpret_cast<unsigned*>(io.out_flag + base) + lane, fl);
+        if (__any_sync(0xffffffffu, (st[0] | st[1] | st[2] | st[3]) != 0)) {
+            __syncwarp();  // the tile's stores precede the redo's stores to the same addresses
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t e = (it << 12) | ((wd[k] & 31u) << 7) | (uint32_t)(4 * lane + k);
+                const unsigned mp = __ballot_sync(0xffffffffu, st[k] == 3);
+                if (st[k] == 3) R.p[(tp + __popc(mp & lt)) & (kWCapBig - 1)] = e;
+                tp += __popc(mp);
+                const unsigned mb = __ballot_sync(0xffffffffu, st[k] == 1);
+                if (st[k] == 1) R.b[(tb + __popc(mb & lt)) & (kWCapBig - 1)] = e;
+                tb += __popc(mb);
+            }
+            __syncwarp();
+#pragma unroll 1
+            while (tp - hp >= 32u) batch_p(32u);
+#pragma unroll 1
+            while (ta - ha >= 32u) batch_a(32u);
+#pragma unroll 1
+            while (tb - hb >= 32u) batch_b(32u);
+#pragma unroll 1
+            while (tc - hc >= 32u) batch_c(32u);
+        }
+    }
+    // drain: P before A, B before C (the hand-overs)
+#pragma unroll 1
+    while (tp != hp) batch_p(tp - hp < 32u ? tp - hp : 32u);
+#pragma unroll 1
+    while (ta != ha) batch_a(ta - ha < 32u ? ta - ha : 32u);
+#pragma unroll 1
+    while (tb != hb) batch_b(tb - hb < 32u ? tb - hb : 32u);
+#pragma unroll 1
+    while (tc != hc) batch_c(tc - hc < 32u ? tc - hc : 32u);
+
+    // the last n % 128 points
+    if (blockIdx.x == 0) {
+        const size_t i = (size_t)n_tiles * kWT + tid;
         if (i < n) redo_full<MODE, SOA>(L, S.table, io, i);
     }
 }
@@ -987,11 +1204,47 @@ std::atomic<int> g_sweep_mode{2};
 std::atomic<int> g_skeleton{0};
 #endif
 
+std::atomic<int> g_tier_kernel{0};  // 0 = CTA tiles + CTA rings (one_leg_tier_kernel, the faster one: 118 vs 110-114 Gpoints/s), 1 = warp-autonomous
+
+template <int MODE, bool SOA>
+cudaError_t launch_warp_impl(const LegPlan& plan, const FastTables& ft, const AtlasView& atlas,
+                             const VolumeView& vol, const float* ix, const float* iy, const float* iz,
+                             float* ox, float* oy, float* oz, uint8_t* flag, size_t n, cudaStream_t stream,
+                             const int* gate, int gate_want) {
+    auto kernel = one_leg_warp_kernel<MODE, SOA>;
+    constexpr size_t smem = sizeof(WarpSmem);
+    static int ctas_per_sm_dev[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& ctas_per_sm = ctas_per_sm_dev[dev & 63];
+    if (ctas_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kWW * 32, smem);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = occ < 1 ? 1 : occ;
+    }
+    const size_t tiles = n / kWT;
+    size_t grid = (size_t)sm_count() * ctas_per_sm;
+    if ((tiles + kWW - 1) / kWW < grid) grid = (tiles + kWW - 1) / kWW;
+    if (grid == 0) grid = 1;
+    // chunks of up to 8 consecutive tiles (one lattice column) per warp, fewer on small sweeps
+    int kshift = 0;
+    const int kshift_max = g_tier_chunk_shift.load(std::memory_order_relaxed);
+    while (kshift < kshift_max && (tiles >> (kshift + 1)) >= grid * kWW * 8) kshift++;
+    const RedoIo io{ix, iy, iz, ox, oy, oz, flag};
+    kernel<<<(unsigned)grid, kWW * 32, smem, stream>>>(plan, ft, atlas, vol, io, n, kshift, gate, gate_want);
+    return cudaGetLastError();
+}
+
 template <int MODE, bool SOA>
 cudaError_t launch_tier_impl(const LegPlan& plan, const FastTables& ft, const AtlasView& atlas,
                              const VolumeView& vol, const float* ix, const float* iy, const float* iz,
                              float* ox, float* oy, float* oz, uint8_t* flag, size_t n, cudaStream_t stream,
                              const int* gate, int gate_want) {
+    if (g_tier_kernel.load(std::memory_order_relaxed) == 1 && n < (size_t(1) << 38))
+        return launch_warp_impl<MODE, SOA>(plan, ft, atlas, vol, ix, iy, iz, ox, oy, oz, flag, n, stream, gate, gate_want);
     auto kernel = one_leg_tier_kernel<MODE, SOA>;
     constexpr size_t smem = sizeof(TierSmem);
     static int ctas_per_sm_dev[64] = {0};
@@ -1081,7 +1334,10 @@ cudaError_t launch_stream(const LegPlan& plan, const float* ix, const float* iy,
                           cudaStream_t stream, size_t n_call = 0) {
     AtlasView none{};
     static const FastTables no_tables{};
-    const bool big = (n_call > n ? n_call : n) >= g_fast_min_points.load(std::memory_order_relaxed);
+    const size_t n_eff = n_call > n ? n_call : n;
+    const size_t n_min = g_fast_min_points.load(std::memory_order_relaxed);
+    const bool big = n_eff >= n_min ||
+                     (n_eff >= kCachedMinPoints && n_min == kAtlasMinPoints && !plan.generic && tables_cached(plan));
     const int vmode = g_sweep_mode.load(std::memory_order_relaxed);
     if (MODE == kModeReach) {
         // large reach-only sweeps read the valid bit of the plane atlas instead of testing circles
@@ -1168,6 +1424,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 size_t set_fast_path_min_points(size_t n) { return g_fast_min_points.exchange(n); }
 int set_sweep_mode(int mode) { return g_sweep_mode.exchange(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); }
+int set_tier_kernel(int which) { return g_tier_kernel.exchange(which ? 1 : 0); }
 int set_tier_chunk_shift(int shift) { return g_tier_chunk_shift.exchange(shift < 0 ? 0 : (shift > 8 ? 8 : shift)); }
 int set_skeleton(int on) {
 #ifdef LRM_ENABLE_SKELETON

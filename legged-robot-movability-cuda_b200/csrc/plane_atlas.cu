@@ -292,6 +292,15 @@ int set_choice_volume_shape(float cell_mm, int dim) {
 void get_choice_volume_shape(float* cell_mm, int* dim) { *cell_mm = g_vol_cell.load(), *dim = g_vol_dim.load(); }
 unsigned long long table_builds() { return g_builds.load(); }
 
+bool tables_cached(const LegPlan& plan) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
+    for (const Entry* c : g_cache[dev])
+        if (c->used && std::memcmp(&c->plan, &plan, sizeof(LegPlan)) == 0) return true;
+    return false;
+}
+
 cudaError_t acquire_tables(const LegPlan& plan, cudaStream_t stream, AtlasView* view, FastTables* tables,
                            TableLease* lease) {
     lease->entry = nullptr;

@@ -114,3 +114,20 @@ def test_gpu_recurs_matches_oracle(lrm, port):
     got_h = lrm.apply_recurs(pts[:5000], lrm.get_M2_leg(0.0), 5)
     want_h = port.apply_recurs(pts[:5000], port.get_leg(1, 0.0), 5)
     assert (got_h[:, 0] != want_h[:, 0]).sum() <= 10
+
+
+@pytest.mark.gpu
+def test_gpu_octree_shards_merge_to_the_full_tree(lrm, port):
+    """lrm_oct_sharded: the root's children dealt round-robin to 2 / 3 / 8 shards; the merged lists
+    (top-level child c from shard c % nshards) equal the unsharded result, order included."""
+    torch = pytest.importorskip("torch")
+    terr = torch.from_numpy(terrain.sine_terrain(25, 1200.0, 80.0)).cuda()
+    leg = lrm.LegDimensions.from_array(wide_leg(port))
+    full, counts = lrm.apply_oct(terr, leg, 6, child_counts=True)
+    assert len(full) > 0 and counts.sum() == len(full)
+    for nshards in (2, 3, 8):
+        parts = [lrm.apply_oct(terr, leg, 6, shard=r, nshards=nshards, child_counts=True) for r in range(nshards)]
+        for r, (_, c) in enumerate(parts):
+            assert all(c[k] == 0 for k in range(8) if k % nshards != r)
+        merged = lrm.merge_oct_shards(parts)
+        assert np.array_equal(merged, full), nshards

@@ -219,14 +219,17 @@ def test_kernel_ms_is_reported(lrm):
     assert 0 < ms < 50
 
 
-@pytest.fixture(params=["two-tier", "tiered"])
+@pytest.fixture(params=["two-tier", "tiered-cta", "tiered-warp"])
 def sweep(request, lrm):
     """lrm_set_option("sweep"): 0 = the two-tier sweep (certified tables + full evaluation), 1 = the
     tiered sweep through the choice volume, waiting for the volume instead of letting it build in
-    the background; 2 (the default), a coherence probe picks one per launch."""
+    the background; 2 (the default), a coherence probe picks one per launch.  "tier_kernel" picks
+    the tiered sweep's organisation: 0 = CTA tiles + CTA-wide rings, 1 = warp-autonomous."""
     old = lrm.set_option("sweep", 0 if request.param == "two-tier" else 1)
+    oldk = lrm.set_option("tier_kernel", 0 if request.param == "tiered-cta" else 1)
     yield request.param
     lrm.set_option("sweep", old)
+    lrm.set_option("tier_kernel", oldk)
 
 
 # ---- the fast path (certified tables + deferred redo) only runs on sweeps of >= 4 Mi points -------
@@ -334,23 +337,27 @@ def test_every_sweep_returns_the_same_bits(lrm):
         edge = (lattice - v).contiguous()
         for name, pts in (("lattice", lattice), ("cloud", cloud), ("edge", edge)):
             got = {}
-            for mode in (0, 1, 2):
+            for mode, kern in ((0, 1), (1, 0), (1, 1), (2, 1)):
                 lrm.set_option("sweep", mode)
+                lrm.set_option("tier_kernel", kern)
                 fr, vec = lrm.reach_dist(pts, leg)
                 d, f = lrm.distance(pts, leg)
-                got[mode] = (fr, vec, d, f)
-            for mode in (1, 2):
-                for a, b in zip(got[0], got[mode]):
-                    assert torch.equal(a, b), (name, mode)
+                got[(mode, kern)] = (fr, vec, d, f)
+            for key in ((1, 0), (1, 1), (2, 1)):
+                for a, b in zip(got[(0, 1)], got[key]):
+                    assert torch.equal(a, b), (name, key)
         # a call whose output buffer IS its input buffer (lrm_c.h allows it): parked points are
         # redone from an input the tile's store has not changed
         lrm.set_option("sweep", 1)
         want = lrm.distance(lattice, leg)[0]
-        buf = lattice.clone()
-        lrm.distance(buf, leg, out=buf)
-        assert torch.equal(buf, want)
+        for kern in (0, 1):
+            lrm.set_option("tier_kernel", kern)
+            buf = lattice.clone()
+            lrm.distance(buf, leg, out=buf)
+            assert torch.equal(buf, want), kern
     finally:
         lrm.set_option("sweep", old)
+        lrm.set_option("tier_kernel", 0)
 
 
 def test_plan_cache_eviction_keeps_results(lrm):

@@ -175,3 +175,38 @@ def test_robot_full_struct_wrapper_and_edge_cases(lrm, port):
     # a non-rotation quaternion is rejected (the search radii assume an isometry)
     with pytest.raises(lrm.LrmError):
         lrm.positionability(bodies, terr, legs, quats=np.array([[0.5, 0, 0, 0]], np.float32))
+
+
+@pytest.mark.gpu
+def test_predicate_counts(lrm, port):
+    """lrm_positionability_counts: same flags as lrm_positionability; the executed leg-predicate
+    count is positive and below the algorithmic one (pruning + early exit), which equals a brute-force
+    count of the map points inside the reach cylinder (several_leg.cu:505-520) x legs x orientations."""
+    torch = pytest.importorskip("torch")
+    from tests import terrain
+    terr = terrain.sine_terrain(49, 600.0, 60.0)
+    bx, by, bz = np.meshgrid(np.linspace(-300, 300, 5, dtype=np.float32), np.linspace(-300, 300, 5, dtype=np.float32),
+                             np.linspace(50, 350, 4, dtype=np.float32), indexing="ij")
+    bodies = np.ascontiguousarray(np.stack([bx, by, bz], -1).reshape(-1, 3), np.float32)
+    legs = [lrm.get_M2_leg(float(np.float32(k) * np.float32(np.pi / 2))) for k in range(4)]
+    quats = lrm.full_struct_orientations()[:5]
+    d_b, d_t = torch.from_numpy(bodies).cuda(), torch.from_numpy(terr).cuda()
+    want = lrm.positionability(d_b, d_t, legs, quats)
+    got, cnt = lrm.positionability_counts(d_b, d_t, legs, quats)
+    assert torch.equal(want, got)
+    assert 0 < cnt["leg_predicates_executed"] <= cnt["leg_predicates_algorithmic"]
+    # brute force: orientation frame = qtRotate(q, .); cylinder of leg 0 after the limit rotation
+    total = 0
+    for q in quats:
+        T = np.stack([port.qt_rotate(q, t) for t in terr])
+        leg0 = port.rotate_leg_data(q, legs[0].as_array())
+        s_p, c_p = np.sin(np.float32(leg0[2])), np.cos(np.float32(leg0[2]))
+        radius = leg0[1] + c_p * leg0[3] + leg0[5] + leg0[4]
+        plus = s_p * leg0[3] + leg0[4] * np.sin(leg0[6]) + leg0[5] * np.sin(min(np.pi / 2, leg0[12]))
+        minus = s_p * leg0[3] - leg0[5] - leg0[4]
+        for b in bodies:
+            B = port.qt_rotate(q, b)
+            d = T - B
+            inside = (np.hypot(d[:, 0], d[:, 1]) < radius) & (d[:, 2] < plus) & (d[:, 2] > minus)
+            total += int(inside.sum()) * len(legs)
+    assert abs(cnt["leg_predicates_algorithmic"] - total) <= max(8, total // 2000), (cnt, total)

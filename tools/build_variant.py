@@ -22,6 +22,6 @@ if r.returncode != 0:
     sys.exit(r.stderr[-3000:])
 lines = r.stderr.splitlines()
 for i, l in enumerate(lines):
-    if "one_leg_tier_kernelILi3ELb0" in l and "Compiling" in l:
+    if ("one_leg_tier_kernelILi3ELb0" in l or "one_leg_warp_kernelILi3ELb0" in l) and "Compiling" in l:
         print(name, " | ".join(x.strip() for x in lines[i + 2:i + 4]))
 print(out)

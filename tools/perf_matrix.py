@@ -17,23 +17,23 @@ libs = {"product": None}
 for f in sorted(os.listdir(var)) if os.path.isdir(var) else []:
     if f.startswith("liblrm_") and f.endswith(".so") and "skel" not in f:
         libs[f[len("liblrm_"):-3]] = os.path.join(var, f)
-shapes = [("3", "512"), ("2.5", "640"), ("2", "768"), ("4", "384")]
+shapes = [("3", "512", "0"), ("3", "512", "1"), ("2.5", "640", "0"), ("2", "768", "0"), ("4", "384", "0")]
 rows = []
 for name, lib in libs.items():
-    for cell, dim in (shapes if name == "product" else shapes[:1]):
+    for cell, dim, kern in (shapes if name == "product" else shapes[:1]):
         env = dict(os.environ)
         if lib:
             env["LRM_B200_LIB"] = lib
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tier_check.py"), points, "lattice", cell, dim],
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tier_check.py"), points, "lattice", cell, dim, kern],
                            capture_output=True, text=True, env=env, cwd=ROOT)
         line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
         try:
             row = json.loads(line)
         except Exception:
             row = {"error": (r.stderr or r.stdout)[-800:]}
-        row["build"], row["cell"], row["dim"] = name, cell, dim
+        row["build"], row["cell"], row["dim"], row["kernel"] = name, cell, dim, kern
         rows.append(row)
-        print(json.dumps({k: row.get(k) for k in ("build", "cell", "dim", "flags_equal", "max_vec_diff_mm", "auto_equal",
+        print(json.dumps({k: row.get(k) for k in ("build", "cell", "dim", "kernel", "flags_equal", "max_vec_diff_mm", "auto_equal",
                                                   "reach_equal", "error")} |
                          {m: row.get(m, {}).get("fused_gpoints_s") for m in ("two_tier", "three_tier", "auto")} |
                          {"dist": row.get("three_tier", {}).get("dist_gpoints_s"),

@@ -1,5 +1,5 @@
 """A few launches of one one-leg kernel on a resident lattice slab (profiling target).
-    python tools/run_fused.py [points] [reps] [reach|dist|both]"""
+    python tools/run_fused.py [points] [reps] [reach|dist|both] [sweep: 0 two-tier | 1 tiered | 2 auto]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -14,6 +14,8 @@ lrm.make_lattice(pts, lo, step, dims, 0, n)
 flags = torch.empty(n, dtype=torch.uint8, device="cuda")
 vec = torch.empty((n, 3), dtype=torch.float32, device="cuda")
 mode = sys.argv[3] if len(sys.argv) > 3 else "both"
+if len(sys.argv) > 4:
+    lrm.set_option("sweep", int(sys.argv[4]))
 for _ in range(reps):
     if mode == "reach":
         lrm.reachability(pts, leg, out=flags)

@@ -22,6 +22,9 @@ if len(sys.argv) > 4:
     lrm.set_option("volume_cell_mm", float(sys.argv[3]))
     lrm.set_option("volume_dim", int(sys.argv[4]))
     out["volume"] = [float(sys.argv[3]), int(sys.argv[4])]
+if len(sys.argv) > 5:
+    lrm.set_option("tier_kernel", int(sys.argv[5]))
+    out["tier_kernel"] = int(sys.argv[5])
 res = {}
 for name, mode in (("two_tier", 0), ("three_tier", 1), ("auto", 2)):
     lrm.set_option("sweep", mode)
