@@ -109,6 +109,36 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa(local):
+    """Bind this process to the CPUs that sit next to GPU `local` (sysfs local_cpulist of its PCI
+    function), so that the pinned staging buffers allocated afterwards are first touched on that
+    NUMA node.  Best effort: returns what it found / did."""
+    info = {"bound": False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        info["pci"] = bdf
+        info["numa_node"] = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        info["local_cpulist"] = cpulist
+        cpus = set()
+        for part in cpulist.split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+        info["cpus_used"] = len(os.sched_getaffinity(0))
+    except Exception as e:  # no sysfs entry (containers), single node, ...
+        info["note"] = f"{type(e).__name__}: {e}"
+    return info
+
+
 def lattice_dims(points):
     """nx x 1000 x 1000 points (z fastest) with nx = ceil(points / 1e6)."""
     ny = nz = 1000
@@ -215,17 +245,18 @@ def run_positionability(lrm, torch, dist, dev, rank, world, args):
     8 chunks per rank dealt round-robin (poses differ by orders of magnitude in cost); no collective
     in the search; standable counts and kernel times are reduced at the end."""
     from importlib import import_module
-    from tests import terrain
-    slabs = import_module("lrm_b200.slabs")
+    slabs, fixtures = import_module("lrm_b200.slabs"), import_module("lrm_b200.fixtures")
     side, poses = args.posit_map, args.posit_poses
     n_map = side * side
-    d_terr = torch.empty((n_map, 3), dtype=torch.float32, device=dev)
     gen_s = 0.0
     if rank == 0:
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        terr = terrain.perlin_terrain((side, side))
+        d_terr = fixtures.perlin_terrain((side, side), device=dev)     # generated on the device
+        torch.cuda.synchronize()
         gen_s = time.perf_counter() - t0
-        d_terr.copy_(torch.from_numpy(terr))
+    else:
+        d_terr = torch.empty((n_map, 3), dtype=torch.float32, device=dev)
     bcast_ms = 0.0
     if world > 1:
         torch.cuda.synchronize()
@@ -233,13 +264,15 @@ def run_positionability(lrm, torch, dist, dev, rank, world, args):
         dist.broadcast(d_terr, src=0)
         torch.cuda.synchronize()
         bcast_ms = (time.perf_counter() - t0) * 1e3
-        terr = d_terr.cpu().numpy()
-    bodies_all = terrain.body_lattice(terr, poses, poses, poses)
-    mine = slabs.dealt_chunks(len(bodies_all), rank, world, chunks_per_rank=8)
-    bodies = np.concatenate([bodies_all[f:f + c] for f, c in mine]) if mine else np.zeros((0, 3), np.float32)
+    d_all = fixtures.body_lattice(d_terr, poses, poses, poses)
+    mine = slabs.dealt_chunks(d_all.shape[0], rank, world, chunks_per_rank=8)
+    d_bod = torch.cat([d_all[f:f + c] for f, c in mine]).contiguous() if mine else d_all[:0]
+    n_poses_all = int(d_all.shape[0])
+    del d_all
+    bodies = d_bod.cpu().numpy()
+    terr = d_terr.cpu().numpy() if rank == 0 else None
     legs = [lrm.get_M2_leg(float(np.float32(k) * np.float32(np.pi / 2))) for k in range(4)]
     quats = lrm.full_struct_orientations()
-    d_bod = torch.from_numpy(np.ascontiguousarray(bodies)).to(dev)
     out, ms = lrm.positionability(d_bod, d_terr, legs, quats, timing=True)   # warm-up
     best = None
     for _ in range(2):
@@ -274,14 +307,15 @@ def run_positionability(lrm, torch, dist, dev, rank, world, args):
     if rank != 0:
         return None
     wall = max(walls)
-    rec = {"metric": "body poses/s (4-leg map positionability)", "value": len(bodies_all) / wall, "unit": "poses/s",
+    rec = {"metric": "body poses/s (4-leg map positionability)", "value": n_poses_all / wall, "unit": "poses/s",
            "config": f"BASELINE configs[2]: 4 M2 legs at k*pi/2, {n_map}-point Perlin map (seed 42), {poses}^3 = "
-                     f"{len(bodies_all)} body poses, 45 orientations of robot_full_struct, no pre-cull",
-           "n_gpus": world, "poses": len(bodies_all), "map_points": n_map, "orientations": int(len(quats)),
+                     f"{n_poses_all} body poses, 45 orientations of robot_full_struct, no pre-cull",
+           "n_gpus": world, "poses": n_poses_all, "map_points": n_map, "orientations": int(len(quats)),
            "wall_ms": wall * 1e3, "kernel_ms_min": min(kms), "kernel_ms_max": max(kms),
            "kernel_ms_per_rank": [round(k, 2) for k in kms], "standable": int(standable.item()),
            "partition": "8 contiguous chunks per rank, dealt round-robin; map broadcast once",
-           "map_broadcast_ms": bcast_ms, "map_generation_s": round(gen_s, 2),
+           "map_broadcast_ms": bcast_ms, "map_generation_s": round(gen_s, 3),
+           "map_generator": "lrm_b200.fixtures.perlin_terrain on the device (bit-identical to the reference's numpy generator)",
            "predicates": {"leg_executed": float(c[0]), "cylinder_executed": float(c[1]),
                           "leg_algorithmic": float(c[2]),
                           "leg_executed_per_s": float(c[0]) / (max(kms) * 1e-3),
@@ -388,7 +422,10 @@ def run_b200(args):
     value = n_all * args.steps / (total_ms_max * 1e-3) / 1e9
     reach_count = int(flags.sum().item())
 
-    # end to end through the C ABI with HOST buffers (pinned), copies inside the timed region
+    # end to end through the C ABI with HOST buffers (pinned), copies inside the timed region;
+    # the buffers are first touched on the GPU's own NUMA node
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local)
     ne = min(args.e2e_points, n)
     h_pts = torch.empty((ne, 3), dtype=torch.float32).pin_memory()
     h_pts.copy_(pts[:ne])
@@ -409,6 +446,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = ne * world * e2e_steps / float(t.item()) / 1e9
     assert np.array_equal(hf[:4096], flags[:4096].cpu().numpy())
+    os.sched_setaffinity(0, all_cpus)     # the cpu_baseline leg uses every host thread
 
     line = None
     exit_code = 0
@@ -439,7 +477,7 @@ def run_b200(args):
                          "bytes_per_point": BYTES_PER_POINT},
             "e2e": {"value": e2e_value, "unit": "Gpoints/s", "h2d_bytes_per_step": 12 * ne,
                     "d2h_bytes_per_step": 13 * ne, "points_per_step": ne,
-                    "note": "lrm_reach_dist with pinned host buffers, H2D + kernel + D2H per step"},
+                    "note": "lrm_reach_dist with pinned host buffers, H2D + kernel + D2H per step", "numa_rank0": numa},
             # per step: the coherence probe (1 CTA), the tiered sweep it selects for a lattice, and the
             # two-tier sweep that reads the verdict and returns at once
             "gpu_launches": 3 * args.steps, "clocks": clk,

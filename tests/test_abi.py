@@ -167,8 +167,14 @@ def test_reference_call_sites_compile_against_the_shim(lrm, tmp_path):
     ref = "/root/reference"
     if not os.path.isdir(ref):
         pytest.skip("reference tree not present (the GPU box)")
-    bench = open(os.path.join(ref, "bench.cpp")).read().splitlines()[119:158]
-    several = open(os.path.join(ref, "several_leg.cpp")).read().splitlines()[123:223]
+    lines = open(os.path.join(ref, "bench.cpp")).read().splitlines()
+    first = next(i for i, l in enumerate(lines) if l.strip() == "float duration;")
+    last = next(i for i, l in enumerate(lines) if "Compute Mode Error" in l and i > first)
+    bench = lines[first:last + 1]                                   # bench.cpp:123-158, the five arms
+    lines = open(os.path.join(ref, "several_leg.cpp")).read().splitlines()
+    first = next(i for i, l in enumerate(lines) if "dist_input_tx.bin" in l) - 2   # the opening brace of the block
+    last = next(i for i, l in enumerate(lines) if l.strip() == "return 0;" and i > first)
+    several = lines[first:last + 1]                                 # several_leg.cpp:124-222, both file-protocol blocks
     src = tmp_path / "ref_callsites.cpp"
     src.write_text("\n".join([
         '#include <chrono>', '#include <iostream>', '#include <vector>', '#include "lrm_compat.hpp"',

@@ -33,3 +33,29 @@ def test_perlin_terrain_shape_and_determinism():
     assert 100 < np.ptp(t1[:, 2]) < 1500
     b = terrain.body_lattice(t1, 4, 5, 6)
     assert b.shape == (120, 3) and b[1, 2] > b[0, 2]  # z fastest
+
+
+def test_device_generator_matches_the_numpy_restatement(lrm):
+    """lrm_b200.fixtures.perlin_terrain (torch tensor ops; here on the CPU device) returns the bytes
+    of the numpy generator for the same seed, on square and ragged shapes; body_lattice too."""
+    torch = pytest.importorskip("torch")
+    from importlib import import_module
+    fx = import_module("lrm_b200.fixtures")
+    for shape in (128, (256, 128), (384, 512)):
+        want = terrain.perlin_terrain(shape, seed=7)
+        got = fx.perlin_terrain(shape, seed=7, device="cpu").numpy()
+        assert np.array_equal(want, got), shape
+    t = terrain.perlin_terrain(128)
+    assert np.array_equal(terrain.body_lattice(t, 5, 6, 7), fx.body_lattice(torch.from_numpy(t), 5, 6, 7).numpy())
+
+
+@pytest.mark.gpu
+def test_device_generator_on_the_gpu(lrm):
+    """The same on cuda:0 at BASELINE configs[2]'s size (1024 x 1024): float64 mul / add / remainder
+    are exact IEEE operations on both sides, so the terrain is the reference's bit for bit."""
+    torch = pytest.importorskip("torch")
+    from importlib import import_module
+    fx = import_module("lrm_b200.fixtures")
+    want = terrain.perlin_terrain(1024)
+    got = fx.perlin_terrain(1024, device="cuda").cpu().numpy()
+    assert np.array_equal(want, got)

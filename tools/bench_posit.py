@@ -7,8 +7,10 @@
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_posit.py ...
 
 Multi-GPU: rank 0 builds the map and broadcasts it once over NCCL (NVLink /
-NVSwitch); every rank then owns a contiguous slab of poses — no collective in the search itself;
-the per-slab standable counts are gathered at the end and the time is the max over ranks.
+NVSwitch); the poses are cut into 8 contiguous chunks per rank, dealt round-robin (poses differ by
+orders of magnitude in cost) — no collective in the search itself; the standable counts are
+gathered at the end and the time is the max over ranks.  The body-space octree (c4) is sharded by
+top-level children (lrm_oct_sharded): rank r refines children c with c % N == r.
 The CPU check runs the oracle (all host threads) on a random sample of poses of rank 0's slab.
 """
 import argparse, json, os, sys, time
@@ -58,14 +60,17 @@ lrm = lrm_loader.load()
 from importlib import import_module
 slabs = import_module("lrm_b200.slabs")
 
+fixtures = import_module("lrm_b200.fixtures")
 n_map = map_shape[0] * map_shape[1]
-d_terr = torch.empty((n_map, 3), dtype=torch.float32, device=dev)
 gen_s = 0.0
 if rank == 0:
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    terr = terrain.perlin_terrain(map_shape)
+    d_terr = fixtures.perlin_terrain(map_shape, device=dev)   # generated on the device (60 s of numpy at 50 M points)
+    torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
-    d_terr.copy_(torch.from_numpy(terr))
+else:
+    d_terr = torch.empty((n_map, 3), dtype=torch.float32, device=dev)
 bcast_ms = 0.0
 if world > 1:
     torch.cuda.synchronize()
@@ -73,13 +78,15 @@ if world > 1:
     dist.broadcast(d_terr, src=0)          # the map is replicated once
     torch.cuda.synchronize()
     bcast_ms = (time.perf_counter() - t0) * 1e3
-    terr = d_terr.cpu().numpy()
-bodies_all = terrain.body_lattice(terr, *args.poses)
-first, count = slabs.slab_range(len(bodies_all), rank, world)
-bodies = bodies_all[first:first + count]
+d_all = fixtures.body_lattice(d_terr, *args.poses)
+n_all = int(d_all.shape[0])
+mine = slabs.dealt_chunks(n_all, rank, world, chunks_per_rank=8)
+d_bod = torch.cat([d_all[f:f + c] for f, c in mine]).contiguous()
+del d_all
+bodies = d_bod.cpu().numpy()
+terr = d_terr.cpu().numpy() if rank == 0 else None
 legs = [lrm.get_M2_leg(float(np.float32(k) * np.float32(2 * np.pi) / np.float32(args.legs))) for k in range(args.legs)]
 quats = lrm.yaw_orientations(args.yaws) if args.yaws > 0 else lrm.full_struct_orientations()
-d_bod = torch.from_numpy(bodies).to(dev)
 out, ms = lrm.positionability(d_bod, d_terr, legs, quats, pre_cull=args.pre_cull, timing=True)  # warm-up
 times = []
 for _ in range(args.reps):
@@ -90,20 +97,24 @@ for _ in range(args.reps):
     out, ms = lrm.positionability(d_bod, d_terr, legs, quats, pre_cull=args.pre_cull, timing=True)
     torch.cuda.synchronize()
     t = torch.tensor([time.perf_counter() - t0, ms], dtype=torch.float64, device=dev)
+    g = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)]
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    times.append((float(t[0]), float(t[1])))
-wall, kms = min(times)
+        dist.all_gather(g, t)
+    else:
+        g = [t]
+    times.append((max(float(x[0]) for x in g), max(float(x[1]) for x in g), min(float(x[1]) for x in g)))
+wall, kms, kms_min = min(times)
 got = out.cpu().numpy()
 standable = torch.tensor([int((got != 0).sum())], dtype=torch.int64, device=dev)
 if world > 1:
     dist.all_reduce(standable)
 if rank == 0:
-    line = {"metric": f"body poses/s ({args.legs}-leg map positionability)", "value": len(bodies_all) / wall,
+    line = {"metric": f"body poses/s ({args.legs}-leg map positionability)", "value": n_all / wall,
             "unit": "poses/s", "config": args.config or "custom",
-            "n_gpus": world, "poses": len(bodies_all), "map_points": n_map, "orientations": len(quats),
-            "legs": args.legs, "wall_ms": wall * 1e3, "kernel_ms_max": kms, "standable": int(standable.item()),
-            "pre_cull": args.pre_cull, "map_broadcast_ms": bcast_ms, "map_generation_s": round(gen_s, 1)}
+            "n_gpus": world, "poses": n_all, "map_points": n_map, "orientations": len(quats),
+            "legs": args.legs, "wall_ms": wall * 1e3, "kernel_ms_max": kms, "kernel_ms_min": kms_min,
+            "partition": "8 contiguous chunks per rank, dealt round-robin", "standable": int(standable.item()),
+            "pre_cull": args.pre_cull, "map_broadcast_ms": bcast_ms, "map_generation_s": round(gen_s, 3)}
     if args.check and not args.pre_cull:
         from oracle.oracle import PortOracle
         from tests import parity
@@ -123,23 +134,35 @@ if rank == 0:
                          "mismatches": [{"pose": [float(v) for v in bodies[idx[k]]], "b200": int(got[idx[k]]),
                                          "oracle": int(want[k])} for k in bad[:8]]}
     print(json.dumps(line), flush=True)
-    if args.oct_depth >= 0:
-        # apply_oct semantics on the whole map as footholds: shipped leg (no box can be valid, see
-        # DESIGN.md) and a wide-coxa leg (valid boxes appear once boxes are small)
-        for name, leg in (("M2_as_shipped", lrm.get_M2_leg(0.0)), ("wide_coxa", None)):
-            if leg is None:
-                a = lrm.get_M2_leg(0.0).as_array()
-                a[8], a[9] = 3.0, -3.0
-                leg = lrm.LegDimensions.from_array(a)
-            res, oms = lrm.apply_oct(d_terr, leg, max_depth=args.oct_depth, cap=1 << 20, timing=True)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            res, oms = lrm.apply_oct(d_terr, leg, max_depth=args.oct_depth, cap=1 << 20, timing=True)
-            torch.cuda.synchronize()
-            owall = time.perf_counter() - t0
+if args.oct_depth >= 0:
+    # apply_oct semantics on the whole map as footholds, sharded by top-level children: shipped leg
+    # (no box can be valid) and a wide-coxa leg (valid boxes appear once boxes are small)
+    for name, leg in (("M2_as_shipped", lrm.get_M2_leg(0.0)), ("wide_coxa", None)):
+        if leg is None:
+            a = lrm.get_M2_leg(0.0).as_array()
+            a[8], a[9] = 3.0, -3.0
+            leg = lrm.LegDimensions.from_array(a)
+        lrm.apply_oct(d_terr, leg, max_depth=args.oct_depth, cap=1 << 20, shard=rank, nshards=world)   # warm-up
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res, counts, oms = lrm.apply_oct(d_terr, leg, max_depth=args.oct_depth, cap=1 << 20, timing=True,
+                                         shard=rank, nshards=world, child_counts=True)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0, oms, float(len(res))], dtype=torch.float64, device=dev)
+        g = [torch.zeros(3, dtype=torch.float64, device=dev) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(g, t)
+        else:
+            g = [t]
+        if rank == 0:
+            owall = max(float(x[0]) for x in g)
             print(json.dumps({"metric": "apply_oct (body-space octree) wall ms", "config": args.config or "custom",
-                              "leg": name, "footholds": n_map, "max_depth": args.oct_depth,
-                              "valid_boxes": int(len(res)), "wall_ms": owall * 1e3, "kernel_ms": oms,
+                              "leg": name, "footholds": n_map, "max_depth": args.oct_depth, "n_gpus": world,
+                              "sharding": "top-level children c % N == rank (lrm_oct_sharded)",
+                              "valid_boxes": int(sum(float(x[2]) for x in g)), "wall_ms": owall * 1e3,
+                              "kernel_ms_per_rank": [round(float(x[1]), 1) for x in g],
                               "footholds_per_s": n_map / owall}), flush=True)
 if world > 1:
     dist.destroy_process_group()
