@@ -358,8 +358,13 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path); use --impl reference")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version
+    # banner at the first collective, ...) goes to stderr — fd 1 is pointed at fd 2 for the run and
+    # the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's banner / debug lines go to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -519,10 +524,13 @@ def run_b200(args):
             line["positionability"] = rec
             if rec.get("parity") and not rec["parity"]["green"]:
                 exit_code = 3
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if exit_code:
         sys.exit(exit_code)
 

@@ -36,7 +36,10 @@ constexpr bool kSkipB = LRM_SKIP_B != 0;  // skip the flipped solution by its lo
 constexpr size_t kAtlasMinPoints = size_t(1) << 22;
 std::atomic<size_t> g_fast_min_points{kAtlasMinPoints};
 // ... but once a plan's tables are cached they cost nothing: sweeps from this size on use them
-constexpr size_t kCachedMinPoints = size_t(1) << 16;
+constexpr size_t kCachedMinPoints = size_t(1) << 20;  // (measured on the reference's size sweep: the probe +
+// two gated launches cost more than they save at 256 Ki points)
+// below this, a launch is latency: the plain kernel (no staging pipeline to fill and drain)
+constexpr size_t kPlainMaxPoints = size_t(1) << 14;
 // deferred points of the fast path: entries of at most two tiles plus a partial flush block
 constexpr int kQueueCap = 2 * kTile + kThreads + 256;
 static_assert(kTile % kThreads == 0 && kTile % 16 == 0 && kTile <= 1024, "tile shape");
@@ -560,6 +563,30 @@ __device__ __noinline__ void tile_point_full(const LegPlan& L, const SectorTable
     flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
 }
 
+// both solutions through the tables for one point of the tile in shared memory, in place (a warp
+// whose points ALL lie in uncertified cubes — a sweep inside a decision surface, e.g. the
+// reference's own y = 0 benchmark slice — is dense as it stands: no ring needed); false (slot
+// untouched) if the tables cannot decide the point
+template <int MODE, bool SOA>
+__device__ __noinline__ bool tile_point_fast(const LegPlan& L, const FastView F, const AtlasView& A,
+                                             const WinnerTable& W, float* tile, uint8_t* flag, int i) {
+    float x, y, z;
+    if (SOA) {
+        x = tile[i], y = tile[kTL + i], z = tile[2 * kTL + i];
+    } else {
+        x = tile[3 * i], y = tile[3 * i + 1], z = tile[3 * i + 2];
+    }
+    DistResult r;
+    if (!dist_fast<true, false, true>(L, F, A, W, to_coxa_frame(L, x, y, z), &r)) return false;
+    if (SOA) {
+        tile[i] = r.dx, tile[kTL + i] = r.dy, tile[2 * kTL + i] = r.dz;
+    } else {
+        tile[3 * i] = r.dx, tile[3 * i + 1] = r.dy, tile[3 * i + 2] = r.dz;
+    }
+    flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
+    return true;
+}
+
 template <int MODE, bool SOA>
 __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
     one_leg_tier_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
@@ -702,6 +729,7 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
         };
         auto park = [&](int i, int why, unsigned word) {
             const uint32_t entry = (it << 15) | ((word & 31u) << 10) | (uint32_t)i;
+            // why: 3 -> ring P, 1 -> ring B, 2 -> ring C (the tables have already failed)
             if (why == 3 && rp.push(S.ring_p, &S.cnt[0][rot], entry)) return;
             if (why == 3 && ra.push(S.ring_a, &S.cnt[1][rot], entry)) return;  // P full: the explicit plane evaluation
             if (why == 1 && rb.push(S.ring_b, &S.cnt[2][rot], entry)) return;
@@ -745,9 +773,23 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
 #pragma unroll
                 for (int k = 0; k < LRM_T0_GROUP; k++)
                     if (st[k] == 0) store_pt(tid + (g + k) * kTT, r[k]);
+                // a warp that is uncertified as a whole (a sweep inside a decision surface) is dense
+                // already: the table path on the spot instead of 128 pushes into ring B, which such a
+                // sweep would only overflow.  One vote per tile.
+                bool all_b = true;
 #pragma unroll
-                for (int k = 0; k < LRM_T0_GROUP; k++)
-                    if (st[k] != 0) park(tid + (g + k) * kTT, st[k], w[g + k]);
+                for (int k = 0; k < LRM_T0_GROUP; k++) all_b = all_b && st[k] == 1;
+                if (__all_sync(0xffffffffu, all_b)) {
+#pragma unroll 1
+                    for (int k = 0; k < LRM_T0_GROUP; k++) {
+                        const int i = tid + (g + k) * kTT;
+                        if (!tile_point_fast<MODE, SOA>(L, fview, atlas, S.winners, in, flag, i)) park(i, 2, 0u);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < LRM_T0_GROUP; k++)
+                        if (st[k] != 0) park(tid + (g + k) * kTT, st[k], w[g + k]);
+                }
             }
         } else {
 #pragma unroll 1
@@ -1438,7 +1480,8 @@ int set_skeleton(int on) {
 cudaError_t launch_one_leg_aos(int mode, const LegPlan& plan, const float* xyz, float* out_vec,
                                uint8_t* flag, size_t n, cudaStream_t stream, size_t n_call) {
     if (n == 0) return cudaSuccess;
-    const bool bulk_ok = aligned16(xyz) && aligned16(out_vec) && aligned16(flag);
+    const bool bulk_ok = aligned16(xyz) && aligned16(out_vec) && aligned16(flag) &&
+                         (n_call > n ? n_call : n) >= kPlainMaxPoints;
     switch (mode) {
         case kModeReach:
             return bulk_ok ? launch_stream<kModeReach, false>(plan, xyz, nullptr, nullptr, nullptr,

@@ -270,6 +270,24 @@ def test_fast_path_parity_on_large_sweeps(lrm, oracle, sweep):
         _sample_check(lrm, oracle, pts, lrm.get_leg(robot, az), q, f"fast robot{robot} az{az}")
 
 
+def test_reference_bench_slice_at_scale(lrm, oracle, sweep):
+    """The reference's own benchmark shape (bench.cpp:109-120: the y = 0 slice, x in [-100, 601],
+    z in [-100, 51], float-accumulated arange) at 16.5 M points: every point lies IN a decision
+    surface of the yaw tests (y = +0), so no cube of the choice volume is certified — the tiered
+    sweep takes its whole-warp table path, the two-tier sweep its full redo; both must meet the bars."""
+    def arange32(start, end, step):
+        out, v, step = [], np.float32(start), np.float32(step)
+        while v <= np.float32(end):
+            out.append(v)
+            v = np.float32(v + step)
+        return np.array(out, np.float32)
+    xs, zs = arange32(-100, 601, 0.08), arange32(-100, 51, 0.08)
+    X, Z = np.meshgrid(xs, zs, indexing="ij")
+    pts = np.ascontiguousarray(np.stack([X, np.zeros_like(X), Z], -1).reshape(-1, 3), np.float32)
+    assert len(pts) == 16_544_544
+    _sample_check(lrm, oracle, torch.from_numpy(pts).cuda(), lrm.get_M2_leg(0.0), None, "bench slice", n_sample=200_000)
+
+
 def test_fast_path_with_every_point_parked(lrm, oracle, sweep):
     """Points on / next to the coxa axis and on the yaw seam cannot be certified: the whole sweep
     goes through the deferred redo (ring wrap-around, partial last block, drain at the end)."""

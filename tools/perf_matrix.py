@@ -17,7 +17,7 @@ libs = {"product": None}
 for f in sorted(os.listdir(var)) if os.path.isdir(var) else []:
     if f.startswith("liblrm_") and f.endswith(".so") and "skel" not in f:
         libs[f[len("liblrm_"):-3]] = os.path.join(var, f)
-shapes = [("3", "512", "0"), ("3", "512", "1"), ("2.5", "640", "0"), ("2", "768", "0"), ("4", "384", "0")]
+shapes = [("3", "512", "0")]
 rows = []
 for name, lib in libs.items():
     for cell, dim, kern in (shapes if name == "product" else shapes[:1]):
