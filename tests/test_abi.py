@@ -191,3 +191,12 @@ def test_reference_call_sites_compile_against_the_shim(lrm, tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
 
 
+
+
+def test_library_reads_no_environment():
+    """Tuning knobs are ABI options (lrm_set_option): no getenv anywhere in the product sources, so
+    no environment variable of the caller's process can change which kernel runs."""
+    src = os.path.join(ROOT, "legged-robot-movability-cuda_b200", "csrc")
+    for name in os.listdir(src):
+        text = open(os.path.join(src, name)).read()
+        assert "getenv" not in text, name
