@@ -16,6 +16,10 @@
  *     asynchronous on `stream` unless kernel_ms is requested (then it synchronises the stream).
  *     on_device == 0: pointers are host pointers; the library stages through device memory
  *     (alloc, H2D, kernel, D2H, free — the contract of apply_kernel, cross_compiled.cu:34-79).
+ *   - out_xyz may be the very buffer xyz (an in-place call): every sweep reads a point before it
+ *     writes that point's vector, and points that are finished late (the rings of the large sweeps)
+ *     are re-read from an input their tile's store has left unchanged.  Partially overlapping
+ *     buffers are not supported.
  *   - kernel_ms (may be NULL) receives the cudaEvent time of the kernel(s) only — the number the
  *     reference's apply_kernel returns (cross_compiled.cu:58-65).
  *   - return value: 0 on success, negative lrm_status otherwise; lrm_last_error() gives the text.

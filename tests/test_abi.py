@@ -200,3 +200,21 @@ def test_library_reads_no_environment():
     for name in os.listdir(src):
         text = open(os.path.join(src, name)).read()
         assert "getenv" not in text, name
+
+
+def test_options_are_validated(lrm):
+    """lrm_set_option / lrm_get_stat need no GPU: unknown names and out-of-range values are refused,
+    a valid set returns the previous value."""
+    with pytest.raises(lrm.LrmError):
+        lrm.set_option("no_such_option", 1)
+    with pytest.raises(lrm.LrmError):
+        lrm.set_option("sweep", 7)
+    with pytest.raises(lrm.LrmError):
+        lrm.set_option("volume_dim", 510)       # not a multiple of 4
+    with pytest.raises(lrm.LrmError):
+        lrm.set_option("skeleton", 1)           # measurement builds only
+    with pytest.raises(lrm.LrmError):
+        lrm.get_stat("no_such_stat")
+    assert lrm.set_option("tier_chunk_shift", 3) == 3
+    assert lrm.set_option("volume_cell_mm", 2.5) == 3.0 and lrm.set_option("volume_cell_mm", 3.0) == 2.5
+    assert lrm.get_stat("volume_dim") == 512 and lrm.get_stat("table_builds") >= 0

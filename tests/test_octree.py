@@ -66,13 +66,25 @@ def test_gpu_octree_matches_oracle(lrm, port):
     for depth in (1, 3, 5, 6):
         want = port.apply_oct(terr, wide, depth)
         got = lrm.apply_oct(torch.from_numpy(terr).cuda(), leg, depth)
-        ws, gs = {tuple(r) for r in want.tolist()}, {tuple(r) for r in got.tolist()}
-        # box flags hinge on exact comparisons of distance vectors with box half-extents: allow a
-        # small symmetric difference, require the bulk (and the traversal order of the common part)
-        assert len(ws ^ gs) <= max(1, len(ws) // 20), (depth, len(ws), len(gs), len(ws ^ gs))
-        common_w = [tuple(r) for r in want.tolist() if tuple(r) in gs]
-        common_g = [tuple(r) for r in got.tolist() if tuple(r) in ws]
-        assert common_w == common_g
+        # the predicate is pinned to the reference's own kernel child by child
+        # (tests/test_refgpu_pin.py); the whole tree must therefore equal the restatement's: same
+        # boxes, same traversal order.  A box may only differ where one of its (foothold, sample,
+        # leg) distance vectors ties with a box half-extent to the last float32 bit — such a box
+        # is reported, and must be re-decided identically by the restatement for a foothold set
+        # nudged by 1e-3 mm (the flag band of the parity protocol); anything else fails.
+        if not np.array_equal(want, got):
+            ws, gs = {tuple(r) for r in want.tolist()}, {tuple(r) for r in got.tolist()}
+            nudged = set()
+            for d in (-1e-3, 1e-3):
+                for ax in range(3):
+                    t2 = terr.copy()
+                    t2[:, ax] += np.float32(d)
+                    nudged |= {tuple(r) for r in port.apply_oct(t2, wide, depth).tolist()} ^ ws
+            assert (ws ^ gs) <= nudged, (depth, len(ws), len(gs), sorted(ws ^ gs)[:4])
+            assert len(ws ^ gs) <= 2, (depth, len(ws ^ gs))
+            common_w = [tuple(r) for r in want.tolist() if tuple(r) in gs]
+            common_g = [tuple(r) for r in got.tolist() if tuple(r) in ws]
+            assert common_w == common_g
     # host-pointer path and the shipped configuration (empty result)
     got_h = lrm.apply_oct(terr, leg, 5)
     assert len(got_h) == len(lrm.apply_oct(torch.from_numpy(terr).cuda(), leg, 5))

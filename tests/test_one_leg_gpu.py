@@ -119,8 +119,12 @@ def test_ragged_sizes(lrm, oracle, n):
     dev = torch.from_numpy(pts).cuda()
     fr, vec = lrm.reach_dist(dev, leg)
     torch.cuda.synchronize()
-    assert (fr.cpu().numpy() != want_r).sum() <= 1
-    assert (np.abs(vec.cpu().numpy() - want_d).max(axis=1) > 1e-2).sum() <= max(1, n // 2000)
+    # every difference must be EXPLAINED: a flag only within 1e-3 mm of the boundary, a vector only
+    # on a seam of the reference's own piecewise field (tests/parity.py)
+    rep = parity.flag_report(pts, fr.cpu().numpy(), want_r, lambda p: oracle.reach(p, la))
+    assert rep["unexplained"] == 0 and rep["mismatch"] <= 1, rep
+    rep = parity.dist_report(pts, vec.cpu().numpy(), want_d, lambda p: oracle.dist(p, la)[0])
+    assert rep["unexplained"] == 0 and rep["over_tol"] <= max(1, n // 2000), rep
     # host-pointer path
     fr_h, vec_h = lrm.reach_dist(pts, leg)
     assert np.array_equal(fr_h, fr.cpu().numpy()) and np.array_equal(vec_h, vec.cpu().numpy())
@@ -419,13 +423,41 @@ def test_hexapod_legs_stay_cached(lrm):
         assert torch.equal(a, b)
 
 
-def test_options_are_validated(lrm):
-    with pytest.raises(lrm.LrmError):
-        lrm.set_option("no_such_option", 1)
-    with pytest.raises(lrm.LrmError):
-        lrm.set_option("sweep", 7)
-    with pytest.raises(lrm.LrmError):
-        lrm.set_option("volume_dim", 510)       # not a multiple of 4
-    with pytest.raises(lrm.LrmError):
-        lrm.set_option("skeleton", 1)           # measurement builds only
-    assert lrm.set_option("tier_chunk_shift", 3) == 3
+
+
+@pytest.mark.parametrize("n", [777, 40_000, 300_000])
+def test_in_place_calls_at_every_size_class(lrm, n):
+    """out_xyz == xyz (lrm_c.h allows it) through the plain kernel (< 16 Ki points), the staged
+    kernel, and — tables cached by an earlier large call — the table sweeps."""
+    g = torch.Generator(device="cuda").manual_seed(n)
+    pts = torch.rand((n, 3), device="cuda", generator=g) * 900.0 - 300.0
+    leg = lrm.get_M2_leg(0.0)
+    want, wf = lrm.distance(pts, leg)
+    buf = pts.clone()
+    got, gf = lrm.distance(buf, leg, out=buf)
+    assert got.data_ptr() == buf.data_ptr()
+    assert torch.equal(got, want) and torch.equal(gf, wf)
+
+
+def test_two_devices_keep_separate_table_caches(lrm):
+    """One process driving two GPUs: each device keeps its own LRU of plans, a sweep on
+    one never evicts or rebuilds the other's tables, and tensors are launched on their own device
+    whatever the current device is."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = 4 * (1 << 20) + 5
+    legs = [lrm.get_leg(r, az) for r in (1, 0) for az in (0.0, 0.9, 1.8)]
+    pts = [torch.rand((n, 3), device=f"cuda:{d}", generator=torch.Generator(device=f"cuda:{d}").manual_seed(3)) * 900 - 300
+           for d in (0, 1)]
+    first = [[lrm.distance(pts[d], leg)[0] for leg in legs] for d in (0, 1)]       # current device stays cuda:0
+    for d in (0, 1):
+        torch.cuda.synchronize(d)
+    builds = lrm.get_stat("table_builds")
+    second = [[lrm.distance(pts[d], leg)[0] for leg in legs] for d in (1, 0)][::-1]
+    for d in (0, 1):
+        torch.cuda.synchronize(d)
+    assert lrm.get_stat("table_builds") == builds          # 6 plans per device fit its own 8 entries
+    for d in (0, 1):
+        for a, b in zip(first[d], second[d]):
+            assert a.device.index == d and torch.equal(a, b)
+    assert torch.equal(first[0][0].cpu(), first[1][0].cpu())
