@@ -268,6 +268,14 @@ constexpr int kMaxDevices = 64;
 std::vector<Entry*> g_cache[kMaxDevices];
 unsigned long long g_clock = 0;
 std::mutex g_mutex;
+// The volume is built in the BACKGROUND while sweeps of the same plan keep running (two-tier sweep,
+// same bits): a build that fills every SM (16 CTAs of 128 threads each) finishes in 40 ms but
+// slows the foreground sweeps of those 40 ms by 50 x (measured: 0.5 ms -> 28-87 ms per call); with
+// a few CTAs per SM the build takes longer and the foreground keeps most of the registers.
+#ifndef LRM_VOL_BUILD_CTAS
+#define LRM_VOL_BUILD_CTAS 3
+#endif
+constexpr int kVolBuildCtasPerSm = LRM_VOL_BUILD_CTAS;
 std::atomic<int> g_vol_dim{512};
 std::atomic<float> g_vol_cell{3.0f};
 std::atomic<unsigned long long> g_builds{0};  // atlas builds since the library was loaded (diagnostics / tests)
@@ -454,11 +462,11 @@ cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, Volu
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, hit->device);
         // the block map lives behind the texels in the same staging allocation
         unsigned char* block_done = reinterpret_cast<unsigned char*>(hit->vol_linear + cubes);
-        volume_coarse_kernel<<<sms * 8, 128, 0, hit->vol_stream>>>(hit->plan, hit->tables, hit->vol_linear, block_done,
+        volume_coarse_kernel<<<sms * kVolBuildCtasPerSm, 128, 0, hit->vol_stream>>>(hit->plan, hit->tables, hit->vol_linear, block_done,
                                                                   dim, cell);
         AtlasView atlas{};
         fill_view(hit, &atlas);
-        volume_build_kernel<<<sms * 16, 128, 0, hit->vol_stream>>>(hit->plan, hit->tables, atlas, hit->vol_linear,
+        volume_build_kernel<<<sms * kVolBuildCtasPerSm, 128, 0, hit->vol_stream>>>(hit->plan, hit->tables, atlas, hit->vol_linear,
                                                                    block_done, dim, cell);
         e = cudaGetLastError();
         if (e == cudaSuccess) {

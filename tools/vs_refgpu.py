@@ -160,6 +160,12 @@ def _one_leg():
         # device-resident, one launch, kernel-only time: what apply_kernel's return value measures
         import torch
         d_pts = torch.from_numpy(pts).cuda()
+        # steady state: the first calls of a new leg build its tables (the choice volume in the
+        # background, which slows the foreground sweeps of those ~100 ms: tools/first_calls.py)
+        lrm.reachability(d_pts, leg)
+        lrm.distance(d_pts, leg)
+        torch.cuda.synchronize()
+        time.sleep(0.6)
         r_us, t_r = None, 1e30
         for _ in range(4):
             r_us, t = lrm.reachability(d_pts, leg, timing=True)
