@@ -12,8 +12,13 @@
  *   - flags are one byte per element, 0 or 1 (the layout of Array<bool>).
  *   - quat is the body orientation in the reference's storage (settings.h:51 quatTest,
  *     unified_math_cuda.cu.h:13-27): {1,0,0,0} is the identity.  NULL means identity.
- *   - on_device != 0: all data pointers are device pointers on the current device, the call is
- *     asynchronous on `stream` unless kernel_ms is requested (then it synchronises the stream).
+ *   - on_device != 0: all data pointers are device pointers on the current device.  The one-leg
+ *     entry points (lrm_reach, lrm_dist, lrm_reach_dist(_soa), lrm_forward_kine, lrm_recurs,
+ *     lrm_make_lattice) are asynchronous on `stream` unless kernel_ms is requested (then they
+ *     synchronise the stream) — also on the first call of a new (leg, orientation), whose certified
+ *     tables are built on `stream`, and when a cached plan is evicted (the rebuild is ordered behind
+ *     the victim's recorded uses by events).  lrm_positionability, lrm_oct* build per-call scratch
+ *     (the cell grid of the map) and return when their work on `stream` has finished.
  *     on_device == 0: pointers are host pointers; the library stages through device memory
  *     (alloc, H2D, kernel, D2H, free — the contract of apply_kernel, cross_compiled.cu:34-79).
  *   - out_xyz may be the very buffer xyz (an in-place call): every sweep reads a point before it
@@ -157,7 +162,9 @@ LRM_API int lrm_rpy_to_quat(float roll, float pitch, float yaw, float out_quat4[
  * body position bodies[b] passes the cull cylinders and EVERY leg reaches at least one map point
  * (reachable_rotate_leg, several_leg.cu:48-67); 0 if none.  The reference hard-codes 4 legs
  * (several_leg.cu:681-697); nlegs is free here (hexapod = 6).
- * bodies: nb x 3, map: nt x 3 (device pointers when on_device). */
+ * bodies: nb x 3, map: nt x 3 (device pointers when on_device).  Unlike the one-leg sweeps this
+ * call returns only when the search has finished on `stream` (its per-call scratch — the cell grid
+ * of the map, the plans — is released on return). */
 LRM_API int lrm_positionability(const float* bodies, size_t nb, const float* map, size_t nt,
                         const lrm_leg_t* legs, int nlegs, const float* quats, int nq,
                         const lrm_posit_opts_t* opts, uint8_t* standable, int on_device,

@@ -189,7 +189,7 @@ void settle_volume(Entry* c) {
         cudaEventSynchronize(c->vol_done);
         c->vol_building = false;
     }
-    if (c->vol_linear) cudaFree(c->vol_linear);
+    if (c->vol_linear) cudaFreeAsync(c->vol_linear, c->vol_stream);
     c->vol_linear = nullptr;
 }
 void release_volume(Entry* c) {
@@ -456,7 +456,9 @@ cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, Volu
         e = cudaStreamWaitEvent(hit->vol_stream, hit->ready, 0);
         if (e != cudaSuccess) return e;
         const size_t cubes = (size_t)dim * dim * dim;
-        e = cudaMalloc((void**)&hit->vol_linear, cubes * sizeof(unsigned short) + cubes / 64 + 64);
+        // stream-ordered allocation on the build's own stream: freeing it later (cudaFreeAsync) does
+        // not synchronise the device the way cudaFree does
+        e = cudaMallocAsync((void**)&hit->vol_linear, cubes * sizeof(unsigned short) + cubes / 64 + 64, hit->vol_stream);
         if (e != cudaSuccess) return e;
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, hit->device);
@@ -480,8 +482,8 @@ cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, Volu
         }
         if (e == cudaSuccess) e = cudaEventRecord(hit->vol_done, hit->vol_stream);
         if (e != cudaSuccess) {
+            cudaFreeAsync(hit->vol_linear, hit->vol_stream);
             cudaStreamSynchronize(hit->vol_stream);
-            cudaFree(hit->vol_linear);
             hit->vol_linear = nullptr;
             return e;
         }
@@ -497,7 +499,7 @@ cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, Volu
         if (e != cudaSuccess) return e;
         hit->vol_building = false;
         hit->vol_ready = true;
-        cudaFree(hit->vol_linear);
+        cudaFreeAsync(hit->vol_linear, hit->vol_stream);
         hit->vol_linear = nullptr;
     }
     (void)stream;  // vol_done has completed on the host's clock: no device-side wait needed
