@@ -25,6 +25,28 @@ def test_slab_ranges_partition_exactly(lrm):
         slabs.slab_range(10, 2, 2)
 
 
+def test_dealt_chunks_partition_exactly(lrm):
+    """dealt_chunks: world x chunks_per_rank contiguous chunks dealt round-robin; over all ranks
+    they partition [0, n) exactly, and every rank's share differs by at most chunks_per_rank units."""
+    from importlib import import_module
+    slabs = import_module("lrm_b200.slabs")
+    for n in (0, 5, 1000, 16_777_216):
+        for world in (1, 2, 8):
+            parts = [slabs.dealt_chunks(n, r, world, chunks_per_rank=8) for r in range(world)]
+            spans = sorted(sum(parts, []))
+            pos = 0
+            for f, c in spans:
+                assert f == pos
+                pos += c
+            assert pos == n
+            sizes = [sum(c for _, c in p) for p in parts]
+            assert max(sizes) - min(sizes) <= 8
+            for p in parts:
+                assert p == sorted(p)
+    with pytest.raises(ValueError):
+        slabs.dealt_chunks(10, 2, 2)
+
+
 def test_two_rank_gloo_job_covers_the_lattice():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
