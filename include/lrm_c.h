@@ -89,12 +89,16 @@ LRM_API size_t lrm_set_fast_path_min_points(size_t n);
  *                           on the device by a coherence probe of the input
  *   "tier_chunk_shift"      log2 of the consecutive tiles a CTA of the tiered sweep takes (default 3)
  *   "volume_cell_mm", "volume_dim"   cube size and cubes per side of choice volumes built from now
- *                           on (default 3 mm x 512: 268 MB per cached plan)
+ *                           on (default 3 mm x 512: 537 MB per cached plan)
+ *   "volume_bricks"         1 (default): cubes the grid cannot settle carry a brick of 4^3 fine cubes
+ *                           (up to 1.4 GB more per cached plan at the default shape); 0: coarse grid only
  *   "staging_chunk_points"  points per chunk of the host-pointer pipeline (default 2 Mi)
  *   "skeleton"              measurement builds only (LRM_ERR_UNSUPPORTED otherwise) */
 LRM_API int lrm_set_option(const char* name, double value, double* previous);
 /* Counters: "table_builds" (plane-atlas builds since the library was loaded: a cached plan builds
- * nothing), "volume_cell_mm", "volume_dim". */
+ * nothing), "volume_builds" (background builds of a choice volume that a later sweep found finished),
+ * "volume_cell_mm", "volume_dim", "volume_bricks" / "volume_brick_capacity" (bricks the last finished
+ * volume build asked for / the size of its pool). */
 LRM_API int lrm_get_stat(const char* name, double* value);
 LRM_API int lrm_device_count(void);
 LRM_API int lrm_set_device(int device);

@@ -58,15 +58,18 @@ void release_tables(TableLease* lease, cudaStream_t stream);
 // true if acquire_tables(plan) would build nothing on the current device
 bool tables_cached(const LegPlan& plan);
 
-// Choice volume of a leased plan: 3-D texture of 16-bit texels (winning coxa solution + plane label
-// per cube, plane_atlas.cu).  Built in the background on first request: until it is there the call
+// Choice volume of a leased plan: 3-D texture of 32-bit texels (winning coxa solution + plane label
+// per cube, or a pointer to a brick of 4^3 fine cubes, plane_atlas.cu).  Built in the background on first request: until it is there the call
 // returns cudaErrorNotReady (wait = false) or blocks (wait = true).
 struct VolumeView;
 cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, VolumeView* view, bool wait);
 // cube size (mm) and cubes per side (multiple of 4) of volumes built from now on; -1 if out of range
 int set_choice_volume_shape(float cell_mm, int dim);
 void get_choice_volume_shape(float* cell_mm, int* dim);
+int set_volume_bricks(int on);                               // bricks under uncertified cubes; returns the previous value
+void get_brick_stats(unsigned* used, unsigned* capacity);    // of the last finished volume build
 unsigned long long table_builds();  // atlas builds since load (diagnostics)
+unsigned long long volume_builds_done();  // choice-volume builds a sweep has seen finished since load
 
 // Multi-leg positionability (positionability.cu).  All pointers are device pointers.
 struct PositParams {

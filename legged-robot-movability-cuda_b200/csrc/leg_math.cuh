@@ -423,6 +423,38 @@ LRM_HD float angle_margin(const AngleTest& t, float X, float Y) {
     return fminf(fabsf(cr), fabsf(Y));               // ... or to the X axis, where `up` flips
 }
 
+// Winner: the projection on circle (c, r); rival: corner K of the workspace.  plane_clamp lets the
+// corner take over when  best_abs^2 > |P - K|^2  (one_leg.cu:109-118).  For a corner ON the circle
+// (|K - c| = r), with v = P - c and u = (K - c) / r:
+//     |P - K|^2 - (r - |v|)^2  =  2 r s(P),     s(P) = |v| - v . u  >=  0,
+// so the corner wins nowhere, and float rounding can only flip the comparison where 2 r s is tiny —
+// next to the normal through the corner.  |grad s| = |v / |v| - u| =: chord, and chord changes by at
+// most 2 rho / (|v| - rho) within distance rho, hence inside the ball B(P, rho)
+//     s  >=  s(P) - rho (chord(P) + 2 rho / m'),        m' = |v| - rho_cap,  rho <= rho_cap.
+// Returns the largest such rho (capped) for which 2 r s stays above the rounding noise of both sides
+// — (r - |v|)^2 through an approximate rsqrt, |P - K|^2, and the corner being off the circle by a few
+// ulp — or 0 if the corner is not on the circle or P is too close to the ray.
+LRM_HD float corner_on_circle_safety(float cx, float cy, float r, float kx, float ky, float X, float Y, float ckey) {
+    const float ux = kx - cx, uy = ky - cy;
+    const float ru = sqrtf(fmaf(ux, ux, uy * uy));
+    const float off = fabsf(ru - r);
+    if (!(off < 1.0e-3f) || !(r > 1.f)) return 0.f;
+    const float vx = X - cx, vy = Y - cy;
+    const float m = sqrtf(fmaf(vx, vx, vy * vy));
+    const float cap = fminf(0.125f * m, 8.f);
+    const float mp = m - cap;
+    if (!(mp > 1.f)) return 0.f;
+    const float s = m - fmaf(vx, ux, vy * uy) / ru;
+    // noise: both squares (relative 4e-7 of (m + r)^2 covers a 3-ulp rsqrt), the corner off the
+    // circle, a floor; then as a bound on s, plus the rounding of s itself
+    const float tau = 4.0e-7f * (m + r) * (m + r) + 2.f * (ckey + cap) * (off + 2.0e-5f) + 0.02f;
+    const float sp = s - (tau / (2.f * r) + 1.0e-6f * m + 1.0e-4f);
+    if (!(sp > 0.f)) return 0.f;
+    const float chord = sqrtf(2.f * s / m) * 1.001f;
+    const float rho = 0.25f * mp * (sqrtf(fmaf(chord, chord, 8.f * sp / mp)) - chord);
+    return fminf(cap, 0.98f * rho);
+}
+
 // plane_clamp<false> instrumented: same arithmetic, plus the distance within which every decision
 // THAT CAN CHANGE THE OUTCOME keeps its sign:
 //   * the sector tests that select the circle set (middle, and the saturation test of this side);
@@ -432,6 +464,9 @@ LRM_HD float angle_margin(const AngleTest& t, float X, float Y) {
 //     (when P is invalid) and any circle that is, or within the cell could become, a candidate
 //     (a circle that is robustly NOT a candidate needs no lead; one that is far behind needs no
 //     robust candidacy).  Every distance involved is 1-Lipschitz, hence the factor 1/2 on leads.
+// LABEL = false: only valid / valid_safety are wanted (the reach bits and the choice certificate of
+// the volume build): the winner analysis is skipped, `safety` is not meaningful.
+template <bool LABEL = true>
 LRM_HD PlaneProbe plane_probe(const LegPlan& L, const SectorTable& tab, float X, float Y) {
     const float upf = up_flag(Y);
     const bool upper = angle_gt(L.middle, X, Y, upf);
@@ -482,6 +517,13 @@ LRM_HD PlaneProbe plane_probe(const LegPlan& L, const SectorTable& tab, float X,
     }
     safety = fminf(safety, valid ? valid_margin : invalid_margin);
     const float valid_safety = safety;  // sector tests, circle centres, validity: all reach needs
+    if (!LABEL) {
+        PlaneProbe early;
+        early.label = (valid ? 0x40 : 0) | (s << 4) | kAtlasNone;
+        early.safety = 0.f;
+        early.valid_safety = valid_safety;
+        return early;
+    }
     // winner
     int win = kAtlasNone;
     float best = 3.0e38f;
@@ -504,7 +546,15 @@ LRM_HD PlaneProbe plane_probe(const LegPlan& L, const SectorTable& tab, float X,
     }
     if (!valid)
         for (int i = 0; i < L.n_corners; i++)
-            if (4 + i != win) safety = fminf(safety, 0.5f * (ckey[i] - best));
+            if (4 + i != win) {
+                float lead = 0.5f * (ckey[i] - best);
+                // A corner that lies ON the winning circle (an end of one of its arcs) can never be
+                // nearer than the projection on that circle, but its lead over it only grows with the
+                // SQUARE of the distance from the normal through the corner: half the lead certifies
+                // nothing for centimetres around that ray.  Certify the comparison itself instead.
+                if (win < 4 && lead < 8.f) lead = fmaxf(lead, corner_on_circle_safety(cx[win], cy[win], r[win], L.corner_x[i], L.corner_y[i], X, Y, ckey[i]));
+                safety = fminf(safety, lead);
+            }
     if (win >= 4 && win != kAtlasNone) safety = fminf(safety, best - 0.01f);  // keep off the corner itself
     if (win == kAtlasNone) safety = fminf(safety, 0.f);  // "nothing qualifies" is never certified
     PlaneProbe out;
@@ -882,9 +932,10 @@ constexpr unsigned kVolPure = 0x80u;
 // cube (bit 5), and its value (bit 6) — the reach-only sweep reads nothing else for such a point
 constexpr unsigned kVolReachKnown = 0x20u, kVolReachValue = 0x40u;
 struct VolumeView {
-    cudaTextureObject_t tex;  // 3-D texture of cube bytes (point sampling, border = 0)
+    cudaTextureObject_t tex;  // 3-D texture of 32-bit cube texels (point sampling, border = 0)
     float inv_cell, o, oy;    // cube coordinates = p * inv_cell + o (x, z), + oy (y)
     int dim;
+    const unsigned short* bricks;  // fine texels of the bricks, 64 per brick (x fastest); nullptr: none
 };
 // The grid is shifted by half a cube along y: the y = 0 plane (a decision boundary for every leg:
 // the sign of y picks the coxa limit of the limit-plane rule, and carries atan2f's signed-zero
@@ -918,9 +969,9 @@ LRM_HD ChoiceProbe choice_probe(const LegPlan& L, const SectorTable& tab, const 
     // the chosen one stays strictly nearer ...  (0.05 mm: float rounding of both lengths)
     float m = 0.5f * (no - nc) - 0.05f;
     // ... or stays valid with an unsaturated yaw: res = true decides for it whatever the lengths
-    if (!c_sat && c_valid) m = fmaxf(m, plane_probe(L, tab, Xc, p.z).valid_safety - 0.01f);
+    if (!c_sat && c_valid) m = fmaxf(m, plane_probe<false>(L, tab, Xc, p.z).valid_safety - 0.01f);
     // the other one must not turn res = true anywhere nearby
-    if (!o_sat) m = o_valid ? -1.f : fminf(m, plane_probe(L, tab, Xo, p.z).valid_safety - 0.01f);
+    if (!o_sat) m = o_valid ? -1.f : fminf(m, plane_probe<false>(L, tab, Xo, p.z).valid_safety - 0.01f);
     out.margin = m;
     return out;
 }
@@ -943,12 +994,15 @@ LRM_HD float vol_pad(float h) {
     // coordinate itself is far below 0.01 mm
     return h * (1.f / 64.f) + 0.01f;
 }
+// pad_h (all cube functions): the cube size whose texture-coordinate slack applies — the cube's own
+// (0: a cube of the coarse grid), or the coarse cube's for a fine cube of a brick (the sweep finds the
+// brick through the coarse texel fetch).
 LRM_HD CellFirst choice_cell_first(const LegPlan& L, const SectorTable& tab, const FastTables& FT, float x0,
-                                   float y0, float z0, float h) {
+                                   float y0, float z0, float h, float pad_h = 0.f) {
     CellFirst out;
     out.byte = 0u, out.refine = false, out.direct = true;
     out.reach = 0u, out.reach_refine = false, out.reach_flip = false;
-    const float pad = vol_pad(h);
+    const float pad = vol_pad(pad_h > 0.f ? pad_h : h);
     const float xa = x0 - pad, xb = x0 + h + pad, ya = y0 - pad, yb = y0 + h + pad;
     if (ya <= 0.f && yb >= 0.f) return out;
     const int combo = yaw_combo(L, xa, ya);
@@ -967,7 +1021,7 @@ LRM_HD CellFirst choice_cell_first(const LegPlan& L, const SectorTable& tab, con
             const float side = h + 2.f * pad, hs = 0.5f * side;
             const float cx = xa + hs, cy = ya + hs, cz = z0 - pad + hs;
             const float rho = sqrtf(fmaf(cx, cx, cy * cy));
-            const PlaneProbe pr = plane_probe(L, tab, (out.reach_flip ? -rho : rho) - L.coxa_length, cz);
+            const PlaneProbe pr = plane_probe<false>(L, tab, (out.reach_flip ? -rho : rho) - L.coxa_length, cz);
             const unsigned bits = kVolReachKnown | ((pr.label & 0x40) ? kVolReachValue : 0u);
             if (pr.valid_safety > 0.8660255f * side + 0.01f) {
                 out.reach = bits;
@@ -1003,8 +1057,8 @@ LRM_HD CellFirst choice_cell_first(const LegPlan& L, const SectorTable& tab, con
     return out;
 }
 LRM_HD bool choice_cell_sub(const LegPlan& L, const SectorTable& tab, float x0, float y0, float z0, float h,
-                            int k, bool direct) {
-    const float pad = vol_pad(h);
+                            int k, bool direct, float pad_h = 0.f) {
+    const float pad = vol_pad(pad_h > 0.f ? pad_h : h);
     const float side = h + 2.f * pad;
     const float sub = side * (1.f / kVolSub), r1 = 0.8660255f * sub;
     CoxaPoint q;
@@ -1016,27 +1070,27 @@ LRM_HD bool choice_cell_sub(const LegPlan& L, const SectorTable& tab, float x0, 
 }
 // sub-cube k of a cube whose centre left the reach bit open: same validity, safely
 LRM_HD bool reach_cell_sub(const LegPlan& L, const SectorTable& tab, float x0, float y0, float z0, float h,
-                           int k, bool flip, bool valid) {
-    const float pad = vol_pad(h);
+                           int k, bool flip, bool valid, float pad_h = 0.f) {
+    const float pad = vol_pad(pad_h > 0.f ? pad_h : h);
     const float side = h + 2.f * pad;
     const float sub = side * (1.f / kVolSub), r1 = 0.8660255f * sub;
     const float qx = x0 - pad + ((float)(k % kVolSub) + 0.5f) * sub;
     const float qy = y0 - pad + ((float)((k / kVolSub) % kVolSub) + 0.5f) * sub;
     const float qz = z0 - pad + ((float)(k / (kVolSub * kVolSub)) + 0.5f) * sub;
     const float rho = sqrtf(fmaf(qx, qx, qy * qy));
-    const PlaneProbe pr = plane_probe(L, tab, (flip ? -rho : rho) - L.coxa_length, qz);
+    const PlaneProbe pr = plane_probe<false>(L, tab, (flip ? -rho : rho) - L.coxa_length, qz);
     return ((pr.label & 0x40) != 0) == valid && pr.valid_safety > r1 + 0.01f;
 }
 LRM_HD unsigned choice_cell_byte(const LegPlan& L, const SectorTable& tab, const FastTables& FT, float x0,
-                                 float y0, float z0, float h) {
-    const CellFirst f = choice_cell_first(L, tab, FT, x0, y0, z0, h);
+                                 float y0, float z0, float h, float pad_h = 0.f) {
+    const CellFirst f = choice_cell_first(L, tab, FT, x0, y0, z0, h, pad_h);
     unsigned byte = f.byte, reach = f.reach;
     if (f.refine)
         for (int k = 0; k < kVolSub * kVolSub * kVolSub && byte; k++)
-            if (!choice_cell_sub(L, tab, x0, y0, z0, h, k, f.direct)) byte = 0u;
+            if (!choice_cell_sub(L, tab, x0, y0, z0, h, k, f.direct, pad_h)) byte = 0u;
     if (f.reach_refine)
         for (int k = 0; k < kVolSub * kVolSub * kVolSub && reach; k++)
-            if (!reach_cell_sub(L, tab, x0, y0, z0, h, k, f.reach_flip, (reach & kVolReachValue) != 0)) reach = 0u;
+            if (!reach_cell_sub(L, tab, x0, y0, z0, h, k, f.reach_flip, (reach & kVolReachValue) != 0, pad_h)) reach = 0u;
     return byte | reach;
 }
 
@@ -1084,8 +1138,8 @@ LRM_HD unsigned cube_plane_scan(const AtlasView& A, float Xc, float zc, float si
     return ref;
 }
 // Centre of the padded cube and its side, as choice_cell_first sees them.
-LRM_HD CoxaPoint cube_centre(float x0, float y0, float z0, float h, float* side) {
-    const float pad = vol_pad(h);
+LRM_HD CoxaPoint cube_centre(float x0, float y0, float z0, float h, float* side, float pad_h = 0.f) {
+    const float pad = vol_pad(pad_h > 0.f ? pad_h : h);
     *side = h + 2.f * pad;
     CoxaPoint c;
     c.x = x0 - pad + 0.5f * *side, c.y = y0 - pad + 0.5f * *side, c.z = z0 - pad + 0.5f * *side;
@@ -1106,14 +1160,67 @@ LRM_HD unsigned coarse_block_word(const LegPlan& L, const SectorTable& tab, cons
 // Whole texel of one cube, serially (host emulation; the device build splits the work):
 // probe = true certifies the plane label as the coarse pass does, false as the fine pass does.
 LRM_HD unsigned choice_cell_word(const LegPlan& L, const SectorTable& tab, const FastTables& FT, const AtlasView& A,
-                                 float x0, float y0, float z0, float h, bool probe) {
-    const unsigned lo = choice_cell_byte(L, tab, FT, x0, y0, z0, h);
+                                 float x0, float y0, float z0, float h, bool probe, float pad_h = 0.f) {
+    const unsigned lo = choice_cell_byte(L, tab, FT, x0, y0, z0, h, pad_h);
     if (!(lo & kVolPure)) return lo;
     float side;
-    const CoxaPoint c = cube_centre(x0, y0, z0, h, &side);
+    const CoxaPoint c = cube_centre(x0, y0, z0, h, &side, pad_h);
     const float Xc = solution_plane_x(L, c, (lo & 1u) != 0u);
     const unsigned hi = probe ? cube_plane_probe(L, tab, Xc, c.z, side) : cube_plane_scan(A, Xc, c.z, side);
     return lo | (hi << 8);
+}
+
+// ---- bricks: a second, finer level under the cubes the coarse grid cannot settle --------------------
+// The uncertified cubes hug the decision surfaces (shells a few cubes thick).  Such a cube can carry a
+// BRICK of 4 x 4 x 4 fine cubes (a quarter of its side), each certified on its own by the very same
+// functions: the shell that stays uncertified is four times thinner.  The coarse texel (32 bit) is
+// then not a result but a pointer: bit 31, the brick's number, the parity of the coarse cube's three
+// indices and the cube's reach bits (bits 5-6, where the reach-only sweep reads them in either kind
+// of texel).  The sweep computes the fine cube of a point with its own arithmetic; the coarse fetch
+// resolves cube coordinates to 1 / 256 of a cube, so next to a cube face the texture unit may have
+// picked the neighbour — the parity bits tell, and the point then belongs to the outermost fine cube
+// on that side.  Every fine cube is certified over its box widened by the COARSE cube's pad (pad_h),
+// which covers exactly that slack.  classic texel: bit 31 clear, low 16 bits as described above.
+constexpr unsigned kVolBrick = 0x80000000u;
+constexpr unsigned kBrickMaxCount = 1u << 26;
+constexpr int kBrickSub = 4;  // fine cubes per axis
+LRM_HD unsigned brick_texel(unsigned idx, int ix, int iy, int iz, unsigned reach_bits) {
+    return kVolBrick | ((unsigned)(ix & 1) << 28) | ((unsigned)(iy & 1) << 29) | ((unsigned)(iz & 1) << 30) |
+           (reach_bits & (kVolReachKnown | kVolReachValue)) | (idx & 31u) | ((idx >> 5) << 7);
+}
+LRM_HD unsigned brick_index(unsigned w) { return (w & 31u) | ((w >> 2) & 0x03ffffe0u); }
+// does a cube with this classic texel want a brick?  (no certified choice, or no plane label)
+LRM_HD bool brick_candidate(unsigned word) { return !(word & kVolPure) || (word >> 8) == 0u; }
+// slot (0 .. 63, x fastest) of the fine cube that holds p in the brick the coarse fetch returned
+LRM_HD unsigned brick_slot(const VolumeView& V, unsigned w, const CoxaPoint p) {
+    const float inv_f = 4.f * V.inv_cell;
+    const int fx = (int)floorf(fmaf(p.x, inv_f, 4.f * V.o)), fy = (int)floorf(fmaf(p.y, inv_f, 4.f * V.oy)),
+              fz = (int)floorf(fmaf(p.z, inv_f, 4.f * V.o));
+    // same coarse cube as the texture unit's (parity agrees): the fine index; the neighbour: the
+    // point sits within the pad of the shared face
+    const unsigned dx = ((unsigned)(fx >> 2) ^ (w >> 28)) & 1u, dy = ((unsigned)(fy >> 2) ^ (w >> 29)) & 1u,
+                   dz = ((unsigned)(fz >> 2) ^ (w >> 30)) & 1u;
+    const unsigned sx = (unsigned)fx & 3u, sy = (unsigned)fy & 3u, sz = (unsigned)fz & 3u;
+    const unsigned lx = dx ? (sx >= 2u ? 0u : 3u) : sx, ly = dy ? (sy >= 2u ? 0u : 3u) : sy,
+                   lz = dz ? (sz >= 2u ? 0u : 3u) : sz;
+    return (lz << 4) | (ly << 2) | lx;
+}
+// Classic 16-bit texel of fine cube `slot` of the brick under the coarse cube at (x0, y0, z0), side h,
+// whose own classic texel is `coarse` — serially (host emulation; the device build shares the work).
+// A coarse cube whose choice is certified hands its low byte to its fine cubes (their boxes lie inside
+// its own): only the plane label is looked for again.
+LRM_HD unsigned brick_fine_word(const LegPlan& L, const SectorTable& tab, const FastTables& FT, const AtlasView& A,
+                                unsigned coarse, float x0, float y0, float z0, float h, unsigned slot) {
+    const float hf = h * (1.f / kBrickSub);
+    const float xf = x0 + (float)(slot & 3u) * hf, yf = y0 + (float)((slot >> 2) & 3u) * hf,
+                zf = z0 + (float)(slot >> 4) * hf;
+    if (coarse & kVolPure) {
+        float side;
+        const CoxaPoint c = cube_centre(xf, yf, zf, hf, &side, h);
+        const unsigned hi = cube_plane_scan(A, solution_plane_x(L, c, (coarse & 1u) != 0u), c.z, side);
+        return (coarse & 0xffu) | (hi << 8);
+    }
+    return choice_cell_word(L, tab, FT, A, xf, yf, zf, hf, false, h);
 }
 
 // One point of a certified cube: the chosen solution only.  Same arithmetic as dist_fast for that

@@ -292,6 +292,8 @@ int lrm_set_option(const char* name, double value, double* previous) {
         prev = k == "volume_dim" ? (double)dim : (double)cell;
         if (lrm::set_choice_volume_shape(k == "volume_dim" ? cell : (float)value, k == "volume_dim" ? (int)value : dim) != 0)
             return fail(LRM_ERR_INVALID, "volume_cell_mm must be 0.5..64, volume_dim a multiple of 4 in 16..1024");
+    } else if (k == "volume_bricks") {
+        prev = lrm::set_volume_bricks(value != 0 ? 1 : 0);
     } else if (k == "staging_chunk_points") {
         if (!(value >= 4096 && value <= (double)(size_t(1) << 30)))
             return fail(LRM_ERR_INVALID, "staging_chunk_points must be 4096..2^30");
@@ -317,6 +319,12 @@ int lrm_get_stat(const char* name, double* value) {
         int dim;
         lrm::get_choice_volume_shape(&cell, &dim);
         *value = k == "volume_dim" ? (double)dim : (double)cell;
+    } else if (k == "volume_builds") {
+        *value = (double)lrm::volume_builds_done();
+    } else if (k == "volume_bricks" || k == "volume_brick_capacity") {
+        unsigned used, cap;
+        lrm::get_brick_stats(&used, &cap);
+        *value = k == "volume_bricks" ? (double)used : (double)cap;
     } else {
         return fail(LRM_ERR_INVALID, "unknown statistic: " + k);
     }

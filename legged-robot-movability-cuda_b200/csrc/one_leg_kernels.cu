@@ -260,8 +260,9 @@ __global__ void __launch_bounds__(kThreads)
                         x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
                     }
                     p[k] = to_coxa_frame(L, x, y, z);
-                    c[k] = tex3D<unsigned short>(vol.tex, fmaf(p[k].x, vol.inv_cell, vol.o),
-                                                 fmaf(p[k].y, vol.inv_cell, vol.oy), fmaf(p[k].z, vol.inv_cell, vol.o));
+                    // the reach bits sit in bits 5-6 of either kind of texel (classic or brick pointer)
+                    c[k] = tex3D<unsigned>(vol.tex, fmaf(p[k].x, vol.inv_cell, vol.o),
+                                           fmaf(p[k].y, vol.inv_cell, vol.oy), fmaf(p[k].z, vol.inv_cell, vol.o));
                 }
 #pragma unroll
                 for (int k = 0; k < kPer; k++) {
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(kThreads)
 constexpr int kTT = LRM_TIER_THREADS;  // threads per CTA
 constexpr int kTL = LRM_TIER_TILE;     // points per tile
 constexpr int kPer = kTL / kTT;        // points per thread and tile
-static_assert(kTL % kTT == 0 && kTL % 16 == 0 && kTL <= 1024 && kPer % LRM_T0_GROUP == 0, "tier tile shape");
+static_assert(kTL % kTT == 0 && kTL % 16 == 0 && kTL <= 2048 && kPer % LRM_T0_GROUP == 0, "tier tile shape");
 // Parked points come in runs (a lattice column that grazes a decision surface parks hundreds of
 // consecutive points): rings P and B hold two such tiles.  Measured at 1e9 points: 512 / 512 entries
 // 119.0, 1024 / 512 123.0, 1024 / 1024 125.0 Gpoints/s (an overflowing push falls to a slower tier).
@@ -445,8 +446,28 @@ static_assert(kTL % kTT == 0 && kTL % 16 == 0 && kTL <= 1024 && kPer % LRM_T0_GR
 #define LRM_RING_C 512
 #endif
 constexpr int kRingP = LRM_RING_P, kRingA = LRM_RING_A, kRingB = LRM_RING_B, kRingC = LRM_RING_C;  // entries (powers of two)
-// ring entry: iteration (17 bits) | cube byte bits 0-4 | index in tile (10 bits)
-constexpr int kEntryIterBits = 17;
+// ring entry: iteration (17 or 16 bits) | cube byte bits 0-4 | index in tile (10 or 11 bits)
+constexpr int kEntryIdxBits = kTL <= 1024 ? 10 : 11;
+constexpr int kEntryIterBits = 32 - 5 - kEntryIdxBits;
+
+// Classic 16-bit texels of a thread's NPT points: the coarse texel itself, or — where that is a brick
+// pointer — the fine texel of the point's fine cube (leg_math.cuh, "bricks").  One warp vote skips the
+// whole thing where no lane met a brick (most of the far field); the fine loads of a thread are
+// issued together.
+template <int NPT>
+__device__ __forceinline__ void resolve_bricks(const VolumeView& vol, const CoxaPoint* p, unsigned* w) {
+    unsigned any = 0u;
+#pragma unroll
+    for (int k = 0; k < NPT; k++) any |= w[k];
+    if (!__any_sync(0xffffffffu, (any & kVolBrick) != 0u)) return;
+    const unsigned short* src[NPT];
+#pragma unroll
+    for (int k = 0; k < NPT; k++)
+        src[k] = vol.bricks + ((size_t)brick_index(w[k]) << 6) + brick_slot(vol, w[k], p[k]);
+#pragma unroll
+    for (int k = 0; k < NPT; k++)
+        if (w[k] & kVolBrick) w[k] = __ldg(src[k]);
+}
 
 struct alignas(128) TierSmem {
     float in[3][3 * kTL];  // in-place tiles: being loaded / computed / stored
@@ -661,8 +682,8 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
 
     constexpr uint32_t kIterMask = (1u << kEntryIterBits) - 1u;
     auto global_index = [&](uint32_t entry) -> size_t {
-        const uint32_t age = (it - (entry >> 15)) & kIterMask;
-        return (size_t)tile_of(it - age) * kTL + (entry & 1023u);
+        const uint32_t age = (it - (entry >> (5 + kEntryIdxBits))) & kIterMask;
+        return (size_t)tile_of(it - age) * kTL + (entry & ((1u << kEntryIdxBits) - 1u));
     };
     auto do_c = [&](uint32_t entry) { redo_full<MODE, SOA>(L, S.table, io, global_index(entry)); };
     auto do_b = [&](uint32_t entry) {
@@ -670,10 +691,10 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
             if (!rc.push(S.ring_c, &S.cnt[3][rot], entry)) do_c(entry);
     };
     auto do_a = [&](uint32_t entry) {
-        redo_choice<MODE, SOA>(L, S.table, sols, (entry >> 10) & 31u, io, global_index(entry));
+        redo_choice<MODE, SOA>(L, S.table, sols, (entry >> kEntryIdxBits) & 31u, io, global_index(entry));
     };
     auto do_p = [&](uint32_t entry) {
-        if (!redo_atlas<MODE, SOA>(L, sols, (entry >> 10) & 31u, atlas, S.winners, io, global_index(entry)))
+        if (!redo_atlas<MODE, SOA>(L, sols, (entry >> kEntryIdxBits) & 31u, atlas, S.winners, io, global_index(entry)))
             if (!ra.push(S.ring_a, &S.cnt[1][rot], entry)) do_a(entry);
     };
 
@@ -728,7 +749,7 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
             flag[i] = (MODE == kModeBoth ? r.reach : r.flag) ? 1 : 0;
         };
         auto park = [&](int i, int why, unsigned word) {
-            const uint32_t entry = (it << 15) | ((word & 31u) << 10) | (uint32_t)i;
+            const uint32_t entry = (it << (5 + kEntryIdxBits)) | ((word & 31u) << kEntryIdxBits) | (uint32_t)i;
             // why: 3 -> ring P, 1 -> ring B, 2 -> ring C (the tables have already failed)
             if (why == 3 && rp.push(S.ring_p, &S.cnt[0][rot], entry)) return;
             if (why == 3 && ra.push(S.ring_a, &S.cnt[1][rot], entry)) return;  // P full: the explicit plane evaluation
@@ -737,8 +758,8 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
             tile_point_full<MODE, SOA>(L, S.table, in, flag, i);
         };
         auto fetch = [&](const CoxaPoint& p) -> unsigned {
-            return tex3D<unsigned short>(vol.tex, fmaf(p.x, vol.inv_cell, vol.o), fmaf(p.y, vol.inv_cell, vol.oy),
-                                         fmaf(p.z, vol.inv_cell, vol.o));
+            return tex3D<unsigned>(vol.tex, fmaf(p.x, vol.inv_cell, vol.o), fmaf(p.y, vol.inv_cell, vol.oy),
+                                   fmaf(p.z, vol.inv_cell, vol.o));
         };
         if (skeleton) {
         } else if (cnt == (uint32_t)kTL) {
@@ -752,6 +773,7 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
                 p[k] = to_coxa_frame(L, x, y, z);
                 w[k] = fetch(p[k]);
             }
+            resolve_bricks<kPer>(vol, p, w);
 #pragma unroll
             for (int g = 0; g < kPer; g += LRM_T0_GROUP) {
                 // the limit-plane rule needs a valid plane point (bit 6 of the label): skipped when
@@ -797,7 +819,8 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
                 float x, y, z;
                 load_pt(i, x, y, z);
                 const CoxaPoint p = to_coxa_frame(L, x, y, z);
-                const unsigned w = fetch(p);
+                unsigned w = fetch(p);
+                if (w & kVolBrick) w = __ldg(vol.bricks + ((size_t)brick_index(w) << 6) + brick_slot(vol, w, p));
                 DistResult r;
                 const int st = dist_choice_label<true>(L, sols, w, S.winners, p, &r);
                 if (st == 0) store_pt(i, r);
@@ -1019,9 +1042,10 @@ __global__ void __launch_bounds__(kWW * 32, LRM_WARP_CTAS)
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             p[k] = to_coxa_frame(L, x[k], y[k], z[k]);
-            wd[k] = tex3D<unsigned short>(vol.tex, fmaf(p[k].x, vol.inv_cell, vol.o), fmaf(p[k].y, vol.inv_cell, vol.oy),
-                                          fmaf(p[k].z, vol.inv_cell, vol.o));
+            wd[k] = tex3D<unsigned>(vol.tex, fmaf(p[k].x, vol.inv_cell, vol.o), fmaf(p[k].y, vol.inv_cell, vol.oy),
+                                    fmaf(p[k].z, vol.inv_cell, vol.o));
         }
+        resolve_bricks<4>(vol, p, wd);
         DistResult r[4];
         int st[4];
         // the limit-plane rule needs a valid plane point (bit 6 of the label): skipped when no lane

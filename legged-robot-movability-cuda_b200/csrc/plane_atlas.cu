@@ -50,7 +50,7 @@ __global__ void atlas_build_kernel(const __grid_constant__ LegPlan L, unsigned c
 // cubes of the other blocks — the shells around the decision surfaces.
 __global__ void __launch_bounds__(128)
     volume_coarse_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT,
-                         unsigned short* __restrict__ linear, unsigned char* __restrict__ block_done, int dim,
+                         unsigned* __restrict__ linear, unsigned char* __restrict__ block_done, int dim,
                          float cell) {
     __shared__ SectorTable table;
     fill_sector_table(L, &table, threadIdx.x, blockDim.x);
@@ -65,27 +65,72 @@ __global__ void __launch_bounds__(128)
         const unsigned w = coarse_block_word(L, table, FT, x0, y0, z0, 4.f * cell);
         block_done[i] = w != 0u ? 1 : 0;
         if (w != 0u) {
-            const unsigned long long four = (unsigned long long)w * 0x0001000100010001ull;  // four texels along x (dim % 4 == 0)
+            const uint4 four = make_uint4(w, w, w, w);  // four texels along x (dim % 4 == 0)
             for (int dz = 0; dz < 4; dz++)
                 for (int dy = 0; dy < 4; dy++)
-                    *reinterpret_cast<unsigned long long*>(
+                    *reinterpret_cast<uint4*>(
                         linear + ((size_t)(4 * bz + dz) * dim + (size_t)(4 * by + dy)) * dim + 4 * bx) = four;
         }
     }
 }
 
-// One lane per cube of the choice volume (x fastest, like the 3-D array upload).  Cubes whose centre
-// cannot decide are refined on 4^3 sub-cubes; those cubes hug the decision surfaces (a few lanes
-// per warp), so the warp refines them one after the other with all 32 lanes, two sub-cubes each,
-// instead of leaving 29 lanes idle while three of them run 64 probes.
+// Classic texel of the cube at (x0, y0, z0), side `cell`; ALL 32 lanes of a warp call it together,
+// one cube per lane (live = false: no cube).  Cubes whose centre cannot decide are refined on 4^3
+// sub-cubes; those cubes hug the decision surfaces (a few lanes per warp), so the warp refines them
+// one after the other with all 32 lanes, two sub-cubes each, instead of leaving 29 lanes idle while
+// three of them run 64 probes.  pad_h: see choice_cell_first.
+__device__ __forceinline__ unsigned cube_word_coop(const LegPlan& L, const SectorTable& table, const FastTables& FT,
+                                                   const AtlasView& atlas, float x0, float y0, float z0, float cell,
+                                                   float pad_h, bool live, int lane) {
+    static_assert(kVolSub * kVolSub * kVolSub == 64, "two sub-cubes per lane");
+    CellFirst f;
+    f.byte = 0u, f.refine = false, f.direct = true, f.reach = 0u, f.reach_refine = false, f.reach_flip = false;
+    if (live) f = choice_cell_first(L, table, FT, x0, y0, z0, cell, pad_h);
+    unsigned need = __ballot_sync(0xffffffffu, f.refine);
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const float sx = __shfl_sync(0xffffffffu, x0, src), sy = __shfl_sync(0xffffffffu, y0, src),
+                    sz = __shfl_sync(0xffffffffu, z0, src);
+        const bool sdir = __shfl_sync(0xffffffffu, (int)f.direct, src) != 0;
+        const bool ok = choice_cell_sub(L, table, sx, sy, sz, cell, lane, sdir, pad_h) &&
+                        choice_cell_sub(L, table, sx, sy, sz, cell, lane + 32, sdir, pad_h);
+        const bool all = __all_sync(0xffffffffu, ok);
+        if (lane == src && !all) f.byte = 0u;
+    }
+    need = __ballot_sync(0xffffffffu, f.reach_refine);
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const float sx = __shfl_sync(0xffffffffu, x0, src), sy = __shfl_sync(0xffffffffu, y0, src),
+                    sz = __shfl_sync(0xffffffffu, z0, src);
+        const unsigned sbits = __shfl_sync(0xffffffffu, f.reach | (f.reach_flip ? 1u : 0u), src);
+        const bool flip = (sbits & 1u) != 0u, valid = (sbits & kVolReachValue) != 0u;
+        const bool ok = reach_cell_sub(L, table, sx, sy, sz, cell, lane, flip, valid, pad_h) &&
+                        reach_cell_sub(L, table, sx, sy, sz, cell, lane + 32, flip, valid, pad_h);
+        const bool all = __all_sync(0xffffffffu, ok);
+        if (lane == src && !all) f.reach = 0u;
+    }
+    if (!live) return 0u;
+    // plane label of the chosen solution (tier 0 of the sweep): the atlas cells under the cube's
+    // plane rectangle all carry one certified label
+    unsigned hi = 0u;
+    if (f.byte & kVolPure) {
+        float side;
+        const CoxaPoint c = cube_centre(x0, y0, z0, cell, &side, pad_h);
+        hi = cube_plane_scan(atlas, solution_plane_x(L, c, (f.byte & 1u) != 0u), c.z, side);
+    }
+    return f.byte | f.reach | (hi << 8);
+}
+
+// One lane per cube of the choice volume (x fastest, like the 3-D array upload).
 __global__ void __launch_bounds__(128)
     volume_build_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT, const AtlasView atlas,
-                        unsigned short* __restrict__ linear, const unsigned char* __restrict__ block_done, int dim,
+                        unsigned* __restrict__ linear, const unsigned char* __restrict__ block_done, int dim,
                         float cell) {
     __shared__ SectorTable table;
     fill_sector_table(L, &table, threadIdx.x, blockDim.x);
     __syncthreads();
-    static_assert(kVolSub * kVolSub * kVolSub == 64, "two sub-cubes per lane");
     const size_t total = (size_t)dim * dim * dim;
     const size_t stride = (size_t)gridDim.x * blockDim.x;  // a multiple of 32: whole warps step together
     const float half = 0.5f * (float)dim;
@@ -98,44 +143,67 @@ __global__ void __launch_bounds__(128)
         const bool live = i < total && !(block_done != nullptr &&
                                          block_done[((size_t)(iz >> 2) * (dim >> 2) + (iy >> 2)) * (dim >> 2) + (ix >> 2)]);
         const float x0 = ((float)ix - half) * cell, y0 = ((float)iy - half - kVolShiftY) * cell, z0 = ((float)iz - half) * cell;
-        CellFirst f;
-        f.byte = 0u, f.refine = false, f.direct = true, f.reach = 0u, f.reach_refine = false, f.reach_flip = false;
-        if (live) f = choice_cell_first(L, table, FT, x0, y0, z0, cell);
-        unsigned need = __ballot_sync(0xffffffffu, f.refine);
+        const unsigned w = cube_word_coop(L, table, FT, atlas, x0, y0, z0, cell, 0.f, live, lane);
+        if (live) linear[i] = w;
+    }
+}
+
+// Bricks (see leg_math.cuh): a warp reads 32 consecutive coarse texels, and for every cube among them
+// that wants a brick computes its 64 fine texels — two per lane — with the same functions, the box
+// widened by the coarse cube's pad.  A brick is kept if at least kBrickMinUseful of its fine cubes
+// end up settled for tier 0 (choice and plane label); the coarse texel then becomes the pointer.
+// Bricks are numbered by an atomic counter; cubes that come after the pool is full stay as they are.
+constexpr int kBrickMinUseful = 8;
+__global__ void __launch_bounds__(128)
+    brick_build_kernel(const __grid_constant__ LegPlan L, const __grid_constant__ FastTables FT, const AtlasView atlas,
+                       unsigned* __restrict__ linear, unsigned short* __restrict__ bricks, unsigned* __restrict__ counter,
+                       unsigned capacity, int dim, float cell) {
+    __shared__ SectorTable table;
+    fill_sector_table(L, &table, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const size_t total = (size_t)dim * dim * dim;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const float half = 0.5f * (float)dim;
+    const int lane = threadIdx.x & 31;
+    const float hf = cell * (1.f / kBrickSub);
+    for (size_t base = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) & ~size_t(31); base < total; base += stride) {
+        const size_t i = base + lane;
+        const unsigned w = i < total ? linear[i] : 0u;
+        unsigned need = __ballot_sync(0xffffffffu, i < total && brick_candidate(w));
         while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
-            const float sx = __shfl_sync(0xffffffffu, x0, src), sy = __shfl_sync(0xffffffffu, y0, src),
-                        sz = __shfl_sync(0xffffffffu, z0, src);
-            const bool sdir = __shfl_sync(0xffffffffu, (int)f.direct, src) != 0;
-            const bool ok = choice_cell_sub(L, table, sx, sy, sz, cell, lane, sdir) &&
-                            choice_cell_sub(L, table, sx, sy, sz, cell, lane + 32, sdir);
-            const bool all = __all_sync(0xffffffffu, ok);
-            if (lane == src && !all) f.byte = 0u;
-        }
-        need = __ballot_sync(0xffffffffu, f.reach_refine);
-        while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            const float sx = __shfl_sync(0xffffffffu, x0, src), sy = __shfl_sync(0xffffffffu, y0, src),
-                        sz = __shfl_sync(0xffffffffu, z0, src);
-            const unsigned sbits = __shfl_sync(0xffffffffu, f.reach | (f.reach_flip ? 1u : 0u), src);
-            const bool flip = (sbits & 1u) != 0u, valid = (sbits & kVolReachValue) != 0u;
-            const bool ok = reach_cell_sub(L, table, sx, sy, sz, cell, lane, flip, valid) &&
-                            reach_cell_sub(L, table, sx, sy, sz, cell, lane + 32, flip, valid);
-            const bool all = __all_sync(0xffffffffu, ok);
-            if (lane == src && !all) f.reach = 0u;
-        }
-        if (live) {
-            // plane label of the chosen solution (tier 0 of the sweep): the atlas cells under the
-            // cube's plane rectangle all carry one certified label
-            unsigned hi = 0u;
-            if (f.byte & kVolPure) {
-                float side;
-                const CoxaPoint c = cube_centre(x0, y0, z0, cell, &side);
-                hi = cube_plane_scan(atlas, solution_plane_x(L, c, (f.byte & 1u) != 0u), c.z, side);
+            const size_t ci = base + src;
+            const unsigned cw = __shfl_sync(0xffffffffu, w, src);
+            const int ix = (int)(ci % dim), iy = (int)((ci / dim) % dim), iz = (int)(ci / ((size_t)dim * dim));
+            const float x0 = ((float)ix - half) * cell, y0 = ((float)iy - half - kVolShiftY) * cell, z0 = ((float)iz - half) * cell;
+            unsigned fw[2];
+#pragma unroll 1
+            for (int hlf = 0; hlf < 2; hlf++) {
+                const unsigned slot = (unsigned)lane + 32u * hlf;
+                const float xf = x0 + (float)(slot & 3u) * hf, yf = y0 + (float)((slot >> 2) & 3u) * hf,
+                            zf = z0 + (float)(slot >> 4) * hf;
+                if (cw & kVolPure) {  // warp-uniform: the choice holds for the whole coarse cube, only the label is missing
+                    float side;
+                    const CoxaPoint c = cube_centre(xf, yf, zf, hf, &side, cell);
+                    const unsigned hi = cube_plane_scan(atlas, solution_plane_x(L, c, (cw & 1u) != 0u), c.z, side);
+                    fw[hlf] = (cw & 0xffu) | (hi << 8);
+                } else {
+                    fw[hlf] = cube_word_coop(L, table, FT, atlas, xf, yf, zf, hf, cell, true, lane);
+                }
             }
-            linear[i] = (unsigned short)(f.byte | f.reach | (hi << 8));
+            const int useful = __popc(__ballot_sync(0xffffffffu, !brick_candidate(fw[0]))) +
+                               __popc(__ballot_sync(0xffffffffu, !brick_candidate(fw[1])));
+            if (useful >= kBrickMinUseful) {
+                unsigned idx = 0u;
+                if (lane == 0) idx = atomicAdd(counter, 1u);
+                idx = __shfl_sync(0xffffffffu, idx, 0);
+                if (idx < capacity) {
+                    bricks[(size_t)idx * 64 + lane] = (unsigned short)fw[0];
+                    bricks[(size_t)idx * 64 + 32 + lane] = (unsigned short)fw[1];
+                    if (lane == 0) linear[ci] = brick_texel(idx, ix, iy, iz, cw);
+                }
+            }
         }
     }
 }
@@ -180,7 +248,12 @@ struct Entry {
     bool vol_building = false;
     cudaStream_t vol_stream = nullptr;
     cudaEvent_t vol_done = nullptr;
-    unsigned short* vol_linear = nullptr;  // staging copy, freed once the build has finished
+    unsigned* vol_linear = nullptr;        // staging copy (32-bit texels), freed once the build has finished
+    // bricks: fine texels under the cubes the coarse grid cannot settle (kept as long as the array)
+    unsigned short* vol_bricks = nullptr;
+    unsigned* vol_brick_count = nullptr;   // device word: bricks handed out by the last build (may exceed the pool)
+    unsigned vol_brick_cap = 0;
+    int vol_bricks_on = -1;                // the "volume_bricks" option the volume was built with
     float vol_build_ms = 0.f;              // wall time of the last build (host clock around the wait), diagnostics
 };
 // a build in flight must finish before its buffers or its plan's atlas go away
@@ -196,6 +269,9 @@ void release_volume(Entry* c) {
     settle_volume(c);
     if (c->vol_tex) cudaDestroyTextureObject(c->vol_tex);
     if (c->vol_array) cudaFreeArray(c->vol_array);
+    if (c->vol_bricks) cudaFree(c->vol_bricks);
+    if (c->vol_brick_count) cudaFree(c->vol_brick_count);
+    c->vol_bricks = nullptr, c->vol_brick_count = nullptr, c->vol_brick_cap = 0;
     c->vol_tex = 0, c->vol_array = nullptr, c->vol_ready = false, c->vol_dim = 0;
 }
 // every stream that used the entry must have finished with it before its buffers are rewritten:
@@ -278,6 +354,9 @@ std::mutex g_mutex;
 constexpr int kVolBuildCtasPerSm = LRM_VOL_BUILD_CTAS;
 std::atomic<int> g_vol_dim{512};
 std::atomic<float> g_vol_cell{3.0f};
+std::atomic<int> g_vol_bricks{1};  // bricks under the uncertified cubes (0: coarse grid only)
+std::atomic<unsigned> g_last_bricks{0}, g_last_brick_cap{0};  // diagnostics of the last finished build
+std::atomic<unsigned long long> g_vol_builds_done{0};         // volume builds seen finished since the library was loaded
 std::atomic<unsigned long long> g_builds{0};  // atlas builds since the library was loaded (diagnostics / tests)
 
 void fill_view(const Entry* hit, AtlasView* view) {
@@ -290,7 +369,8 @@ void fill_view(const Entry* hit, AtlasView* view) {
 
 }  // namespace
 
-// 3 mm cubes over +-768 mm: 268 MB per cached plan (16-bit texels).  Measured on the bench lattice
+// 3 mm cubes over +-768 mm: 537 MB per cached plan (32-bit texels) + the brick pool (128 B per brick,
+// one brick per 12 cubes: 1.4 GB).  Measured on the bench lattice
 // with 8-bit texels: 4 mm / 384 is 2 % slower, 2.5 mm / 640 1 % faster.
 int set_choice_volume_shape(float cell_mm, int dim) {
     if (!(cell_mm >= 0.5f && cell_mm <= 64.f) || dim < 16 || dim > 1024 || dim % 4 != 0) return -1;
@@ -298,7 +378,10 @@ int set_choice_volume_shape(float cell_mm, int dim) {
     return 0;
 }
 void get_choice_volume_shape(float* cell_mm, int* dim) { *cell_mm = g_vol_cell.load(), *dim = g_vol_dim.load(); }
+int set_volume_bricks(int on) { return g_vol_bricks.exchange(on ? 1 : 0); }
+void get_brick_stats(unsigned* used, unsigned* capacity) { *used = g_last_bricks.load(), *capacity = g_last_brick_cap.load(); }
 unsigned long long table_builds() { return g_builds.load(); }
+unsigned long long volume_builds_done() { return g_vol_builds_done.load(); }
 
 bool tables_cached(const LegPlan& plan) {
     std::lock_guard<std::mutex> lock(g_mutex);
@@ -414,7 +497,9 @@ cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, Volu
     cudaError_t e;
     const int dim = g_vol_dim.load();
     const float cell = g_vol_cell.load();
-    if (hit->vol_ready && (hit->vol_dim != dim || hit->vol_cell != cell)) hit->vol_ready = false;  // shape changed
+    const int bricks_on = g_vol_bricks.load();
+    if (hit->vol_ready && (hit->vol_dim != dim || hit->vol_cell != cell || hit->vol_bricks_on != bricks_on))
+        hit->vol_ready = false;  // shape changed
     if (!hit->vol_ready && !hit->vol_building) {
         if (hit->vol_array && hit->vol_dim != dim) {
             // the old array may still be read by sweeps in flight
@@ -429,9 +514,18 @@ cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, Volu
             if (e != cudaSuccess) return e;
         }
         if (!hit->vol_array) {
-            const cudaChannelFormatDesc fmt = cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned);
+            const cudaChannelFormatDesc fmt = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindUnsigned);
             e = cudaMalloc3DArray(&hit->vol_array, &fmt, make_cudaExtent(dim, dim, dim));
             if (e != cudaSuccess) return e;
+            // brick pool: one brick per 12 cubes (the shells around the decision surfaces of a leg
+            // hold about 8 % of the cubes); without the memory the volume works without bricks
+            hit->vol_brick_cap = (unsigned)((size_t)dim * dim * dim / 12);
+            if (cudaMalloc((void**)&hit->vol_bricks, (size_t)hit->vol_brick_cap * 64 * sizeof(unsigned short)) != cudaSuccess ||
+                cudaMalloc((void**)&hit->vol_brick_count, sizeof(unsigned)) != cudaSuccess) {
+                (void)cudaGetLastError();
+                if (hit->vol_bricks) cudaFree(hit->vol_bricks);
+                hit->vol_bricks = nullptr, hit->vol_brick_cap = 0;
+            }
             cudaResourceDesc res;
             std::memset(&res, 0, sizeof res);
             res.resType = cudaResourceTypeArray;
@@ -458,7 +552,7 @@ cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, Volu
         const size_t cubes = (size_t)dim * dim * dim;
         // stream-ordered allocation on the build's own stream: freeing it later (cudaFreeAsync) does
         // not synchronise the device the way cudaFree does
-        e = cudaMallocAsync((void**)&hit->vol_linear, cubes * sizeof(unsigned short) + cubes / 64 + 64, hit->vol_stream);
+        e = cudaMallocAsync((void**)&hit->vol_linear, cubes * sizeof(unsigned) + cubes / 64 + 64, hit->vol_stream);
         if (e != cudaSuccess) return e;
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, hit->device);
@@ -470,11 +564,17 @@ cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, Volu
         fill_view(hit, &atlas);
         volume_build_kernel<<<sms * kVolBuildCtasPerSm, 128, 0, hit->vol_stream>>>(hit->plan, hit->tables, atlas, hit->vol_linear,
                                                                    block_done, dim, cell);
+        hit->vol_bricks_on = bricks_on;
+        if (hit->vol_brick_count) cudaMemsetAsync(hit->vol_brick_count, 0, sizeof(unsigned), hit->vol_stream);
+        if (bricks_on && hit->vol_bricks)
+            brick_build_kernel<<<sms * kVolBuildCtasPerSm, 128, 0, hit->vol_stream>>>(
+                hit->plan, hit->tables, atlas, hit->vol_linear, hit->vol_bricks, hit->vol_brick_count, hit->vol_brick_cap,
+                dim, cell);
         e = cudaGetLastError();
         if (e == cudaSuccess) {
             cudaMemcpy3DParms cp;
             std::memset(&cp, 0, sizeof cp);
-            cp.srcPtr = make_cudaPitchedPtr(hit->vol_linear, (size_t)dim * sizeof(unsigned short), (size_t)dim, (size_t)dim);
+            cp.srcPtr = make_cudaPitchedPtr(hit->vol_linear, (size_t)dim * sizeof(unsigned), (size_t)dim, (size_t)dim);
             cp.dstArray = hit->vol_array;
             cp.extent = make_cudaExtent(dim, dim, dim);
             cp.kind = cudaMemcpyDeviceToDevice;
@@ -499,8 +599,16 @@ cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, Volu
         if (e != cudaSuccess) return e;
         hit->vol_building = false;
         hit->vol_ready = true;
+        g_vol_builds_done.fetch_add(1);
         cudaFreeAsync(hit->vol_linear, hit->vol_stream);
         hit->vol_linear = nullptr;
+        if (hit->vol_brick_count) {  // diagnostics (lrm_get_stat): the build has finished, the copy does not wait
+            unsigned used = 0;
+            if (cudaMemcpy(&used, hit->vol_brick_count, sizeof used, cudaMemcpyDeviceToHost) == cudaSuccess)
+                g_last_bricks.store(used), g_last_brick_cap.store(hit->vol_brick_cap);
+            else
+                (void)cudaGetLastError();
+        }
     }
     (void)stream;  // vol_done has completed on the host's clock: no device-side wait needed
     view->tex = hit->vol_tex;
@@ -508,6 +616,7 @@ cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, Volu
     view->o = 0.5f * (float)hit->vol_dim;
     view->oy = view->o + kVolShiftY;
     view->dim = hit->vol_dim;
+    view->bricks = (hit->vol_bricks_on && hit->vol_bricks) ? hit->vol_bricks : nullptr;
     return cudaSuccess;
 }
 

@@ -210,7 +210,7 @@ void emu_dist_choice(const float* xyz, size_t n, const lrm_leg_t* leg, const flo
 // explicit plane evaluation, dist_fast, the full evaluation.
 void emu_dist_tier0(const float* xyz, size_t n, const lrm_leg_t* leg, const float* quat, int dim, float cell,
                     float vol_h, int vol_dim, float* out_vec, uint8_t* out_flag, uint8_t* out_reach,
-                    size_t* tiers, uint8_t* out_tier) {
+                    size_t* tiers, uint8_t* out_tier, int bricks) {
     lrm::LegPlan L;
     lrm::build_leg_plan(*leg, quat, &L);
     lrm::SectorTable tab;
@@ -233,32 +233,68 @@ void emu_dist_tier0(const float* xyz, size_t n, const lrm_leg_t* leg, const floa
     std::unordered_map<uint64_t, unsigned> cubes, blocks;
     const float vo = 0.5f * vol_dim, vinv = 1.0f / vol_h;
     for (int k = 0; k < 5; k++) tiers[k] = 0;
+    std::unordered_map<uint64_t, unsigned> fine;
+    // classic texel of a cube, computed on demand the way the device build does it
+    auto classic_word = [&](int ix, int iy, int iz) -> unsigned {
+        const uint64_t bkey = ((uint64_t)(iz >> 2) * vol_dim + (iy >> 2)) * vol_dim + (ix >> 2);
+        auto bt = blocks.find(bkey);
+        if (bt == blocks.end()) {
+            // volume_coarse_kernel: the block is settled only if nothing needs refinement
+            const float x0 = ((float)(ix & ~3) - vo) * vol_h, y0 = ((float)(iy & ~3) - vo - lrm::kVolShiftY) * vol_h,
+                        z0 = ((float)(iz & ~3) - vo) * vol_h;
+            bt = blocks.emplace(bkey, lrm::coarse_block_word(L, tab, ft, x0, y0, z0, 4.f * vol_h)).first;
+        }
+        if (bt->second != 0u) return bt->second;
+        const uint64_t key = ((uint64_t)iz * vol_dim + iy) * vol_dim + ix;
+        auto it = cubes.find(key);
+        if (it == cubes.end())
+            it = cubes.emplace(key, lrm::choice_cell_word(L, tab, ft, A, ((float)ix - vo) * vol_h,
+                                                          ((float)iy - vo - lrm::kVolShiftY) * vol_h,
+                                                          ((float)iz - vo) * vol_h, vol_h, false)).first;
+        return it->second;
+    };
     for (size_t i = 0; i < n; i++) {
         const lrm::CoxaPoint p = lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
         const float fx = fmaf(p.x, vinv, vo), fy = fmaf(p.y, vinv, vo + lrm::kVolShiftY), fz = fmaf(p.z, vinv, vo);
         unsigned word = 0;
-        if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)vol_dim && fy < (float)vol_dim && fz < (float)vol_dim) {
+        const bool inside = fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)vol_dim && fy < (float)vol_dim && fz < (float)vol_dim;
+        if (inside) word = classic_word((int)fx, (int)fy, (int)fz);
+        if (bricks && inside) {
+            // bricks (leg_math.cuh): an unsettled cube points to 4^3 fine cubes, certified by the same
+            // functions over boxes widened by the COARSE pad.  The device finds the brick through a
+            // texture fetch that resolves cube coordinates to 1 / 256 of a cube: next to a face it may
+            // pick the neighbouring cube.  Both outcomes are emulated; where both yield a tier-0 texel
+            // the results must agree bit for bit.
+            const lrm::VolumeView V{0, vinv, vo, vo + lrm::kVolShiftY, vol_dim, nullptr};
+            auto texel_via = [&](int cx, int cy, int cz) -> unsigned {
+                if (cx < 0 || cy < 0 || cz < 0 || cx >= vol_dim || cy >= vol_dim || cz >= vol_dim) return 0u;
+                const unsigned cw = classic_word(cx, cy, cz);
+                if (!lrm::brick_candidate(cw)) return cw;
+                const unsigned ptr = lrm::brick_texel(0u, cx, cy, cz, cw);
+                const unsigned slot = lrm::brick_slot(V, ptr, p);
+                const uint64_t key = ((((uint64_t)cz * vol_dim + cy) * vol_dim + cx) << 6) | slot;
+                auto it = fine.find(key);
+                if (it == fine.end())
+                    it = fine.emplace(key, lrm::brick_fine_word(L, tab, ft, A, cw, ((float)cx - vo) * vol_h,
+                                                                ((float)cy - vo - lrm::kVolShiftY) * vol_h,
+                                                                ((float)cz - vo) * vol_h, vol_h, slot)).first;
+                return it->second;
+            };
             const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
-            const uint64_t bkey = ((uint64_t)(iz >> 2) * vol_dim + (iy >> 2)) * vol_dim + (ix >> 2);
-            auto bt = blocks.find(bkey);
-            if (bt == blocks.end()) {
-                // volume_coarse_kernel: the block is settled only if nothing needs refinement
-                const float x0 = ((float)(ix & ~3) - vo) * vol_h, y0 = ((float)(iy & ~3) - vo - lrm::kVolShiftY) * vol_h,
-                            z0 = ((float)(iz & ~3) - vo) * vol_h;
-                unsigned w = lrm::coarse_block_word(L, tab, ft, x0, y0, z0, 4.f * vol_h);
-                bt = blocks.emplace(bkey, w).first;
-            }
-            word = bt->second;
-            if (word == 0u) {
-                const uint64_t key = ((uint64_t)iz * vol_dim + iy) * vol_dim + ix;
-                auto it = cubes.find(key);
-                if (it == cubes.end()) {
-                    const unsigned w = lrm::choice_cell_word(L, tab, ft, A, ((float)ix - vo) * vol_h,
-                                                             ((float)iy - vo - lrm::kVolShiftY) * vol_h,
-                                                             ((float)iz - vo) * vol_h, vol_h, false);
-                    it = cubes.emplace(key, w).first;
-                }
-                word = it->second;
+            word = texel_via(ix, iy, iz);
+            const float q = 1.0f / 200.f;  // a little more than the texture unit's 1 / 256
+            for (int ax = 0; ax < 3; ax++) {
+                const float f = ax == 0 ? fx : ax == 1 ? fy : fz;
+                const float fr = f - floorf(f);
+                const int d = fr < q ? -1 : fr > 1.f - q ? 1 : 0;
+                if (d == 0) continue;
+                const unsigned other = texel_via(ix + (ax == 0 ? d : 0), iy + (ax == 1 ? d : 0), iz + (ax == 2 ? d : 0));
+                lrm::DistResult ra, rb;
+                if (lrm::dist_choice_label<true>(L, sols, word, win, p, &ra) == 0 &&
+                    lrm::dist_choice_label<true>(L, sols, other, win, p, &rb) == 0 &&
+                    (std::memcmp(&ra.dx, &rb.dx, 12) != 0 || ra.flag != rb.flag || ra.reach != rb.reach))
+                    tiers[0] = (size_t)-1 << 20;
+                if (lrm::dist_choice_label<true>(L, sols, word, win, p, &ra) != 0) word = other;  // exercise the neighbour's texel too
             }
         }
         lrm::DistResult r;

@@ -16,6 +16,8 @@ vec = torch.empty((n, 3), dtype=torch.float32, device="cuda")
 mode = sys.argv[3] if len(sys.argv) > 3 else "both"
 if len(sys.argv) > 4:
     lrm.set_option("sweep", int(sys.argv[4]))
+if os.environ.get("LRM_TC_BRICKS"):
+    lrm.set_option("volume_bricks", int(os.environ["LRM_TC_BRICKS"]))
 for _ in range(reps):
     if mode == "reach":
         lrm.reachability(pts, leg, out=flags)

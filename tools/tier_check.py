@@ -25,6 +25,9 @@ if len(sys.argv) > 4:
 if len(sys.argv) > 5:
     lrm.set_option("tier_kernel", int(sys.argv[5]))
     out["tier_kernel"] = int(sys.argv[5])
+if os.environ.get("LRM_TC_BRICKS"):
+    lrm.set_option("volume_bricks", int(os.environ["LRM_TC_BRICKS"]))
+    out["volume_bricks_option"] = int(os.environ["LRM_TC_BRICKS"])
 res = {}
 for name, mode in (("two_tier", 0), ("three_tier", 1), ("auto", 2)):
     lrm.set_option("sweep", mode)
@@ -77,4 +80,5 @@ fc, vc, dc, rc = res["auto"]
 out["auto_equal"] = bool(torch.equal(fc, fa) and torch.equal(vc, va) and torch.equal(dc, da))
 out["reach_equal"] = bool(torch.equal(ra, rb) and torch.equal(ra, rc))
 out["reach_vs_fused_mismatch"] = int((ra != fa).sum())
+out["bricks_used"], out["brick_capacity"] = lrm.get_stat("volume_bricks"), lrm.get_stat("volume_brick_capacity")
 print(json.dumps(out))
