@@ -400,9 +400,16 @@ def run_b200(args):
     torch.cuda.synchronize()
     first_call_ms = (time.perf_counter() - t0) * 1e3
     t0 = time.perf_counter()
-    while time.perf_counter() - t0 < 0.4:        # well past the background build of the choice volume
+    builds0 = lrm.get_stat("volume_builds")
+    # until a sweep has found the background build of the choice volume finished (the two-tier sweep
+    # answers meanwhile, same bits), and a little beyond; at most 5 s
+    while True:
         step_fn()
         torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dt > 5.0 or (dt > 0.4 and lrm.get_stat("volume_builds") > builds0):
+            break
+    volume_wait_ms = (time.perf_counter() - t0) * 1e3
     for _ in range(max(args.warmup, 3)):
         step_fn()
     barrier()
@@ -502,8 +509,11 @@ def run_b200(args):
             "setup": {"first_call_ms": first_call_ms,
                       "note": "first lrm_reach_dist of a new (leg, orientation), synchronised: plane atlas (16 MiB) "
                               "built on the caller's stream + that call's two-tier sweep; the choice volume "
-                              f"({vdim}^3 cubes of {cell_mm} mm, 16-bit) builds on a side stream meanwhile",
-                      "table_bytes": 3 * 4096 * 4096 + 2 * vdim ** 3, "table_builds": lrm.get_stat("table_builds")},
+                              f"({vdim}^3 cubes of {cell_mm} mm, 32-bit texels) builds on a side stream meanwhile; "
+                              "volume_wait_ms = wall time of the sweeps issued until one found it finished (>= 400)",
+                      "volume_wait_ms": volume_wait_ms,
+                      "table_bytes": 3 * 4096 * 4096 + 4 * vdim ** 3 + 128 * int(lrm.get_stat("volume_bricks")),
+                      "bricks": int(lrm.get_stat("volume_bricks")), "table_builds": lrm.get_stat("table_builds")},
         }
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1

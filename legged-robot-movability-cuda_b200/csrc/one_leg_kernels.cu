@@ -431,7 +431,9 @@ __global__ void __launch_bounds__(kThreads)
 #endif
 // points of a thread that share one "any valid plane point in the warp" vote: all four (finer
 // groups measured no faster, and the one-point build faulted in its distance-only instantiation)
+#ifndef LRM_T0_GROUP
 #define LRM_T0_GROUP 4
+#endif
 constexpr int kTT = LRM_TIER_THREADS;  // threads per CTA
 constexpr int kTL = LRM_TIER_TILE;     // points per tile
 constexpr int kPer = kTL / kTT;        // points per thread and tile

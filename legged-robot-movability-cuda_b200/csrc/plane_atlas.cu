@@ -354,7 +354,10 @@ std::mutex g_mutex;
 constexpr int kVolBuildCtasPerSm = LRM_VOL_BUILD_CTAS;
 std::atomic<int> g_vol_dim{512};
 std::atomic<float> g_vol_cell{3.0f};
-std::atomic<int> g_vol_bricks{1};  // bricks under the uncertified cubes (0: coarse grid only)
+// bricks under the uncertified cubes (0: coarse grid only).  Off by default: on the bench lattice they
+// halve the share of parked points (11.5 % -> 5.1 %) but the pointer chase costs what the smaller
+// rings save (128.1 -> 128.9 Gpoints/s), for 0.25 s more background build and 1.4 GB per plan.
+std::atomic<int> g_vol_bricks{0};
 std::atomic<unsigned> g_last_bricks{0}, g_last_brick_cap{0};  // diagnostics of the last finished build
 std::atomic<unsigned long long> g_vol_builds_done{0};         // volume builds seen finished since the library was loaded
 std::atomic<unsigned long long> g_builds{0};  // atlas builds since the library was loaded (diagnostics / tests)
@@ -517,15 +520,6 @@ cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, Volu
             const cudaChannelFormatDesc fmt = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindUnsigned);
             e = cudaMalloc3DArray(&hit->vol_array, &fmt, make_cudaExtent(dim, dim, dim));
             if (e != cudaSuccess) return e;
-            // brick pool: one brick per 12 cubes (the shells around the decision surfaces of a leg
-            // hold about 8 % of the cubes); without the memory the volume works without bricks
-            hit->vol_brick_cap = (unsigned)((size_t)dim * dim * dim / 12);
-            if (cudaMalloc((void**)&hit->vol_bricks, (size_t)hit->vol_brick_cap * 64 * sizeof(unsigned short)) != cudaSuccess ||
-                cudaMalloc((void**)&hit->vol_brick_count, sizeof(unsigned)) != cudaSuccess) {
-                (void)cudaGetLastError();
-                if (hit->vol_bricks) cudaFree(hit->vol_bricks);
-                hit->vol_bricks = nullptr, hit->vol_brick_cap = 0;
-            }
             cudaResourceDesc res;
             std::memset(&res, 0, sizeof res);
             res.resType = cudaResourceTypeArray;
@@ -542,6 +536,17 @@ cudaError_t get_choice_volume(const TableLease& lease, cudaStream_t stream, Volu
                 return e;
             }
             hit->vol_dim = dim;
+        }
+        if (bricks_on && !hit->vol_bricks) {
+            // brick pool: one brick per 12 cubes (the shells around the decision surfaces of a leg
+            // hold about 8 % of the cubes); without the memory the volume works without bricks
+            hit->vol_brick_cap = (unsigned)((size_t)dim * dim * dim / 12);
+            if (cudaMalloc((void**)&hit->vol_bricks, (size_t)hit->vol_brick_cap * 64 * sizeof(unsigned short)) != cudaSuccess ||
+                cudaMalloc((void**)&hit->vol_brick_count, sizeof(unsigned)) != cudaSuccess) {
+                (void)cudaGetLastError();
+                if (hit->vol_bricks) cudaFree(hit->vol_bricks);
+                hit->vol_bricks = nullptr, hit->vol_brick_cap = 0;
+            }
         }
         // a sweep of the evicted plan may still read the array that is about to be rewritten, and
         // the build reads the atlas: order the build stream behind both

@@ -382,6 +382,41 @@ def test_every_sweep_returns_the_same_bits(lrm):
         lrm.set_option("tier_kernel", 0)
 
 
+def test_bricks_never_change_a_result(lrm):
+    """lrm_set_option("volume_bricks", 1): cubes the choice volume cannot settle carry a brick of 4^3
+    fine cubes, found through a pointer in the cube's texel.  Same bytes as the two-tier sweep on a
+    lattice slab, on a rotated leg and on points lying ON the reachability edge, through both
+    organisations of the tiered sweep; the build reports how many bricks it made."""
+    n = 5 * (1 << 20) + 77
+    lo, step, dims = lrm.lattice_spec((-100, -400, -500), (600, 400, 200), (6, 1000, 1000))
+    lattice = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    lrm.make_lattice(lattice, lo, step, dims, 0, n)
+    quat = np.array([0.9914449, 0.0, 0.1305262, 0.0], np.float32)   # 15 degrees about y
+    old_sweep, old_bricks = lrm.set_option("sweep", 0), lrm.set_option("volume_bricks", 1)
+    try:
+        for leg, q in ((lrm.get_M2_leg(0.0), None), (lrm.get_moonbot_leg(1.0), quat)):
+            lrm.set_option("sweep", 0)
+            f0, v0 = lrm.reach_dist(lattice, leg, q)
+            r0 = lrm.reachability(lattice, leg, q)
+            edge = (lattice - v0).contiguous()
+            fe, ve = lrm.reach_dist(edge, leg, q)
+            lrm.set_option("sweep", 1)
+            for kern in (0, 1):
+                lrm.set_option("tier_kernel", kern)
+                f1, v1 = lrm.reach_dist(lattice, leg, q)
+                assert torch.equal(f0, f1) and torch.equal(v0, v1), kern
+                assert torch.equal(r0, lrm.reachability(lattice, leg, q)), kern
+                f2, v2 = lrm.reach_dist(edge, leg, q)
+                assert torch.equal(fe, f2) and torch.equal(ve, v2), kern
+            torch.cuda.synchronize()
+            assert lrm.get_stat("volume_bricks") > 1000
+            assert lrm.get_stat("volume_brick_capacity") >= lrm.get_stat("volume_bricks")
+    finally:
+        lrm.set_option("sweep", old_sweep)
+        lrm.set_option("volume_bricks", old_bricks)
+        lrm.set_option("tier_kernel", 0)
+
+
 def test_plan_cache_eviction_keeps_results(lrm):
     """More distinct (leg, orientation) plans than the per-device table cache holds (8), swept back
     to back with the choice volume forced on: every sweep must rebuild / reuse atlas and volume
