@@ -58,7 +58,8 @@ template <int MODE, bool FAST>
 struct alignas(128) StreamSmem {
     // Distance modes work IN PLACE: a thread overwrites its point with the point's vector (same 12
     // bytes), and the tile goes back to global memory from the buffer it arrived in.  Three
-    // buffers rotate (being loaded / being computed / being stored); reach-only needs two.
+    // buffers rotate (being loaded / being computed / being stored); reach-only needs two.  (Two
+    // buffers for the distance modes as well, as in the tiered sweep: 115.2 vs 114.0 Gpoints/s — not kept.)
     static constexpr int kStages = (MODE & kModeDist) ? 3 : 2;
     float in[kStages][3 * kTile];
     uint8_t flag[2][kTile];
@@ -471,15 +472,23 @@ __device__ __forceinline__ void resolve_bricks(const VolumeView& vol, const Coxa
         if (w[k] & kVolBrick) w[k] = __ldg(src[k]);
 }
 
+// tile buffers of the tiered sweep: 3 (being loaded / computed / stored) or 2 (the buffer a tile was
+// stored from is reloaded as soon as the store has read it: 12 KiB less shared memory per CTA, which
+// the SM hands to L1)
+#ifndef LRM_TIER_STAGES
+#define LRM_TIER_STAGES 2  // measured at 1e9 points: 2 buffers 134.6, 3 buffers 129.6 Gpoints/s (L1: 60 KB instead of 28 KB per SM)
+#endif
+constexpr int kTStages = LRM_TIER_STAGES;
+static_assert(kTStages == 2 || kTStages == 3, "tile buffers");
 struct alignas(128) TierSmem {
-    float in[3][3 * kTL];  // in-place tiles: being loaded / computed / stored
+    float in[kTStages][3 * kTL];  // in-place tiles
     uint8_t flag[2][kTL];
     alignas(16) SectorTable table;
     alignas(16) WinnerTable winners;
     alignas(16) YawPair ypair[kYawPairs];
     uint32_t ring_p[kRingP], ring_a[kRingA], ring_b[kRingB], ring_c[kRingC];
     unsigned cnt[4][3];  // [ring P, A, B, C][it % 3]: pushes attempted in that iteration
-    alignas(8) uint64_t full[3];
+    alignas(8) uint64_t full[kTStages];
 };
 
 // Per-thread (uniform) bookkeeping of one ring: accepted entries before this iteration (base),
@@ -629,7 +638,7 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
     const int tid = threadIdx.x;
     const size_t n_bulk = n & ~size_t(15);
     const uint32_t n_tiles = (uint32_t)((n_bulk + kTL - 1) / kTL);  // the launcher keeps n below 2^40
-    constexpr int kStages = 3;
+    constexpr int kStages = kTStages;
 
     fill_sector_table(L, &S.table, tid, kTT);
     fill_winner_table(L, &S.winners, tid, kTT);
@@ -702,8 +711,10 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
 
     for (uint32_t tile = tile_of(0); tile < n_tiles; tile = tile_of(++it)) {
         const uint32_t cnt = tile_count(tile);
-        bulk::mbar_wait(&S.full[rot], parity);
-        float* in = S.in[rot];
+        // buffer and mbarrier phase of this tile: it % 3 and (it / 3) & 1, or it & 1 and (it >> 1) & 1
+        const int buf = kStages == 3 ? rot : (int)(it & 1u);
+        bulk::mbar_wait(&S.full[buf], kStages == 3 ? parity : ((it >> 1) & 1u));
+        float* in = S.in[buf];
         uint8_t* flag = S.flag[it & 1];
 
         // counters of the previous iteration are final since its tile barrier
@@ -848,9 +859,16 @@ __global__ void __launch_bounds__(kTT, LRM_TIER_CTAS)
             }
             if (io.out_flag) bulk::store(io.out_flag + first, flag, cnt);
             bulk::commit_group();
-            static_assert(kPrefetch == 2 && kStages == 3, "the buffer two tiles ahead is the previous one");
+            static_assert(kPrefetch == 2, "two tiles ahead");
             const uint32_t next = tile_of(it + kPrefetch);
-            if (next < n_tiles) issue_load(next, rot == 0 ? 2 : rot - 1);
+            if (kStages == 3) {
+                // the buffer two tiles ahead is the previous tile's, whose store has completed
+                if (next < n_tiles) issue_load(next, rot == 0 ? 2 : rot - 1);
+            } else if (next < n_tiles) {
+                // ... is this tile's own: reload it as soon as the store just issued has read it
+                bulk::wait_group_read<0>();
+                issue_load(next, buf);
+            }
         }
         rot = rot == 2 ? 0 : rot + 1;
         parity ^= (rot == 0) ? 1u : 0u;

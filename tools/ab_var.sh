@@ -1,7 +1,7 @@
 # usage: bash tools/ab_var.sh name1 name2 ...   ("product" = the in-tree library)
 for v in "$@"; do
   if [ "$v" = product ]; then unset LRM_B200_LIB; else export LRM_B200_LIB=tools/_variants/liblrm_$v.so; fi
-  python tools/tier_check.py ${AB_POINTS:-1000000000} lattice 3 512 ${AB_KERNEL:-0} > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+  python tools/tier_check.py ${AB_POINTS:-1000000000} lattice ${AB_CELL:-3} ${AB_DIM:-512} ${AB_KERNEL:-0} > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python -c "
 import json,sys
 try:

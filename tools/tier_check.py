@@ -25,6 +25,9 @@ if len(sys.argv) > 4:
 if len(sys.argv) > 5:
     lrm.set_option("tier_kernel", int(sys.argv[5]))
     out["tier_kernel"] = int(sys.argv[5])
+if os.environ.get("LRM_TC_KSHIFT"):
+    lrm.set_option("tier_chunk_shift", int(os.environ["LRM_TC_KSHIFT"]))
+    out["tier_chunk_shift"] = int(os.environ["LRM_TC_KSHIFT"])
 if os.environ.get("LRM_TC_BRICKS"):
     lrm.set_option("volume_bricks", int(os.environ["LRM_TC_BRICKS"]))
     out["volume_bricks_option"] = int(os.environ["LRM_TC_BRICKS"])
