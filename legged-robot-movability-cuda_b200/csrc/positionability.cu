@@ -29,7 +29,13 @@ namespace lrm {
 
 namespace {
 
-constexpr int kWarpsPerCta = 16;
+#ifndef LRM_POSIT_WARPS
+#define LRM_POSIT_WARPS 16
+#endif
+#ifndef LRM_POSIT_CTAS
+#define LRM_POSIT_CTAS 3
+#endif
+constexpr int kWarpsPerCta = LRM_POSIT_WARPS;
 #ifndef LRM_POSE_CHUNK
 #define LRM_POSE_CHUNK 4
 #endif
@@ -195,7 +201,7 @@ __global__ void target_precull_kernel(CellGrid body_grid, const float* __restric
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) positionability_kernel(const SearchParams P) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, LRM_POSIT_CTAS) positionability_kernel(const SearchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ReachPlan* plans = P.plans;
     if (P.plans_in_smem) {
