@@ -1335,6 +1335,53 @@ LRM_HD void dist_choice_clamp(const LegPlan& L, const SectorTable& tab, const Ya
     out->dz = fmaf(L.Mo[6], b.vx, fmaf(L.Mo[7], b.vy, L.Mo[8] * b.vz));
 }
 
+// ---- "inside the body cylinder under EVERY orientation" (pose search, positionability.cu) ---------
+// The body cylinder of eliminateFarAndColliding (several_leg.cu:504-559) is fixed in the ORIENTATION
+// frame: radius r around the body's z axis, heights in (z_lo, z_hi).  Its axis in the world frame is the
+// third row of the orientation matrix.  If the axes of all orientations lie within an angle theta of
+// the unit vector (ax, ay, az), then for a map point at offset d from the body — axial part
+// a = d . axis, radial part rho, phi the angle between d and the axis — the angle between d and ANY of
+// the axes lies in [phi - theta, phi + theta], the cylinder height of d is |d| cos of that angle and
+// its cylinder radius |d| sin of it: extremes at the ends of the interval, or at 0 / pi (height) and
+// pi / 2 (radius) where the interval contains them.  A point that keeps all three inside limits
+// collides whatever the orientation.  (cm, sm) = (cos, sin) of theta; lo / hi / rad = the limits, a
+// little inside; ok = 0: the axes spread too far, nothing is claimed; gate: see positionability.cu.
+struct AxisCone {
+    float ax, ay, az, cm, sm;
+    float lo, hi, rad;
+    int ok, gate;
+};
+LRM_HD bool cone_collides_always(const AxisCone& C, float dx, float dy, float dz) {
+    const float a = fmaf(C.ax, dx, fmaf(C.ay, dy, C.az * dz));
+    const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+    const float dn = sqrtf(d2), rho = sqrtf(fmaxf(fmaf(-a, a, d2), 0.f));
+    const float lo = fmaf(rho, C.cm, a * C.sm) <= 0.f ? -dn : fmaf(a, C.cm, -rho * C.sm);
+    const float hi = fmaf(rho, C.cm, -a * C.sm) <= 0.f ? dn : fmaf(a, C.cm, rho * C.sm);
+    const float rad = (lo <= 0.f && hi >= 0.f) ? dn : fmaf(rho, C.cm, fabsf(a) * C.sm);
+    return lo > C.lo && hi < C.hi && rad < C.rad;
+}
+// Host side: the cone of n cylinder axes (rows of 3 floats, not necessarily unit), limits 1.5 mm inside
+// (z_lo, z_hi, radius) for the rounding of the rotations, 2 mrad on the angle.
+inline void make_axis_cone(const float* axes, int n, float z_lo, float z_hi, float radius, AxisCone* C) {
+    C->ok = 0, C->gate = 1, C->ax = 0.f, C->ay = 0.f, C->az = 1.f, C->cm = 1.f, C->sm = 0.f;
+    C->lo = z_lo + 1.5f, C->hi = z_hi - 1.5f, C->rad = radius - 1.5f;
+    double m[3] = {0, 0, 0};
+    for (int o = 0; o < n; o++) m[0] += axes[3 * o], m[1] += axes[3 * o + 1], m[2] += axes[3 * o + 2];
+    const double mn = sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+    if (!(mn > 1.0e-6 * n) || !(C->rad > 0.f)) return;
+    double cmin = 1.0;
+    for (int o = 0; o < n; o++) {
+        const double x = axes[3 * o], y = axes[3 * o + 1], z = axes[3 * o + 2];
+        cmin = fmin(cmin, (x * m[0] + y * m[1] + z * m[2]) / (mn * sqrt(x * x + y * y + z * z)));
+    }
+    const double theta = acos(fmax(-1.0, fmin(1.0, cmin))) + 2.0e-3;
+    if (!(theta < 1.2)) return;  // beyond ~70 degrees the region is hardly more than the ball
+    C->ok = 1;
+    C->gate = theta > 0.05 ? 1 : 0;
+    C->ax = (float)(m[0] / mn), C->ay = (float)(m[1] / mn), C->az = (float)(m[2] / mn);
+    C->cm = (float)cos(theta), C->sm = (float)sin(theta);
+}
+
 // The same question for the full plan of the distance entry points (no gravity side, both coxa
 // solutions count: distance_circles' flag is res || resflip): can any point within `rc` of the
 // coxa-frame point p be reachable?  Conservative; `wedge` says the yaw limits span less than pi.

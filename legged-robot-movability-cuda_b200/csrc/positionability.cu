@@ -64,15 +64,10 @@ struct SearchParams {
     // a map point nearer than r_collide_all is inside the body cylinder under EVERY orientation, and
     // without a map point within r_near_any the reach cylinder is empty under every orientation
     float r_collide_all, r_near_any;
-    // "inside the body cylinder under EVERY orientation", sharper than the ball: the cylinder axes of
-    // all orientations lie within an angle theta of the unit vector (ax, ay, az); (cm, sm) = (cos, sin)
-    // of theta; a map point at offset d from the body, with axial part a = d . axis and radial part
-    // rho, then has its cylinder height within [lo, hi] and its cylinder radius below rad under every
-    // orientation (collides_always below).  cone = 0: the axes spread too far, ball only.
-    float ax, ay, az, cm, sm;
-    float all_lo, all_hi, all_rad;  // the cylinder's limits, 1.5 mm inside
-    int cone;
-    int cone_gate;  // 1: only where the map's cell over the body reaches above it (tilted orientations)
+    // "inside the body cylinder under EVERY orientation", sharper than the ball (leg_math.cuh:
+    // AxisCone); cone.ok = 0: ball only; cone.gate = 1: looked for only where the map's cell over the
+    // body reaches above it (tilted orientations)
+    AxisCone cone;
     uint8_t* standable;
     unsigned long long* next;   // dynamic work counter
     // STATS instantiation only: [0] leg predicates executed (reach_offset on a live map point),
@@ -239,19 +234,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LRM_POSIT_CTAS) positionabi
             // One orientation-independent scan settles most poses of a dense pose lattice (far above
             // the map, or inside it) before the per-orientation scans: exact, because both bounds
             // are conservative for every rotation.
-            // The cylinder height of offset d under an orientation whose axis makes an angle within
-            // [phi - theta, phi + theta] with d (phi: angle between d and the mean axis) is |d| cos of
-            // that angle, its cylinder radius |d| sin of it: extremes at the ends of the interval, or
-            // at 0 / pi / pi/2 where the interval contains them.
-            auto collides_always = [&](float dx, float dy, float dz) -> bool {
-                const float a = fmaf(P.ax, dx, fmaf(P.ay, dy, P.az * dz));
-                const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                const float dn = sqrtf(d2), rho = sqrtf(fmaxf(fmaf(-a, a, d2), 0.f));
-                const float lo = fmaf(rho, P.cm, a * P.sm) <= 0.f ? -dn : fmaf(a, P.cm, -rho * P.sm);
-                const float hi = fmaf(rho, P.cm, -a * P.sm) <= 0.f ? dn : fmaf(a, P.cm, rho * P.sm);
-                const float rad = (lo <= 0.f && hi >= 0.f) ? dn : fmaf(rho, P.cm, fabsf(a) * P.sm);
-                return lo > P.all_lo && hi < P.all_hi && rad < P.all_rad;
-            };
             bool collide_all = walk_filtered(
                 P.map, bx, by, P.r_collide_all, lane,
                 [&](float x, float y, float z, float rc) {
@@ -269,25 +251,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LRM_POSIT_CTAS) positionabi
             // -> 292 ms).  With level orientations only (all cylinder axes equal: configs[4]) the region IS
             // the cylinder, and one walk settles what every orientation would find: always taken
             // (42 - 46 ms against 50).
-            if (!collide_all && P.cone) {
+            if (!collide_all && P.cone.ok) {
                 const int cx = (int)floorf((bx - P.map.x0) * P.map.inv_cell), cy = (int)floorf((by - P.map.y0) * P.map.inv_cell);
-                bool above = !P.cone_gate;
-                if (P.cone_gate && cx >= 0 && cy >= 0 && cx < P.map.nx && cy < P.map.ny) {
+                bool above = !P.cone.gate;
+                if (P.cone.gate && cx >= 0 && cy >= 0 && cx < P.map.nx && cy < P.map.ny) {
                     const int c = cy * P.map.nx + cx;
                     above = P.map.cell_start[c + 1] == P.map.cell_start[c] || P.map.cell_z[c].y > bz;  // empty cell: unknown
                 }
                 if (above)
                     collide_all = walk_filtered(
-                        P.map, bx, by, P.all_hi, lane,
+                        P.map, bx, by, P.cone.hi, lane,
                         [&](float x, float y, float z, float rc) {
                             // a superset of the upper part of the region: the ball of the cylinder's
                             // height, above the body's plane
                             const float dx = x - bx, dy = y - by, dz = z - bz;
-                            return norm3df(dx, dy, dz) < P.all_hi + rc &&
-                                   fmaf(P.ax, dx, fmaf(P.ay, dy, P.az * dz)) + rc > (P.cone_gate ? 0.f : P.all_lo);
+                            return norm3df(dx, dy, dz) < P.cone.hi + rc &&
+                                   fmaf(P.cone.ax, dx, fmaf(P.cone.ay, dy, P.cone.az * dz)) + rc > (P.cone.gate ? 0.f : P.cone.lo);
                         },
                         [&](float4 t, bool ok) {
-                            return __any_sync(0xffffffffu, ok && t.w != 0.f && collides_always(t.x - bx, t.y - by, t.z - bz)) != 0;
+                            return __any_sync(0xffffffffu, ok && t.w != 0.f && cone_collides_always(P.cone, t.x - bx, t.y - by, t.z - bz)) != 0;
                         });
             }
             const bool near_any = !collide_all && walk_filtered(
@@ -533,32 +515,16 @@ cudaError_t run_positionability(const PositParams& p, cudaStream_t stream, float
         S.r_collide_all = std::fmax(0.f, r_in - 1.f);  // 1 mm of slack for the rounding of the rotations
         S.r_near_any = r_far + 1.f;
         // the cone of cylinder axes (third row of R: height = R[6..8] . d)
-        double m[3] = {0, 0, 0};
-        for (const OrientConsts& O : orient) m[0] += O.R[6], m[1] += O.R[7], m[2] += O.R[8];
-        const double mn = std::sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
-        S.cone = 0, S.cone_gate = 1, S.ax = 0.f, S.ay = 0.f, S.az = 1.f, S.cm = 1.f, S.sm = 0.f;
+        std::vector<float> axes;
         float r_body = 1.0e30f;
-        for (const OrientConsts& O : orient) r_body = std::fmin(r_body, O.radius_out);
-        S.all_lo = -110.f + 1.5f, S.all_hi = 250.f - 1.5f, S.all_rad = r_body - 1.5f;
-        if (mn > 1.0e-6 * orient.size() && S.all_rad > 0.f) {
-            double cmin = 1.0;
-            for (const OrientConsts& O : orient) {
-                const double n = std::sqrt((double)O.R[6] * O.R[6] + (double)O.R[7] * O.R[7] + (double)O.R[8] * O.R[8]);
-                cmin = std::fmin(cmin, (O.R[6] * m[0] + O.R[7] * m[1] + O.R[8] * m[2]) / (mn * n));
-            }
-            const double theta = std::acos(std::fmax(-1.0, std::fmin(1.0, cmin))) + 2.0e-3;
-#ifndef LRM_NO_CONE
-            if (theta < 1.2)  // beyond ~70 degrees the region is hardly more than the ball
-#else
-            if (false)
-#endif
-            {
-                S.cone = 1;
-                S.cone_gate = theta > 0.05 ? 1 : 0;
-                S.ax = (float)(m[0] / mn), S.ay = (float)(m[1] / mn), S.az = (float)(m[2] / mn);
-                S.cm = (float)std::cos(theta), S.sm = (float)std::sin(theta);
-            }
+        for (const OrientConsts& O : orient) {
+            axes.push_back(O.R[6]), axes.push_back(O.R[7]), axes.push_back(O.R[8]);
+            r_body = std::fmin(r_body, O.radius_out);
         }
+        make_axis_cone(axes.data(), (int)orient.size(), -110.f, 250.f, r_body, &S.cone);
+#ifdef LRM_NO_CONE
+        S.cone.ok = 0;
+#endif
     }
     S.standable = p.standable, S.next = d_next;
     S.stats = nullptr;

@@ -428,6 +428,37 @@ void emu_leg_ball(const float* xyz, size_t n, const lrm_leg_t* leg, const float*
         out[i] = lrm::leg_ball_possible(L, lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]), rc, wedge) ? 1 : 0;
 }
 
+// The pose search's orientation-independent collision region (leg_math.cuh: AxisCone): claimed[i] = the
+// region contains offset i; truth[i] = the offset is inside the body cylinder (radius `radius`, heights
+// in (-110, 250), several_leg.cu:504-559) under EVERY one of the nq orientations, evaluated the way
+// positionability.cu does it (matrix from the rotated basis vectors, T = R d).  Returns cone.ok | gate << 1.
+int emu_cone_check(const float* quats, int nq, float radius, const float* offsets, size_t n, uint8_t* claimed,
+                   uint8_t* truth) {
+    std::vector<float> R((size_t)nq * 9), axes((size_t)nq * 3);
+    const float ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0}, ez[3] = {0, 0, 1};
+    for (int o = 0; o < nq; o++) {
+        float c0[3], c1[3], c2[3];
+        lrm::quat_rotate(quats + 4 * o, ex, c0), lrm::quat_rotate(quats + 4 * o, ey, c1), lrm::quat_rotate(quats + 4 * o, ez, c2);
+        for (int r = 0; r < 3; r++) R[9 * o + 3 * r] = c0[r], R[9 * o + 3 * r + 1] = c1[r], R[9 * o + 3 * r + 2] = c2[r];
+        axes[3 * o] = R[9 * o + 6], axes[3 * o + 1] = R[9 * o + 7], axes[3 * o + 2] = R[9 * o + 8];
+    }
+    lrm::AxisCone C;
+    lrm::make_axis_cone(axes.data(), nq, -110.f, 250.f, radius, &C);
+    for (size_t i = 0; i < n; i++) {
+        const float dx = offsets[3 * i], dy = offsets[3 * i + 1], dz = offsets[3 * i + 2];
+        claimed[i] = (C.ok && lrm::cone_collides_always(C, dx, dy, dz)) ? 1 : 0;
+        bool all = true;
+        for (int o = 0; o < nq && all; o++) {
+            const float* M = &R[9 * o];
+            const float tx = fmaf(M[0], dx, fmaf(M[1], dy, M[2] * dz)), ty = fmaf(M[3], dx, fmaf(M[4], dy, M[5] * dz)),
+                        tz = fmaf(M[6], dx, fmaf(M[7], dy, M[8] * dz));
+            all = fmaf(tx, tx, ty * ty) < radius * radius && tz < 250.f && tz > -110.f;
+        }
+        truth[i] = all ? 1 : 0;
+    }
+    return C.ok | (C.gate << 1);
+}
+
 int emu_plan_is_generic(const lrm_leg_t* leg, const float* quat) {
     lrm::LegPlan L;
     lrm::build_leg_plan(*leg, quat, &L);

@@ -340,3 +340,31 @@ def test_host_plan_bytes_match_the_golden_file(emu):
         emu.emu_plan_bytes(leg.ctypes.data, q.ctypes.data, plan.ctypes.data, tables.ctypes.data)
         assert np.array_equal(plan, gold["plan_" + k]), k
         assert np.array_equal(tables, gold["tables_" + k]), k
+
+
+def test_cone_collision_region_is_conservative(emu, port):
+    """positionability.cu settles a pose in one walk when some map point is inside the body cylinder
+    under EVERY orientation.  The region it tests (AxisCone: the cylinder axes of all orientations lie
+    within an angle of their mean) must never claim an offset that escapes the cylinder under one of
+    them — and should claim most of what the brute force finds, far more than the 109 mm ball did."""
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    emu.emu_cone_check.argtypes = [vp, ctypes.c_int, ctypes.c_float, vp, sz, vp, vp]
+    emu.emu_cone_check.restype = ctypes.c_int
+    rng = np.random.default_rng(5)
+    off = rng.uniform(-320, 320, (400_000, 3)).astype(np.float32)
+    level = np.stack([port.rpy_to_quat(0.0, 0.0, float(y)) for y in np.linspace(0, 2 * np.pi, 16, endpoint=False)])
+    wild = np.stack([port.rpy_to_quat(float(r), float(p), 0.3) for r in (-1.2, 0.0, 1.2) for p in (-1.2, 0.0, 1.2)])
+    cases = (("robot_full_struct", port.full_struct_orientations(), 181.0, 3, 0.6),
+             ("level yaws", level, 181.0, 1, 0.97), ("wide spread", wild, 181.0, 2, 0.0))
+    for name, quats, radius, want_state, want_share in cases:
+        q = np.ascontiguousarray(quats, np.float32)
+        claimed = np.zeros(len(off), np.uint8)
+        truth = np.zeros(len(off), np.uint8)
+        state = emu.emu_cone_check(q.ctypes.data, len(q), radius, off.ctypes.data, len(off), claimed.ctypes.data,
+                                   truth.ctypes.data)
+        assert state == want_state, (name, state)                # ok | gate << 1
+        assert not np.any(claimed & ~truth & 1), (name, int((claimed & ~truth & 1).sum()))
+        if want_share:
+            ball = (np.linalg.norm(off, axis=1) < 109.0) & (truth == 1)
+            assert claimed.sum() >= want_share * truth.sum(), (name, int(claimed.sum()), int(truth.sum()))
+            assert claimed.sum() > 1.5 * ball.sum(), (name, int(claimed.sum()), int(ball.sum()))
