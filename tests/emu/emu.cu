@@ -428,6 +428,46 @@ void emu_leg_ball(const float* xyz, size_t n, const lrm_leg_t* leg, const float*
         out[i] = lrm::leg_ball_possible(L, lrm::to_coxa_frame(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]), rc, wedge) ? 1 : 0;
 }
 
+// The certificate of the plane atlas, checked directly: plane_probe(P).safety is a radius within which
+// the outcome of the plane evaluation — valid bit, sector, winning candidate — cannot change.  For each
+// of the n centres (X, Y) with a positive safety, `samples` points at 0 .. 0.98 x safety (capped at
+// `cap` mm) in pseudo-random directions must evaluate to the same label, and plane_clamp itself must
+// pick the labelled winner there (its result equals plane_from_label's, bit for bit).  Returns the
+// number of violations; counts[0] = centres with safety > 0, counts[1] = samples checked,
+// counts[2] = centres certified only thanks to the corner-on-circle certificate.
+size_t emu_probe_ball_check(const float* centres, size_t n, const lrm_leg_t* leg, const float* quat, int samples,
+                            float cap, size_t* counts) {
+    lrm::LegPlan L;
+    lrm::build_leg_plan(*leg, quat, &L);
+    lrm::SectorTable tab;
+    host_table(L, &tab);
+    lrm::WinnerTable win;
+    lrm::fill_winner_table(L, &win, 0, 1);
+    size_t bad = 0;
+    counts[0] = counts[1] = counts[2] = 0;
+    uint32_t rng = 12345u;
+    auto next = [&]() { rng = rng * 1664525u + 1013904223u; return (float)(rng >> 8) * (1.0f / 16777216.0f); };
+    for (size_t i = 0; i < n; i++) {
+        const float X = centres[2 * i], Y = centres[2 * i + 1];
+        const lrm::PlaneProbe pr = lrm::plane_probe(L, tab, X, Y);
+        if (!(pr.safety > 0.05f) || (pr.label & 15) == lrm::kAtlasNone) continue;
+        counts[0]++;
+        const float rmax = fminf(pr.safety, cap) * 0.98f;
+        for (int k = 0; k < samples; k++) {
+            const float ang = 6.2831853f * next(), rad = rmax * sqrtf(next());
+            const float x = X + rad * cosf(ang), y = Y + rad * sinf(ang);
+            counts[1]++;
+            const lrm::PlaneProbe q = lrm::plane_probe(L, tab, x, y);
+            const lrm::PlaneResult a = lrm::plane_clamp<false>(L, tab, x, y);
+            const lrm::PlaneResult b = lrm::plane_from_label(win, (unsigned)pr.label, x, y);
+            if (q.label != pr.label || a.valid != b.valid || std::memcmp(&a.dx, &b.dx, 4) != 0 ||
+                std::memcmp(&a.dy, &b.dy, 4) != 0)
+                bad++;
+        }
+    }
+    return bad;
+}
+
 // The pose search's orientation-independent collision region (leg_math.cuh: AxisCone): claimed[i] = the
 // region contains offset i; truth[i] = the offset is inside the body cylinder (radius `radius`, heights
 // in (-110, 250), several_leg.cu:504-559) under EVERY one of the nq orientations, evaluated the way

@@ -368,3 +368,23 @@ def test_cone_collision_region_is_conservative(emu, port):
             ball = (np.linalg.norm(off, axis=1) < 109.0) & (truth == 1)
             assert claimed.sum() >= want_share * truth.sum(), (name, int(claimed.sum()), int(truth.sum()))
             assert claimed.sum() > 1.5 * ball.sum(), (name, int(claimed.sum()), int(ball.sum()))
+
+
+def test_plane_certificate_holds_inside_its_radius(emu, port):
+    """plane_probe's safety — what the plane atlas and the cube labels are certified with, including the
+    corner-on-circle certificate next to the arc ends — is a radius within which the plane evaluation
+    keeps its valid bit, sector and winner, and plane_clamp returns the labelled winner's projection bit
+    for bit: checked on random balls all over the femur plane, two legs, limits rotated by a body pitch."""
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    emu.emu_probe_ball_check.argtypes = [vp, sz, vp, vp, ctypes.c_int, ctypes.c_float, vp]
+    emu.emu_probe_ball_check.restype = sz
+    rng = np.random.default_rng(11)
+    centres = np.ascontiguousarray(rng.uniform([-420, -520], [520, 420], (60_000, 2)), np.float32)
+    for robot, az, q in ((1, 0.0, [1, 0, 0, 0]), (0, 0.7853982, port.quaternion_from_angle_index(0)),
+                         (1, 3.9269907, port.full_struct_orientations()[31])):
+        leg = port.get_leg(robot, az)
+        q = np.ascontiguousarray(q, np.float32)
+        counts = (ctypes.c_size_t * 3)()
+        bad = emu.emu_probe_ball_check(centres.ctypes.data, len(centres), leg.ctypes.data, q.ctypes.data, 12, 6.0, counts)
+        assert counts[0] > 0.9 * len(centres), (robot, az, list(counts))     # nearly every centre has a certificate
+        assert bad == 0, (robot, az, int(bad), list(counts))
