@@ -218,3 +218,36 @@ def test_options_are_validated(lrm):
     assert lrm.set_option("tier_chunk_shift", 3) == 3
     assert lrm.set_option("volume_cell_mm", 2.5) == 3.0 and lrm.set_option("volume_cell_mm", 3.0) == 2.5
     assert lrm.get_stat("volume_dim") == 512 and lrm.get_stat("table_builds") >= 0
+    assert lrm.set_option("volume_bricks", 1) == 0 and lrm.set_option("volume_bricks", 0) == 1   # off by default
+    assert lrm.get_stat("volume_builds") >= 0 and lrm.get_stat("volume_bricks") >= 0
+
+
+def test_register_budgets_of_the_hot_kernels(lrm):
+    """The sweeps are issue / latency bound at the occupancy their registers allow, and their L1 is
+    small (shared memory takes most of the SM's array): a few more spilled bytes cost 10 - 35 % (measured,
+    DESIGN.md §2).  The budgets the measurements were taken with, read from the built library:
+    tiered sweep 64 registers (4 CTAs of 256 threads per SM) and at most 64 B of stack (40 B of it the
+    by-value copy of its I/O pointers for the non-inlined redo functions), pose search 40 registers
+    (3 CTAs of 512 threads), no stack."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.environ.get("LRM_B200_LIB") or os.path.join(ROOT, "legged-robot-movability-cuda_b200", "liblrm_b200.so")
+    text = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout
+    usage = {}
+    name = None
+    for line in text.splitlines():
+        m = re.match(r"\s*Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        elif name and "REG:" in line:
+            usage[name] = (int(re.search(r"REG:(\d+)", line).group(1)), int(re.search(r"STACK:(\d+)", line).group(1)))
+            name = None
+    tier = {k: v for k, v in usage.items() if "one_leg_tier_kernel" in k}
+    posit = {k: v for k, v in usage.items() if "positionability_kernelILb0" in k}
+    assert tier and posit, list(usage)[:5]
+    for k, (reg, stack) in tier.items():
+        assert reg <= 64 and stack <= 64, (k, reg, stack)
+    for k, (reg, stack) in posit.items():
+        assert reg <= 42 and stack == 0, (k, reg, stack)
